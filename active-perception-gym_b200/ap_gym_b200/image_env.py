@@ -1,0 +1,428 @@
+"""Drop-in image vector environments backed by the fused sm_100a step kernel.
+
+Mirrors the reference's public surface for this path:
+  ImagePerceptionConfig            ap_gym/envs/image/image_perception_module.py:20-34
+  ImageClassificationVectorEnv     ap_gym/envs/image_classification.py:22-168
+  ImageLocalizationVectorEnv       ap_gym/envs/image_localization.py:24-254
+  ActivePerceptionVectorEnv.step   ap_gym/active_perception_vector_env.py:84-111
+
+`step({"action": (N,2) f32, "prediction": (N,K)|(N,2) f32})` accepts CUDA torch tensors (zero-copy, fully
+asynchronous, returns DLPack views of engine-owned device buffers that stay valid until the next step) or
+numpy arrays (copied through the C-ABI host call; numpy comes back).  Everything between the two calls is one
+kernel launch; there is no CPU implementation behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Literal, Sequence
+
+import numpy as np
+
+from . import _capi
+from .datasets import ImageBank, bank_from_dataset
+from .loss_fn import CrossEntropyLossFn, make_mse_loss_fn_and_target_space
+from .reset_stream import ImageResetStream
+from .spaces import (NEXT_STEP, ActivePerceptionActionSpace, Box, Dict, Discrete, ImageSpace, LogitSpace,
+                     MultiDiscrete, batch_box)
+
+
+@dataclass(frozen=True)
+class ImagePerceptionConfig:
+    """Same fields and defaults as the reference dataclass (image_perception_module.py:20-34)."""
+
+    dataset: Any
+    sensor_size: tuple[int, int] = (5, 5)
+    sensor_scale: float = 1.0
+    max_step_length: float | Sequence[float] = 0.2
+    step_limit: int = 16
+    display_visitation: bool = True
+    render_unvisited_opacity: float = 0.0
+    render_visited_opacity: float = 0.3
+    prefetch_buffer_size: int = 128
+    prefetch: bool = True
+    unique_sampling_max_grid_cell_size_rel = 0.2
+    unique_sampling_top_k: int = 10
+    randomly_invert_labels: bool = False
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _void(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _ImageVectorEnvBase:
+    metadata: dict[str, Any] = {"render_modes": ["rgb_array"], "render_fps": 2, "autoreset_mode": NEXT_STEP}
+    _TASK = _capi.TASK_CLASSIFICATION
+
+    def __init__(self, num_envs: int, image_perception_config: ImagePerceptionConfig,
+                 render_mode: Literal["rgb_array"] = "rgb_array", *, device: int = 0,
+                 env_offset: int = 0, global_num_envs: int | None = None, track_visited: bool = True,
+                 check_errors: Literal["step", "lazy", "never"] = "lazy",
+                 output: Literal["torch", "numpy"] = "torch", payload_ring: int = 4):
+        if render_mode not in self.metadata["render_modes"]:
+            raise ValueError(f"Unsupported render mode: {render_mode}")
+        cfg = image_perception_config
+        self._config = cfg
+        self._render_mode = render_mode
+        self.num_envs = int(num_envs)
+        self._device = int(device)
+        self._global_n = int(global_num_envs) if global_num_envs is not None else self.num_envs
+        self._slice = slice(int(env_offset), int(env_offset) + self.num_envs)
+        if self._slice.stop > self._global_n:
+            raise ValueError("env_offset + num_envs exceeds global_num_envs")
+        self._check_errors = check_errors
+        self._numpy_mode = output == "numpy"
+        self._steps_since_poll = 0
+        self._lib = _capi.lib()
+
+        bank: ImageBank = bank_from_dataset(cfg.dataset)
+        self._bank = bank
+        M, H, W, Cn = bank.images.shape
+        self._H, self._W, self._C = H, W, Cn
+        self._K = int(bank.num_classes)
+        S0, S1 = (int(s) for s in cfg.sensor_size)
+        self._S0, self._S1 = S0, S1
+        msl = np.ones(2) * np.array(cfg.max_step_length)
+        if msl.shape != (2,):
+            raise ValueError("max_step_length must be a scalar or a pair")
+        eff = np.array(cfg.sensor_size) * cfg.sensor_scale
+        if np.any(np.array([H, W]) < eff):
+            raise ValueError(
+                f"Image size {(H, W)} cannot be smaller than effective sensor size {tuple(eff)}.")
+
+        ccfg = _capi.ImageCfg(
+            device=self._device, num_envs=self.num_envs, task=self._TASK, height=H, width=W, channels=Cn,
+            sensor_h=S0, sensor_w=S1, sensor_scale=float(cfg.sensor_scale),
+            max_step_length=(C.c_double * 2)(float(msl[0]), float(msl[1])), step_limit=int(cfg.step_limit),
+            num_classes=self._K, bank_dtype=_capi.BANK_U8 if bank.is_u8 else _capi.BANK_F32,
+            randomly_invert_labels=int(cfg.randomly_invert_labels), track_visited=int(track_visited),
+            payload_ring=int(payload_ring))
+        self._ring = max(1, min(int(payload_ring) if payload_ring > 0 else _capi.PAYLOAD_RING_DEFAULT,
+                                _capi.PAYLOAD_RING_MAX))
+        h = C.c_void_p()
+        _capi.check(self._lib.apg_image_create(C.byref(ccfg), C.byref(h)))
+        self._h = h
+        _capi.check(self._lib.apg_image_set_bank(self._h, _void(bank.images), _void(bank.labels), M, 0))
+        self._track = bool(track_visited)
+        self._stream: ImageResetStream | None = None
+        self._views = self._make_views()
+        self._build_spaces()
+        self._closed = False
+        self.spec = None
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _buffers(self) -> _capi.ImageBuffers:
+        b = _capi.ImageBuffers()
+        _capi.check(self._lib.apg_image_get_buffers(self._h, C.byref(b)))
+        return b
+
+    def _make_views(self):
+        b = self._buffers()
+        N, S0, S1, Cn, T = self.num_envs, self._S0, self._S1, self._C, int(self._config.step_limit)
+        dev = self._device
+        t = _capi.dlpack_tensor
+        v = {
+            "glimpse": t(b.d_glimpse, dev, "float", 32, (N, S0, S1, Cn)),
+            "glimpse_pos": t(b.d_glimpse_pos, dev, "float", 32, (N, 2)),
+            "time_step": t(b.d_time_step, dev, "float", 32, (N,)),
+            "reward": t(b.d_reward, dev, "float", 32, (N,)),
+            "base_reward": t(b.d_base_reward, dev, "float", 32, (N,)),
+            "loss": t(b.d_loss, dev, "float", 32, (N,)),
+            "terminated": t(b.d_terminated, dev, "bool", 8, (N,)),
+            "truncated": t(b.d_truncated, dev, "bool", 8, (N,)),
+            "index": t(b.d_index, dev, "int", 64, (N,)),
+            "pos": t(b.d_pos, dev, "float", 64, (N, 2)),
+        }
+        if b.d_target_glimpse:
+            v["target_glimpse"] = t(b.d_target_glimpse, dev, "float", 32, (N, S0, S1, Cn))
+            v["target_xy"] = t(b.d_target_xy, dev, "float", 32, (N, 2))
+            v["cur_target_xy"] = t(b.d_cur_target_xy, dev, "float", 32, (N, 2))
+        if b.d_target_label:
+            v["target_label"] = t(b.d_target_label, dev, "int", 32, (N,))
+        if b.d_inverted_label:
+            v["inverted_label"] = t(b.d_inverted_label, dev, "int", 32, (N,))
+        if b.d_visited:
+            v["visited"] = t(b.d_visited, dev, "int", 32, (N, self._H, (self._W + 31) // 32))
+            v["stamp_xy"] = t(b.d_stamp_xy, dev, "int", 32, (T, 2, N))
+            v["stamp_q"] = t(b.d_stamp_q, dev, "float", 32, (T, N))
+        return v
+
+    def _build_spaces(self):
+        S0, S1, Cn, N = self._S0, self._S1, self._C, self.num_envs
+        obs = {
+            "glimpse": ImageSpace(S1, S0, Cn, dtype=np.float32),
+            "glimpse_pos": Box(-1, 1, (2,), np.float32),
+            "time_step": Box(-1, 1, (), np.float32),
+        }
+        if self._config.randomly_invert_labels:
+            obs["inverted_label"] = Discrete(3)
+        if self._TASK == _capi.TASK_LOCALIZATION:
+            obs["target_glimpse"] = ImageSpace(S1, S0, Cn, dtype=np.float32)
+        self.single_observation_space = Dict(obs)
+        batched = {}
+        for k, s in obs.items():
+            if isinstance(s, ImageSpace):
+                batched[k] = batch_box(s, N, ImageSpace)
+            elif isinstance(s, Discrete):
+                batched[k] = MultiDiscrete(np.full((N,), s.n))
+            else:
+                batched[k] = batch_box(s, N)
+        self.observation_space = Dict(batched)
+        inner = Box(-np.ones(2, dtype=np.float32), np.ones(2, dtype=np.float32))
+        if self._TASK == _capi.TASK_CLASSIFICATION:
+            pred = LogitSpace(-np.inf, np.inf, shape=(self._K,))
+            self.single_prediction_target_space = Discrete(self._K)
+            self.prediction_target_space = MultiDiscrete([self._K] * N)
+            self.loss_fn = CrossEntropyLossFn(num_classes=self._K).normalized
+            batched_pred = batch_box(pred, N, LogitSpace)
+        else:
+            pred = Box(low=-1, high=1, shape=(2,))
+            self.loss_fn, self.single_prediction_target_space = make_mse_loss_fn_and_target_space(2, -1, 1)
+            self.prediction_target_space = batch_box(self.single_prediction_target_space, N)
+            batched_pred = batch_box(pred, N)
+        self.single_action_space = ActivePerceptionActionSpace(inner, pred)
+        self.action_space = ActivePerceptionActionSpace(batch_box(inner, N), batched_pred)
+
+    # the reference's derived properties (active_perception_vector_env.py:52-66)
+    prediction_space = property(lambda self: self.action_space["prediction"])
+    inner_action_space = property(lambda self: self.action_space["action"])
+    single_prediction_space = property(lambda self: self.single_action_space["prediction"])
+    single_inner_action_space = property(lambda self: self.single_action_space["action"])
+    render_mode = property(lambda self: self._render_mode)
+    config = property(lambda self: self._config)
+    unwrapped = property(lambda self: self)
+
+    @property
+    def np_random(self):
+        if self._stream is None:
+            self._seed(None)
+        return self._stream.g0
+
+    def _seed(self, seed):
+        self._stream = ImageResetStream(seed, self._global_n, len(self._bank), self._slice)
+
+    # ------------------------------------------------------------------------------------------ errors
+    def _poll(self):
+        flags = C.c_uint32(0)
+        _capi.check(self._lib.apg_image_poll_error(self._h, C.byref(flags), 1))
+        self._steps_since_poll = 0
+        f = flags.value
+        if f & _capi.FLAG_NAN_PRED:
+            raise ValueError("NaN values detected in prediction.")
+        if f & _capi.FLAG_NAN_ACTION:
+            raise ValueError("NaN values detected in action.")
+        if f & _capi.FLAG_OUT_OF_GRID:
+            raise ValueError("One of the requested xi is out of bounds")
+
+    def _maybe_poll(self, host_mode: bool):
+        self._steps_since_poll += 1
+        if self._check_errors == "never":
+            return
+        if self._check_errors == "step" or host_mode or self._steps_since_poll >= 256:
+            self._poll()
+
+    # ------------------------------------------------------------------------------------------ reset
+    def _explicit_targets(self, options, idx, pos) -> np.ndarray | None:
+        return None
+
+    def _autoreset_targets(self) -> np.ndarray | None:
+        return None
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        if seed is not None or self._stream is None:
+            self._seed(seed)
+        idx, inv, pos = self._stream.draw_episode(bool(self._config.randomly_invert_labels))
+        target = self._explicit_targets(options, idx, pos)
+        _capi.check(self._lib.apg_image_reset(self._h, _void(idx), _void(pos), _void(target), _void(inv)))
+        as_numpy = bool(options and options.get("numpy", False)) or self._numpy_mode
+        return self._obs(as_numpy), {"index": self._out("index", as_numpy)}
+
+    def queue_autoreset_payloads(self, count: int = 1):
+        """Draw and upload the payloads of the next `count` autoresets ahead of time (rollouts / graphs).
+        The draws follow the reference's stream order, assuming no explicit reset() happens in between."""
+        for _ in range(count):
+            target = self._autoreset_targets()  # env-level Generator first (image_localization.py:153-156)
+            idx, inv, pos = self._stream.draw_episode(bool(self._config.randomly_invert_labels))
+            _capi.check(self._lib.apg_image_queue_reset_payload(self._h, _void(idx), _void(pos), _void(target),
+                                                               _void(inv)))
+
+    # ------------------------------------------------------------------------------------------ step
+    def _out(self, name: str, as_numpy: bool):
+        v = self._views[name]
+        return v.cpu().numpy() if as_numpy else v
+
+    def _obs(self, as_numpy: bool):
+        keys = ["glimpse", "glimpse_pos", "time_step"]
+        if self._config.randomly_invert_labels:
+            keys.append("inverted_label")
+        if self._TASK == _capi.TASK_LOCALIZATION:
+            keys.append("target_glimpse")
+        return {k: self._out(k, as_numpy) for k in keys}
+
+    def step(self, action):
+        a, p = action["action"], action["prediction"]
+        b = self._buffers()
+        if b.needs_reset and self._lib.apg_image_pending_payloads(self._h) == 0:
+            self.queue_autoreset_payloads(1)
+        host_mode = not _is_torch(a)
+        if host_mode:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            p = np.ascontiguousarray(p, dtype=np.float32)
+            if a.shape != (self.num_envs, 2) or p.shape[0] != self.num_envs:
+                raise ValueError(f"bad action/prediction shapes {a.shape} {p.shape}")
+            N = self.num_envs
+            reward = np.empty(N, np.float32)
+            term = np.empty(N, np.bool_)
+            trunc = np.empty(N, np.bool_)
+            glimpse = np.empty((N, self._S0, self._S1, self._C), np.float32)
+            _capi.check(self._lib.apg_image_step_host(self._h, _void(a), _void(p), _void(reward), _void(term),
+                                                      _void(trunc), _void(glimpse)))
+            self._maybe_poll(True)
+            obs = self._obs(True)
+            obs["glimpse"] = glimpse
+            terminated, truncated = term, trunc
+        else:
+            if not (a.is_cuda and p.is_cuda and a.is_contiguous() and p.is_contiguous()
+                    and a.dtype == p.dtype and str(a.dtype) == "torch.float32"):
+                raise ValueError("torch inputs must be contiguous float32 CUDA tensors")
+            if tuple(a.shape) != (self.num_envs, 2) or p.shape[0] != self.num_envs:
+                raise ValueError(f"bad action/prediction shapes {tuple(a.shape)} {tuple(p.shape)}")
+            _capi.check(self._lib.apg_image_step(self._h, a.data_ptr(), p.data_ptr()))
+            self._maybe_poll(False)
+            obs = self._obs(False)
+            reward = self._views["reward"]
+            terminated, truncated = self._views["terminated"], self._views["truncated"]
+        info = {
+            "index": self._out("index", host_mode),
+            "base_reward": self._out("base_reward", host_mode),
+            "prediction": {"target": self._out(self._TARGET_VIEW, host_mode), "loss": self._out("loss", host_mode)},
+        }
+        return obs, reward, terminated, truncated, info
+
+    def rollout(self, actions, predictions, rewards=None, dones=None):
+        """`n_steps` consecutive steps from stacked CUDA tensors (n_steps, N, 2) / (n_steps, N, K|2); per-step
+        rewards (f32) / dones (bool) land in the optional (n_steps, N) tensors.  Asynchronous."""
+        n_steps = int(actions.shape[0])
+        T = int(self._config.step_limit)
+        b = self._buffers()
+        t, need, resets = b.elapsed, bool(b.needs_reset), 0
+        for _ in range(n_steps):
+            if need:
+                resets, t, need = resets + 1, 0, False
+            else:
+                t += 1
+                need = t >= T
+        missing = resets - self._lib.apg_image_pending_payloads(self._h)
+        if resets > self._ring:
+            raise ValueError(f"a rollout may span at most payload_ring={self._ring} autoresets")
+        if missing > 0:
+            self.queue_autoreset_payloads(missing)
+        _capi.check(self._lib.apg_image_rollout(
+            self._h, actions.data_ptr(), predictions.data_ptr(), n_steps,
+            None if rewards is None else rewards.data_ptr(), None if dones is None else dones.data_ptr()))
+
+    # ------------------------------------------------------------------------------------------ state access
+    def sync(self):
+        _capi.check(self._lib.apg_image_sync(self._h))
+
+    def state(self) -> dict[str, Any]:
+        """Device views of the engine state (float64 positions, visited bitmask, overlay stamp log)."""
+        b = self._buffers()
+        out = {"pos": self._views["pos"], "elapsed": b.elapsed, "needs_reset": bool(b.needs_reset),
+               "stamp_count": b.stamp_count}
+        for k in ("visited", "stamp_xy", "stamp_q", "cur_target_xy"):
+            if k in self._views:
+                out[k] = self._views[k]
+        return out
+
+    def overlay_maps(self, envs: Sequence[int] | None = None):
+        """Rebuilds the reference's render-resolution overlay (`visitation_counts` int32, `prediction_quality_map`
+        float32; image_perception_module.py:219-234) of the current episode from the on-device stamp log."""
+        st = self.state()
+        envs = np.arange(self.num_envs) if envs is None else np.asarray(envs)
+        H, W = self._H, self._W
+        Wr = max(128, self._S1)
+        rs = Wr / W
+        Hr = int(round(rs * H))
+        size = np.round(np.flip(np.array(self._config.sensor_size) * self._config.sensor_scale * rs)).astype(np.int32)
+        counts = np.zeros((len(envs), Hr, Wr), np.int32)
+        quality = np.zeros((len(envs), Hr, Wr), np.float32)
+        n_st = st["stamp_count"]
+        if n_st == 0:
+            return counts, quality
+        xy = st["stamp_xy"][:n_st].cpu().numpy()[:, :, envs]
+        q = st["stamp_q"][:n_st].cpu().numpy()[:, envs]
+        rows = np.arange(len(envs))[:, None, None]
+        for s in range(n_st):
+            xr = xy[s, 0][:, None] + np.arange(size[0]) - size[0] // 2
+            yr = xy[s, 1][:, None] + np.arange(size[1]) - size[1] // 2
+            coords = (rows, np.clip(yr, 0, Hr - 1)[:, :, None], np.clip(xr, 0, Wr - 1)[:, None, :])
+            counts[coords] += 1
+            quality[coords] = q[s][:, None, None]
+        return counts, quality
+
+    def render(self):
+        raise NotImplementedError("render() is host-side tooling outside the hot path (DESIGN.md, out of scope)")
+
+    def close(self):
+        if not getattr(self, "_closed", True):
+            self._closed = True
+            self._views = {}
+            self._lib.apg_image_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class ImageClassificationVectorEnv(_ImageVectorEnvBase):
+    """ap_gym.envs.image_classification.ImageClassificationVectorEnv on the B200 engine."""
+
+    _TASK = _capi.TASK_CLASSIFICATION
+    _TARGET_VIEW = "target_label"
+
+    def _explicit_targets(self, options, idx, pos):
+        return None
+
+
+class ImageLocalizationVectorEnv(_ImageVectorEnvBase):
+    """ap_gym.envs.image_localization.ImageLocalizationVectorEnv on the B200 engine.
+
+    Explicit `reset()` targets: the reference runs `sample_unique_glimpse_positions` (O(N * 729^2 * S^2 C),
+    9.9 s for N=8 on the CPU).  Pass `options={"prediction_target": (N,2) float32}` to supply them, or leave
+    the default `target_sampling="uniform"` which draws U(-1,1) like the reference's own autoreset does
+    (documented deviation); the module Generator is advanced exactly as the reference would."""
+
+    _TASK = _capi.TASK_LOCALIZATION
+    _TARGET_VIEW = "target_xy"
+
+    def __init__(self, *args, target_sampling: Literal["uniform"] = "uniform", **kwargs):
+        super().__init__(*args, **kwargs)
+        if target_sampling != "uniform":
+            raise ValueError("target_sampling must be 'uniform' (or pass options['prediction_target'])")
+
+    def _explicit_targets(self, options, idx, pos):
+        cfg = self._config
+        eff = np.array(cfg.sensor_size) * cfg.sensor_scale
+        lim = (np.array([self._W, self._H]) - 1) / 2 - (eff - 1) / 2
+        max_cell = eff / lim * cfg.unique_sampling_max_grid_cell_size_rel
+        sel, jitter = self._stream.draw_unique_selection(cfg.unique_sampling_top_k, max_cell)
+        if options and options.get("prediction_target") is not None:
+            t = np.ascontiguousarray(options["prediction_target"], dtype=np.float32)
+            if t.shape != (self.num_envs, 2):
+                raise ValueError("options['prediction_target'] must have shape (num_envs, 2)")
+            return t
+        # uniform stand-in built from the same two draws: grid cell (sel/top_k spreads over [-1,1]) is not
+        # available without the uniqueness search, so use the jitter draw rescaled to the full range
+        u = jitter / max_cell  # U(-1, 1)
+        return np.ascontiguousarray(np.clip(u, -1, 1).astype(np.float32))
+
+    def _autoreset_targets(self):
+        return self._stream.draw_autoreset_targets()

@@ -1,0 +1,367 @@
+"""bench.py -- env-steps/s of the B200 stepping engine on the BASELINE.json configurations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mnist|tinyloc|lidar_rooms|lidar_maze]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...     # the CPU restatement of the reference path on the host cores
+
+A "step" is one vector step: every environment of the batch advances once through the fused kernel
+(position update, resample, loss, reward, flags, autoreset).  `value` = env-steps/s with all inputs resident
+in HBM (device-timed, max over ranks); `e2e` = the same through the host-buffer C-ABI call with the
+host<->device copies inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "active-perception-gym_b200"))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per env-step (DESIGN.md "Roofline"; SURVEY.md section 8d with the uint8 bank)
+WORKLOADS = {
+    # name: (description, per-GPU envs, bytes per env-step)
+    "mnist": dict(desc="MNIST-v0 shape: synthetic 60000x28x28x1 u8 bank, ImageClassificationVectorEnv, K=10, S=5, T=16",
+                  n_envs=65536, bytes_per_step=300),
+    "tinyloc": dict(desc="TinyImageNetLoc-v0 shape: synthetic 100000x64x64x3 u8 bank, ImageLocalizationVectorEnv, S=10, T=16",
+                    n_envs=131072, bytes_per_step=1930),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=340)
+    ap.add_argument("--warmup", type=int, default=34)
+    ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=0, help="override per-GPU num_envs")
+    ap.add_argument("--bank", type=int, default=0, help="override bank length")
+    ap.add_argument("--e2e-steps", type=int, default=68)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU side
+def cpu_oracle_run(workload: str, n_envs: int, steps: int, seed: int = 0):
+    """One process of the CPU restatement (oracle/) on a bounded sample; returns env-steps/s."""
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+
+    if workload == "mnist":
+        imgs, labels = synthetic_u8_bank(seed=0, M=4096, H=28, W=28, C=1, K=10)
+        env = ImageEnvOracle(imgs, labels, n_envs, task="cls", num_classes=10, track_overlay=False)
+        pw = 10
+    elif workload == "tinyloc":
+        imgs, labels = synthetic_u8_bank(seed=0, M=512, H=64, W=64, C=3, K=200)
+        env = ImageEnvOracle(imgs, labels, n_envs, task="loc", num_classes=200, sensor_size=(10, 10), track_overlay=False)
+        pw = 2
+    else:
+        raise ValueError(workload)
+    rng = np.random.default_rng(seed)
+    if env.task == "loc":
+        env.reset(seed=seed, explicit_targets=rng.uniform(-1, 1, (n_envs, 2)).astype(np.float32))
+    else:
+        env.reset(seed=seed)
+    a = rng.uniform(-1, 1, (steps, n_envs, 2)).astype(np.float32)
+    p = rng.standard_normal((steps, n_envs, pw)).astype(np.float32)
+    for s in range(3):
+        env.step(a[s], p[s])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        env.step(a[s], p[s])
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def _cpu_worker(args):
+    return cpu_oracle_run(*args)
+
+
+def cpu_baseline(workload: str, procs: int, n_envs: int, steps: int):
+    if procs <= 1:
+        v, dt = cpu_oracle_run(workload, n_envs, steps)
+        return v, dt
+    import multiprocessing as mp
+
+    with mp.get_context("spawn").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(workload, n_envs, steps, i) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    n_envs = 4096 if args.workload == "mnist" else 256
+    steps_per = 17
+    vals = []
+    for _ in range(max(1, args.warmup // 17)):
+        cpu_baseline(args.workload, procs, n_envs, 4)
+    t0 = time.perf_counter()
+    reps = max(1, min(args.steps // 17, 6))
+    for _ in range(reps):
+        v, _ = cpu_baseline(args.workload, procs, n_envs, steps_per)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = float(np.median(vals))
+    sample = f"{procs} processes x {n_envs} envs x {steps_per} steps of the numpy restatement (oracle/), median of {reps}"
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs * procs / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "num_envs_per_gpu": w["n_envs"]},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU side
+def build_env(args, rank, world, device):
+    import ap_gym_b200 as apg
+
+    w = WORKLOADS[args.workload]
+    n = args.envs or w["n_envs"]
+    if args.workload == "mnist":
+        ds = apg.SyntheticImageDataset("mnist", length=args.bank or None, seed=0)
+        cfg = apg.ImagePerceptionConfig(dataset=ds)
+        env = apg.ImageClassificationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
+                                               check_errors="never", payload_ring=64)
+        pw = 10
+    else:
+        ds = apg.SyntheticImageDataset("tinyimagenet", length=args.bank or None, seed=0)
+        cfg = apg.ImagePerceptionConfig(dataset=ds, sensor_size=(10, 10))
+        env = apg.ImageLocalizationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
+                                             check_errors="never", payload_ring=64)
+        pw = 2
+    return env, n, pw
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ap_gym_b200 import _capi
+
+    w = WORKLOADS[args.workload]
+    env, n, pw = build_env(args, rank, world, local_rank)
+    T = 16
+    K, W = args.steps, args.warmup
+    dev = torch.device("cuda", local_rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # distinct inputs for every step: streamed from HBM, total larger than L2
+    chunk = 17 * 3  # steps per rollout call (3 episodes)
+    tot = K + W
+    acts = torch.rand((tot, n, 2), generator=gen, device=dev) * 2 - 1
+    if pw == 2:
+        preds = torch.rand((tot, n, 2), generator=gen, device=dev) * 2 - 1
+    else:
+        preds = torch.randn((tot, n, pw), generator=gen, device=dev)
+    env.reset(seed=0)
+
+    def run(s0, s1):
+        s = s0
+        while s < s1:
+            e = min(s + chunk, s1)
+            env.rollout(acts[s:e], preds[s:e])
+            s = e
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pre-draw the autoreset payloads of warm-up + timed region so the timed region is device-only
+    run(0, W)
+    barrier()
+    # queue as many payloads as the timed region needs (ring depth 64 >= K/17 + 1 for the default K)
+    b = env._buffers()
+    t_, need, resets = b.elapsed, bool(b.needs_reset), 0
+    for _ in range(K):
+        if need:
+            resets, t_, need = resets + 1, 0, False
+        else:
+            t_ += 1
+            need = t_ >= T
+    pre = min(resets, 64) - env._lib.apg_image_pending_payloads(env._h)
+    if pre > 0:
+        env.queue_autoreset_payloads(pre)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.lib().apg_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    run(W, W + K)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _capi.lib().apg_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * n * K / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
+    Ke = args.e2e_steps
+    h_a = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    h_p = torch.empty((n, pw), dtype=torch.float32).pin_memory()
+    h_r = torch.empty((n,), dtype=torch.float32).pin_memory()
+    h_te = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    h_tr = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    h_a.copy_(acts[0].cpu())
+    h_p.copy_(preds[0].cpu())
+    lib = _capi.lib()
+
+    def e2e_step():
+        if env._buffers().needs_reset and lib.apg_image_pending_payloads(env._h) == 0:
+            env.queue_autoreset_payloads(1)
+        _capi.check(lib.apg_image_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
+                                            h_tr.data_ptr(), None))
+
+    for _ in range(5):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / float(t_e.item())
+    h2d = n * (2 + pw) * 4
+    d2h = n * (4 + 1 + 1)
+
+    # ---- final NCCL reduce of run statistics (the only collective of the data path)
+    stats = torch.stack([env._views["reward"].double().sum(), env._views["loss"].double().sum(),
+                         torch.tensor(float(n), device=dev, dtype=torch.float64)])
+    if world > 1:
+        dist.all_reduce(stats)
+    env.sync()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_per_launch = w["bytes_per_step"] * n
+        avg_launch_s = (ms_max * 1e-3) / K
+        achieved = bytes_per_launch / avg_launch_s / 1e9
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}",
+                       "l2": "per-step inputs are distinct and streamed from HBM (%.0f MB total > 126 MB L2); engine-owned obs buffers are rewritten every step" % (acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "api": "apg_image_step_host (pinned host action/prediction in, reward/terminated/truncated out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "kernel": "image_step_kernel", "bytes_per_env_step": w["bytes_per_step"],
+                         "avg_launch_us": avg_launch_s * 1e6},
+            "final_stats_allreduce": {"mean_reward_last_step": float(stats[0] / stats[2]), "mean_loss_last_step": float(stats[1] / stats[2])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            n_cpu = 4096 if args.workload == "mnist" else 256
+            v, dt = cpu_oracle_run(args.workload, n_cpu, 34)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                    "sample": f"numpy restatement (oracle/image_oracle.py), 1 process, N={n_cpu} x 34 steps, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

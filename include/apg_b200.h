@@ -1,0 +1,160 @@
+/*
+ * apg_b200.h -- C-ABI of the B200-native batched stepping engine for ap_gym (active-perception-gym 0.5.0).
+ *
+ * This is the drop-in boundary for the reference's vector-env hot path.  The reference is pure Python
+ * (no FFI of its own), so every entry point names the Python interface it replaces; the ctypes binding a
+ * maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; pointers named d_* are DEVICE pointers, h_* are HOST pointers;
+ *   - every function returns 0 (APG_OK) or a negative apg_status; apg_last_error() gives the text;
+ *   - all work is queued on the handle's CUDA stream (default: the legacy default stream, which is also
+ *     PyTorch's default) and is asynchronous unless the function name ends in _host or says it syncs;
+ *   - a handle is not thread-safe (the reference env is single-threaded too).
+ *   - there is NO CPU fallback: every entry point fails with APG_ERR_CUDA when no device is usable.
+ */
+#ifndef APG_B200_H
+#define APG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APG_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  APG_OK = 0,
+  APG_ERR_INVALID = -1,      /* bad argument / configuration (reference: ValueError at construction) */
+  APG_ERR_CUDA = -2,         /* CUDA runtime failure, or no device */
+  APG_ERR_STATE = -3,        /* call order violated, e.g. step before reset */
+  APG_ERR_NEED_PAYLOAD = -4, /* an autoreset step is due but no reset payload has been queued */
+  APG_ERR_NAN_ACTION = -5,   /* reference: ValueError("NaN values detected in action.")     image_perception_module.py:204-205, lidar_localization2d.py:318-319 */
+  APG_ERR_NAN_PRED = -6,     /* reference: ValueError("NaN values detected in prediction.") image_perception_module.py:194-195, lidar_localization2d.py:320-321 */
+  APG_ERR_OUT_OF_GRID = -7   /* reference: scipy RegularGridInterpolator ValueError (bounds_error=True) */
+} apg_status;
+
+/* sticky device-side error bits, see apg_*_poll_error */
+#define APG_FLAG_NAN_ACTION 1u
+#define APG_FLAG_NAN_PRED 2u
+#define APG_FLAG_OUT_OF_GRID 4u
+
+int apg_version(void);
+const char* apg_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+int64_t apg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Image environments.  Replaces, for one shard of `num_envs` environments:
+ *   ImagePerceptionModule.{reset,step,get_glimpse}   ap_gym/envs/image/image_perception_module.py:120-331
+ *   ImageClassificationVectorEnv._step               ap_gym/envs/image_classification.py:113-127
+ *   ImageLocalizationVectorEnv._step                 ap_gym/envs/image_localization.py:151-181
+ *   ActivePerceptionVectorEnv.step (loss + reward)   ap_gym/active_perception_vector_env.py:84-111
+ *   CrossEntropyLossFn/MSELossFn(.normalized).numpy  ap_gym/loss_fn.py:100-110,212-220,261-267
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct apg_image_env apg_image_env;
+
+#define APG_TASK_CLASSIFICATION 0
+#define APG_TASK_LOCALIZATION 1
+#define APG_BANK_U8 0  /* pixels stored as uint8, converted in-kernel with the reference's f32(u8)/255 */
+#define APG_BANK_F32 1 /* pixels stored as float32 in [0,1] */
+
+typedef struct {
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t num_envs;               /* N of this shard */
+  int32_t task;                   /* APG_TASK_* */
+  int32_t height, width, channels;/* image bank geometry (H, W, C), C in {1, 3} */
+  int32_t sensor_h, sensor_w;     /* ImagePerceptionConfig.sensor_size (S0, S1) */
+  double sensor_scale;            /* ImagePerceptionConfig.sensor_scale */
+  double max_step_length[2];      /* ImagePerceptionConfig.max_step_length broadcast to (x, y) */
+  int32_t step_limit;             /* ImagePerceptionConfig.step_limit (T) */
+  int32_t num_classes;            /* K: dataset.num_classes (classification logits width) */
+  int32_t bank_dtype;             /* APG_BANK_* */
+  int32_t randomly_invert_labels; /* ImagePerceptionConfig.randomly_invert_labels */
+  int32_t track_visited;          /* keep the visited bitmask + overlay stamp log (reference: always on) */
+  int32_t payload_ring;           /* how many future autoreset payloads may be queued (0 -> 4, max 64) */
+} apg_image_cfg;
+
+/* Engine-owned persistent device buffers.  Views stay valid until apg_image_destroy; contents are
+ * overwritten by the next reset/step.  Shapes use N = num_envs, P = S0*S1*C. */
+typedef struct {
+  float* d_glimpse;          /* (N, S0, S1, C)  obs["glimpse"]                                  */
+  float* d_target_glimpse;   /* (N, S0, S1, C)  obs["target_glimpse"]   (localization only)     */
+  float* d_glimpse_pos;      /* (N, 2)          obs["glimpse_pos"]                              */
+  float* d_time_step;        /* (N,)            obs["time_step"]                                */
+  int32_t* d_inverted_label; /* (N,)            obs["inverted_label"]   (randomly_invert_labels) */
+  float* d_reward;           /* (N,)  base_reward - loss                                         */
+  float* d_base_reward;      /* (N,)  info["base_reward"]                                        */
+  float* d_loss;             /* (N,)  info["prediction"]["loss"]                                 */
+  int32_t* d_target_label;   /* (N,)  info["prediction"]["target"]  (classification)            */
+  float* d_target_xy;        /* (N,2) info["prediction"]["target"]  (localization: the scored target) */
+  uint8_t* d_terminated;     /* (N,)                                                             */
+  uint8_t* d_truncated;      /* (N,)                                                             */
+  int64_t* d_index;          /* (N,)  info["index"]                                              */
+  /* state (read-only for callers) */
+  double* d_pos;             /* (N, 2) float64 normalised sensor position                        */
+  float* d_cur_target_xy;    /* (N, 2) current localization target (the one target_glimpse shows) */
+  uint32_t* d_visited;       /* (N, H, ceil(W/32)) image-resolution visited bitmask              */
+  int32_t* d_stamp_xy;       /* (T, 2, N) overlay stamp log: render-resolution rectangle centres */
+  float* d_stamp_q;          /* (T, N)    overlay stamp log: clipped prediction quality          */
+  int32_t stamp_count;       /* number of valid stamps of the current episode (host mirror)      */
+  int32_t elapsed;           /* current time step t of the (shared) episode clock                */
+  int32_t needs_reset;       /* 1 when the next step is the NEXT_STEP autoreset step             */
+} apg_image_buffers;
+
+int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out);
+void apg_image_destroy(apg_image_env* env);
+/* Use the given cudaStream_t (as an opaque pointer) for all subsequent work; NULL = legacy default stream. */
+int apg_image_set_stream(apg_image_env* env, void* cuda_stream);
+
+/* Upload (h_*) or adopt (d_*, on_device=1, caller keeps ownership and must keep it alive) the image bank:
+ * n_items images of (H, W, C) in bank_dtype, and their int32 labels.
+ * Replaces the per-reset `dataset.get_data_point_batch(idx)` gather (image_perception_module.py:123-129). */
+int apg_image_set_bank(apg_image_env* env, const void* bank, const int32_t* labels, int64_t n_items, int on_device);
+
+/* Explicit reset: ImagePerceptionModule.reset() + (localization) the target assignment of
+ * ImageLocalizationVectorEnv.reset().  The random draws are the caller's (host numpy streams):
+ *   h_idx (N) bank indices, h_pos (N,2) float64 start positions, h_target (N,2) float32 targets
+ *   (localization, else NULL), h_invert (N) 0/1 (randomly_invert_labels, else NULL). Synchronous copy-in. */
+int apg_image_reset(apg_image_env* env, const int64_t* h_idx, const double* h_pos, const float* h_target,
+                    const uint8_t* h_invert);
+/* Queue the payload of a FUTURE autoreset (same arrays as above; copied, asynchronous H2D).  Payloads are
+ * consumed in FIFO order by the autoreset steps; up to cfg.payload_ring may be pending. */
+#define APG_PAYLOAD_RING_DEFAULT 4
+#define APG_PAYLOAD_RING_MAX 64
+int apg_image_queue_reset_payload(apg_image_env* env, const int64_t* h_idx, const double* h_pos,
+                                  const float* h_target, const uint8_t* h_invert);
+int apg_image_pending_payloads(apg_image_env* env);
+
+/* One vector step with DEVICE inputs: d_action (N,2) f32, d_pred (N,K) f32 logits or (N,2) f32 coordinates.
+ * One fused kernel launch; asynchronous.  Replaces ActivePerceptionVectorEnv.step end to end. */
+int apg_image_step(apg_image_env* env, const float* d_action, const float* d_pred);
+/* n_steps consecutive steps from stacked device inputs d_actions (n_steps, N, 2), d_preds (n_steps, N, K|2);
+ * per-step reward / done flags are additionally written to d_rewards (n_steps, N) f32 and d_dones
+ * (n_steps, N) u8 when these are non-NULL.  Autoreset steps consume queued payloads.  Asynchronous. */
+int apg_image_rollout(apg_image_env* env, const float* d_actions, const float* d_preds, int32_t n_steps,
+                      float* d_rewards, uint8_t* d_dones);
+/* One vector step with HOST inputs/outputs: copies h_action/h_pred to the device, steps, copies reward (N) f32,
+ * terminated/truncated (N) u8 and, when non-NULL, glimpse (N*P) f32 back, then synchronises.  This is the
+ * reference-facing call: same argument meaning as env.step({"action", "prediction"}). */
+int apg_image_step_host(apg_image_env* env, const float* h_action, const float* h_pred, float* h_reward,
+                        uint8_t* h_terminated, uint8_t* h_truncated, float* h_glimpse);
+
+int apg_image_get_buffers(apg_image_env* env, apg_image_buffers* out);
+/* Reads (and with clear!=0 resets) the sticky device error flags; synchronises the stream. */
+int apg_image_poll_error(apg_image_env* env, uint32_t* flags, int clear);
+int apg_image_sync(apg_image_env* env);
+
+/* ------------------------------------------------------------------------------------------------------
+ * DLPack export of engine-owned device memory (north_star: PyTorch only sees DLPack tensors).
+ * Returns a malloc'ed DLManagedTensor* (DLPack v0.8 layout) whose deleter frees only the descriptor.
+ * dtype_code: 0 int, 1 uint, 2 float (DLDataTypeCode); bits: 8/32/64.
+ * ------------------------------------------------------------------------------------------------------ */
+void* apg_dlpack_wrap(void* d_ptr, int32_t device, int32_t dtype_code, int32_t bits, int32_t ndim,
+                      const int64_t* shape);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APG_B200_H */

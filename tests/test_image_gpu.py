@@ -1,0 +1,203 @@
+"""GPU parity tests of the fused image step (through the C-ABI / ctypes layer) against
+(a) the golden vectors recorded from the unmodified reference and (b) the numpy oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact glimpse pixel coordinates (tap indices, checked through the visited
+bitmask and the overlay stamps), positions, flags, targets, indices; the float64-blended glimpse pixels are
+compared bit-exactly too (same IEEE op order, no FMA); losses/rewards within rtol 1e-5 (+1e-6 abs) because
+numpy's SIMD exp/log are not correctly rounded."""
+import numpy as np
+import pytest
+
+from helpers import IMAGE_CASES, assert_close, image_oracle_for, load_golden, make_bank
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _engine_for(case, imgs, labels, **kw):
+    import ap_gym_b200 as apg
+
+    ds = apg.ArrayImageDataset(imgs, labels, case["K"])
+    cfg = apg.ImagePerceptionConfig(dataset=ds, **case["cfg"])
+    cls = apg.ImageClassificationVectorEnv if case["task"] == "cls" else apg.ImageLocalizationVectorEnv
+    return cls(case["N"], cfg, **kw)
+
+
+def _np(x):
+    return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+
+
+@pytest.mark.parametrize("mode", ["numpy", "torch"])
+@pytest.mark.parametrize("name", list(IMAGE_CASES))
+def test_engine_matches_reference_golden(name, mode):
+    import torch
+
+    case = IMAGE_CASES[name]
+    g = load_golden("image", name)
+    imgs, labels = make_bank(case["bank"])
+    env = _engine_for(case, imgs, labels, check_errors="step")
+    opts = {"prediction_target": g["reset_target"]} if case["task"] == "loc" else None
+    obs, info = env.reset(seed=case["seed"], options=opts)
+    for k in obs:
+        assert np.array_equal(_np(obs[k]), g["reset_" + k]), f"reset obs {k}"
+    assert np.array_equal(_np(info["index"]), g["reset_index"])
+    for s in range(case["steps"]):
+        a, p = g["actions"][s], g["preds"][s]
+        if mode == "torch":
+            a, p = torch.from_numpy(a).cuda(), torch.from_numpy(p).cuda()
+        o, r, te, tr, inf = env.step({"action": a, "prediction": p})
+        for k in o:
+            assert np.array_equal(_np(o[k]), g["obs_" + k][s]), f"step {s} obs {k}"
+        assert np.array_equal(_np(env.state()["pos"]), g["pos64"][s]), f"step {s} float64 position"
+        assert np.array_equal(_np(te), g["terminated"][s]) and np.array_equal(_np(tr), g["truncated"][s])
+        assert np.array_equal(_np(inf["index"]), g["index"][s])
+        assert np.array_equal(_np(inf["prediction"]["target"]), g["target"][s])
+        assert np.array_equal(_np(inf["base_reward"]).astype(np.float64), g["base_reward"][s])
+        assert_close(_np(inf["prediction"]["loss"]), g["loss"][s], RTOL, ATOL, f"step {s} loss")
+        assert_close(_np(r), g["reward"][s], RTOL, ATOL, f"step {s} reward")
+        counts, quality = env.overlay_maps([0, 1])
+        assert np.array_equal(counts.astype(np.uint8), g["counts"][s]), f"step {s} overlay counts"
+        assert_close(quality, g["quality"][s], RTOL, ATOL, f"step {s} overlay quality")
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["mnistlike_cls_n32", "tinyloc_n4", "scaled_cls_n8"])
+def test_engine_matches_oracle_visited_mask_and_taps(name):
+    case = IMAGE_CASES[name]
+    g = load_golden("image", name)
+    oracle, imgs, labels = image_oracle_for(case)
+    env = _engine_for(case, imgs, labels)
+    tgt = g["reset_target"] if case["task"] == "loc" else None
+    oracle.reset(seed=case["seed"], explicit_targets=tgt)
+    env.reset(seed=case["seed"], options={"prediction_target": tgt} if tgt is not None else None)
+    assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited)
+    for s in range(case["steps"]):
+        oracle.step(g["actions"][s], g["preds"][s])
+        env.step({"action": g["actions"][s], "prediction": g["preds"][s]})
+        assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited), f"step {s} visited mask"
+    env.close()
+
+
+def test_engine_matches_oracle_seeded_mnist_2048():
+    """MNIST-shaped bank, N=2048, 40 steps (2 autoresets) of seeded random actions vs the oracle."""
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+    import ap_gym_b200 as apg
+
+    N, K = 2048, 10
+    imgs, labels = synthetic_u8_bank(seed=7, M=4096, H=28, W=28, C=1, K=K)
+    oracle = ImageEnvOracle(imgs, labels, N, task="cls", num_classes=K, track_overlay=False)
+    env = apg.ImageClassificationVectorEnv(
+        N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K)), output="numpy")
+    o0, _ = oracle.reset(seed=11)
+    e0, _ = env.reset(seed=11)
+    assert np.array_equal(e0["glimpse"], o0["glimpse"])
+    rng = np.random.default_rng(5)
+    for s in range(40):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32) * np.float32(1.3)
+        p = (rng.standard_normal((N, K)) * 4).astype(np.float32)
+        oo, orw, ote, otr, oinf = oracle.step(a, p)
+        eo, erw, ete, etr, einf = env.step({"action": a, "prediction": p})
+        for k in oo:
+            assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+        assert np.array_equal(ete, ote) and np.array_equal(etr, otr)
+        assert np.array_equal(einf["prediction"]["target"], oinf["prediction"]["target"])
+        assert np.array_equal(einf["index"], oinf["index"])
+        assert_close(erw, orw, RTOL, ATOL, f"step {s} reward")
+    env.close()
+
+
+def test_error_conventions():
+    import ap_gym_b200 as apg
+    from oracle.datasets import synthetic_u8_bank
+
+    imgs, labels = synthetic_u8_bank(seed=1, M=16, H=28, W=28, C=1, K=10)
+    ds = apg.ArrayImageDataset(imgs, labels, 10)
+    env = apg.ImageClassificationVectorEnv(4, apg.ImagePerceptionConfig(dataset=ds), check_errors="step")
+    with pytest.raises(Exception):
+        env.step({"action": np.zeros((4, 2), np.float32), "prediction": np.zeros((4, 10), np.float32)})  # before reset
+    env.reset(seed=0)
+    a = np.zeros((4, 2), np.float32)
+    p = np.zeros((4, 10), np.float32)
+    a[1, 0] = np.nan
+    with pytest.raises(ValueError, match="NaN values detected in action"):
+        env.step({"action": a, "prediction": p})
+    a[1, 0] = 0
+    p[2, 3] = np.nan
+    with pytest.raises(ValueError, match="NaN values detected in prediction"):
+        env.step({"action": a, "prediction": p})
+    with pytest.raises(ValueError, match="Unsupported render mode"):
+        apg.ImageClassificationVectorEnv(4, apg.ImagePerceptionConfig(dataset=ds), render_mode="human")
+    small = apg.ArrayImageDataset(np.zeros((2, 4, 4, 1), np.uint8), np.zeros(2, np.int32), 2)
+    with pytest.raises(ValueError, match="cannot be smaller than effective sensor size"):
+        apg.ImageClassificationVectorEnv(2, apg.ImagePerceptionConfig(dataset=small))
+    env.close()
+
+
+def test_full_size_properties_mnist_65536():
+    """BASELINE config 2 size: properties that need no oracle run -- determinism, shard invariance, the
+    17-step autoreset cycle, zero-action idempotence, reward identity, value ranges."""
+    import torch
+    import ap_gym_b200 as apg
+
+    N, K, T = 65536, 10, 16
+    ds = apg.SyntheticImageDataset("mnist", length=8192, seed=0)
+    cfg = apg.ImagePerceptionConfig(dataset=ds)
+    env = apg.ImageClassificationVectorEnv(N, cfg)
+    lo, hi = 1000, 1000 + 4096
+    shard = apg.ImageClassificationVectorEnv(hi - lo, cfg, env_offset=lo, global_num_envs=N)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    o, _ = env.reset(seed=3)
+    so, _ = shard.reset(seed=3)
+    assert torch.equal(o["glimpse"][lo:hi], so["glimpse"])
+    prev_glimpse = o["glimpse"].clone()
+    for s in range(2 * (T + 1)):
+        a = torch.rand((N, 2), generator=gen, device="cuda") * 2 - 1
+        if s % 5 == 2:
+            a.zero_()
+        p = torch.randn((N, K), generator=gen, device="cuda")
+        o, r, te, tr, inf = env.step({"action": a, "prediction": p})
+        so, sr, ste, _, sinf = shard.step({"action": a[lo:hi].contiguous(), "prediction": p[lo:hi].contiguous()})
+        cyc = s % (T + 1)
+        assert bool(te.all()) == (cyc == T - 1) and not bool(tr.any())
+        assert torch.equal(o["glimpse"][lo:hi], so["glimpse"]) and torch.equal(r[lo:hi], sr)
+        assert torch.equal(inf["index"][lo:hi], sinf["index"])
+        assert float(o["glimpse"].min()) >= 0.0 and float(o["glimpse"].max()) <= 1.0
+        assert float(o["glimpse_pos"].abs().max()) <= 1.0
+        if s % 5 == 2 and cyc != T:
+            assert torch.equal(o["glimpse"], prev_glimpse), "zero action must not move the sensor"
+        assert torch.allclose(r, inf["base_reward"] - inf["prediction"]["loss"], rtol=1e-6, atol=1e-6)
+        ce = torch.nn.functional.cross_entropy(p, inf["prediction"]["target"].long(), reduction="none") / np.log(K)
+        assert torch.allclose(inf["prediction"]["loss"], ce, rtol=1e-5, atol=1e-6)
+        prev_glimpse = o["glimpse"].clone()
+    env.close()
+    shard.close()
+
+
+def test_rollout_equals_stepping():
+    import torch
+    import ap_gym_b200 as apg
+
+    N, K, steps = 512, 10, 40
+    ds = apg.SyntheticImageDataset("mnist", length=1024, seed=2)
+    cfg = apg.ImagePerceptionConfig(dataset=ds)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    acts = torch.rand((steps, N, 2), generator=gen, device="cuda") * 2 - 1
+    preds = torch.randn((steps, N, K), generator=gen, device="cuda")
+    e1 = apg.ImageClassificationVectorEnv(N, cfg)
+    e2 = apg.ImageClassificationVectorEnv(N, cfg)
+    e1.reset(seed=9)
+    e2.reset(seed=9)
+    rew = torch.empty((steps, N), device="cuda")
+    done = torch.empty((steps, N), dtype=torch.bool, device="cuda")
+    e1.rollout(acts[:20], preds[:20], rew[:20], done[:20])
+    e1.rollout(acts[20:], preds[20:], rew[20:], done[20:])
+    for s in range(steps):
+        o, r, te, tr, _ = e2.step({"action": acts[s], "prediction": preds[s]})
+        assert torch.equal(r, rew[s]) and torch.equal(te, done[s])
+    e1.sync()
+    assert torch.equal(e1.step({"action": acts[0], "prediction": preds[0]})[0]["glimpse"],
+                       e2.step({"action": acts[0], "prediction": preds[0]})[0]["glimpse"])
+    e1.close()
+    e2.close()
