@@ -42,3 +42,15 @@ def assert_close(a, b, rtol=1e-5, atol=1e-6, what=""):
     if not np.all(err <= tol):
         i = np.unravel_index(np.argmax(err - tol), err.shape)
         raise AssertionError(f"{what}: max violation at {i}: got {a[i]!r} want {b[i]!r} (err {err[i]:.3e})")
+
+_mkl = _load("make_golden_lidar", os.path.join(GOLDEN, "make_golden_lidar.py"))
+LIDAR_CASES = _mkl.LIDAR_CASES
+load_bank = _mkl.load_bank
+
+
+def lidar_oracle_for(case):
+    from oracle.lidar_oracle import LidarVecOracle
+
+    maps = load_bank(case["bank"], case["M"])
+    return LidarVecOracle(maps, case["N"], beam_count=case["B"], static_map=case["static"],
+                          static_map_index=case.get("static_idx", 0)), maps
