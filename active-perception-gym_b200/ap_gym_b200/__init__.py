@@ -8,6 +8,8 @@ from .loss_fn import (CrossEntropyLossFn, LambdaLossFn, LossFn, LossFnAffineTran
                       WeightedLossFn, ZeroLossFn)
 from .spaces import ActivePerceptionActionSpace, ImageSpace, LogitSpace
 from .datasets import ArrayImageDataset, ImageBank, SyntheticImageDataset, bank_from_dataset
+from .floor_maps import FloorMapBank, pack_maps, unpack_maps
+from .lidar_env import LIDARLocalization2DVectorEnv, lidar_directions
 from .image_env import ImageClassificationVectorEnv, ImageLocalizationVectorEnv, ImagePerceptionConfig
 
 __version__ = "0.1.0"

@@ -45,6 +45,21 @@ class ImageBuffers(C.Structure):
     ]
 
 
+class LidarCfg(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("num_envs", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+        ("beam_count", C.c_int32), ("lidar_range", C.c_float), ("step_limit", C.c_int32),
+        ("static_map", C.c_int32), ("static_map_index", C.c_int32), ("emit_cells", C.c_int32),
+        ("env_offset", C.c_int64),
+    ]
+
+
+class LidarBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_lidar", "d_odometry", "d_time_step", "d_map", "d_reward", "d_base_reward", "d_loss", "d_target",
+        "d_terminated", "d_truncated", "d_stepped", "d_map_idx", "d_pos", "d_initial_pos", "d_cells", "d_dists")]
+
+
 # name -> (restype, argtypes); every symbol include/apg_b200.h declares must be listed here
 _P = C.c_void_p
 SYMBOLS = {
@@ -64,6 +79,19 @@ SYMBOLS = {
     "apg_image_get_buffers": (C.c_int, [_P, C.POINTER(ImageBuffers)]),
     "apg_image_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),
     "apg_image_sync": (C.c_int, [_P]),
+    "apg_lidar_create": (C.c_int, [C.POINTER(LidarCfg), C.POINTER(_P)]),
+    "apg_lidar_destroy": (None, [_P]),
+    "apg_lidar_set_stream": (C.c_int, [_P, _P]),
+    "apg_lidar_set_map_bank": (C.c_int, [_P, _P, C.c_int64]),
+    "apg_lidar_set_beams": (C.c_int, [_P, _P]),
+    "apg_lidar_reset": (C.c_int, [_P, C.c_uint64]),
+    "apg_lidar_step": (C.c_int, [_P, _P, _P]),
+    "apg_lidar_rollout": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
+    "apg_lidar_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "apg_lidar_get_buffers": (C.c_int, [_P, C.POINTER(LidarBuffers)]),
+    "apg_lidar_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),
+    "apg_lidar_sync": (C.c_int, [_P]),
+    "apg_rng_host_stream": (C.c_int, [C.c_uint64, C.c_int32, _P, _P, _P]),
     "apg_dlpack_wrap": (_P, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
 }
 

@@ -1,0 +1,85 @@
+"""Floor-map banks: the device-resident replacement of the reference's per-episode map fetch
+(ap_gym/envs/floor_map/*.py, ap_gym/envs/lidar_localization2d.py:279-298).
+
+A bank is a FINITE list of occupancy maps stored bit-packed, (M, H, ceil(W/32)) uint32 with bit x&31 of word
+x>>5 set for a wall.  Any object with the reference's FloorMapDataset surface (`map_width`, `map_height`,
+`__len__`, `__getitem__`) can be turned into a bank; the reference's procedural datasets report
+`len == 2**32`, so for those an explicit index list is required (documented deviation: the engine draws
+`integers(0, M)` over the bank where the reference draws `integers(0, 2**32)` over the generator).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+MAX_IMPLICIT_BANK = 1 << 20
+
+
+def pack_maps(maps: np.ndarray) -> np.ndarray:
+    maps = np.asarray(maps, dtype=bool)
+    if maps.ndim == 2:
+        maps = maps[None]
+    M, H, W = maps.shape
+    out = np.zeros((M, H, (W + 31) // 32), dtype=np.uint32)
+    for x in range(W):
+        out[:, :, x >> 5] |= maps[:, :, x].astype(np.uint32) << np.uint32(x & 31)
+    return out
+
+
+def unpack_maps(bits: np.ndarray, width: int) -> np.ndarray:
+    x = np.arange(width)
+    return ((bits[..., x >> 5] >> (x & 31).astype(np.uint32)) & 1).astype(bool)
+
+
+@dataclass
+class FloorMapBank:
+    bits: np.ndarray  # (M, H, words) uint32
+    map_width: int
+    map_height: int
+
+    def __post_init__(self):
+        self.bits = np.ascontiguousarray(self.bits, dtype=np.uint32)
+        if self.bits.ndim != 3 or self.bits.shape[1] != self.map_height or \
+                self.bits.shape[2] != (self.map_width + 31) // 32:
+            raise ValueError("bits must have shape (M, map_height, ceil(map_width/32))")
+
+    def __len__(self):
+        return len(self.bits)
+
+    def load(self):
+        pass
+
+    def get_data_point(self, idx) -> np.ndarray:
+        return unpack_maps(self.bits[int(idx)], self.map_width)
+
+    def __getitem__(self, item):
+        if isinstance(item, (list, tuple, np.ndarray)):
+            return unpack_maps(self.bits[np.asarray(item)], self.map_width)
+        return self.get_data_point(item)
+
+    @classmethod
+    def from_maps(cls, maps: np.ndarray) -> "FloorMapBank":
+        maps = np.asarray(maps, dtype=bool)
+        return cls(pack_maps(maps), maps.shape[-1], maps.shape[-2])
+
+    @classmethod
+    def from_dataset(cls, dataset, indices: Sequence[int] | None = None) -> "FloorMapBank":
+        if isinstance(dataset, FloorMapBank) and indices is None:
+            return dataset
+        if hasattr(dataset, "load"):
+            dataset.load()
+        if indices is None:
+            if len(dataset) > MAX_IMPLICIT_BANK:
+                raise ValueError(
+                    f"dataset has {len(dataset)} maps; pass a finite bank (FloorMapBank.from_dataset(ds, indices))")
+            indices = range(len(dataset))
+        maps = np.stack([np.asarray(dataset[int(i)], dtype=bool) for i in indices])
+        return cls(pack_maps(maps), int(dataset.map_width), int(dataset.map_height))
+
+    @classmethod
+    def load_npz(cls, path: str, limit: int | None = None) -> "FloorMapBank":
+        z = np.load(path)
+        bits = z["bits"] if limit is None else z["bits"][:limit]
+        return cls(bits, int(z["width"]), int(z["height"]))

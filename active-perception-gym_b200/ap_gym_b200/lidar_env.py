@@ -1,0 +1,231 @@
+"""Drop-in vectorised LIDAR localisation environment backed by the fused sm_100a step kernel.
+
+`LIDARLocalization2DVectorEnv(num_envs, dataset, ...)` is the engine's equivalent of what
+`ap_gym.make_vec("LIDARLoc*-v0", num_envs)` assembles from python objects (ap_gym/envs/registration.py:319-356,
+753-767): a gymnasium SyncVectorEnv (NEXT_STEP per-env autoreset, env i seeded with seed+i) over
+`TimeLimit(LIDARLocalization2DEnv(...), 100, issue_termination=True)`.  The constructor keeps the reference's
+keyword arguments (ap_gym/envs/lidar_localization2d.py:122-132) and adds `num_envs` in front.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Literal
+
+import numpy as np
+
+from . import _capi
+from .floor_maps import FloorMapBank
+from .loss_fn import make_mse_loss_fn_and_target_space
+from .spaces import NEXT_STEP, ActivePerceptionActionSpace, Box, Dict, ImageSpace, batch_box
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _void(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def lidar_directions(beam_count: int, lidar_range: float) -> np.ndarray:
+    """The reference's beam table (lidar_localization2d.py:180-187), float32 (B, 2)."""
+    ang = np.linspace(-np.pi, np.pi, beam_count, dtype=np.float32, endpoint=False)
+    unscaled = np.stack([np.cos(ang), np.sin(ang)], axis=-1)
+    return np.ascontiguousarray(unscaled * lidar_range, dtype=np.float32)
+
+
+class LIDARLocalization2DVectorEnv:
+    metadata: dict[str, Any] = {"render_modes": ["rgb_array"], "render_fps": 4, "autoreset_mode": NEXT_STEP}
+
+    def __init__(self, num_envs: int, dataset, render_mode: Literal["rgb_array"] = "rgb_array",
+                 static_map: bool = False, lidar_beam_count: int = 8, lidar_range: float = 5,
+                 static_map_index: int = 0, prefetch: bool = True, prefetch_buffer_size: int = 128, *,
+                 max_episode_steps: int = 100, device: int = 0, env_offset: int = 0, emit_cells: bool = False,
+                 check_errors: Literal["step", "lazy", "never"] = "lazy", output: Literal["torch", "numpy"] = "torch"):
+        if render_mode not in self.metadata["render_modes"]:
+            raise ValueError(f"Invalid render mode: {render_mode}")
+        self._render_mode = render_mode
+        self.num_envs = int(num_envs)
+        self._device = int(device)
+        self._bank = FloorMapBank.from_dataset(dataset)
+        self._static = bool(static_map)
+        self._B = int(lidar_beam_count)
+        self._range = lidar_range
+        self._T = int(max_episode_steps)
+        self._W, self._H = int(self._bank.map_width), int(self._bank.map_height)
+        self._check_errors = check_errors
+        self._numpy_mode = output == "numpy"
+        self._steps_since_poll = 0
+        self._emit = bool(emit_cells)
+        self._lib = _capi.lib()
+        cfg = _capi.LidarCfg(device=self._device, num_envs=self.num_envs, width=self._W, height=self._H,
+                             beam_count=self._B, lidar_range=float(lidar_range), step_limit=self._T,
+                             static_map=int(self._static), static_map_index=int(static_map_index),
+                             emit_cells=int(self._emit), env_offset=int(env_offset))
+        h = C.c_void_p()
+        _capi.check(self._lib.apg_lidar_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._closed = False
+        _capi.check(self._lib.apg_lidar_set_map_bank(self._h, _void(self._bank.bits), len(self._bank)))
+        self._dirs = lidar_directions(self._B, lidar_range)
+        _capi.check(self._lib.apg_lidar_set_beams(self._h, _void(self._dirs)))
+        self._views = self._make_views()
+        self._has_reset = False
+        self.spec = None
+
+        obs = {"lidar": Box(low=0, high=1, shape=(self._B,), dtype=np.float32),
+               "odometry": Box(low=-1, high=1, shape=(2,), dtype=np.float32)}
+        if not self._static:
+            obs["map"] = ImageSpace(width=self._W, height=self._H, channels=1)
+        obs["time_step"] = Box(low=-1.0, high=1.0, shape=(), dtype=np.float32)
+        self.single_observation_space = Dict(obs)
+        self.observation_space = Dict({k: batch_box(s, self.num_envs, ImageSpace if isinstance(s, ImageSpace) else None)
+                                       for k, s in obs.items()})
+        inner = Box(low=-1, high=1, shape=(2,), dtype=np.float32)
+        pred = Box(low=-1, high=1, shape=(2,))
+        self.single_action_space = ActivePerceptionActionSpace(inner, pred)
+        self.action_space = ActivePerceptionActionSpace(batch_box(inner, self.num_envs), batch_box(pred, self.num_envs))
+        self.loss_fn, self.single_prediction_target_space = make_mse_loss_fn_and_target_space(2, -1, 1)
+        self.prediction_target_space = batch_box(self.single_prediction_target_space, self.num_envs)
+
+    prediction_space = property(lambda self: self.action_space["prediction"])
+    inner_action_space = property(lambda self: self.action_space["action"])
+    single_prediction_space = property(lambda self: self.single_action_space["prediction"])
+    single_inner_action_space = property(lambda self: self.single_action_space["action"])
+    render_mode = property(lambda self: self._render_mode)
+    dataset = property(lambda self: self._bank)
+    unwrapped = property(lambda self: self)
+
+    def _make_views(self):
+        b = _capi.LidarBuffers()
+        _capi.check(self._lib.apg_lidar_get_buffers(self._h, C.byref(b)))
+        N, B, dev = self.num_envs, self._B, self._device
+        t = _capi.dlpack_tensor
+        v = {
+            "lidar": t(b.d_lidar, dev, "float", 32, (N, B)),
+            "odometry": t(b.d_odometry, dev, "float", 32, (N, 2)),
+            "time_step": t(b.d_time_step, dev, "float", 32, (N,)),
+            "reward": t(b.d_reward, dev, "float", 32, (N,)),
+            "base_reward": t(b.d_base_reward, dev, "float", 32, (N,)),
+            "loss": t(b.d_loss, dev, "float", 32, (N,)),
+            "target": t(b.d_target, dev, "float", 32, (N, 2)),
+            "terminated": t(b.d_terminated, dev, "bool", 8, (N,)),
+            "truncated": t(b.d_truncated, dev, "bool", 8, (N,)),
+            "stepped": t(b.d_stepped, dev, "bool", 8, (N,)),
+            "map_idx": t(b.d_map_idx, dev, "int", 64, (N,)),
+            "pos": t(b.d_pos, dev, "float", 32, (N, 2)),
+            "initial_pos": t(b.d_initial_pos, dev, "float", 32, (N, 2)),
+        }
+        if b.d_map:
+            v["map"] = t(b.d_map, dev, "float", 32, (N, self._H, self._W, 1))
+        if b.d_cells:
+            v["cells"] = t(b.d_cells, dev, "int", 32, (N, B, 2))
+            v["dists"] = t(b.d_dists, dev, "float", 32, (N, B))
+        return v
+
+    def _out(self, name, as_numpy):
+        v = self._views[name]
+        return v.cpu().numpy() if as_numpy else v
+
+    def _obs(self, as_numpy):
+        keys = ["lidar", "odometry"] + ([] if self._static else ["map"]) + ["time_step"]
+        return {k: self._out(k, as_numpy) for k in keys}
+
+    def _poll(self):
+        flags = C.c_uint32(0)
+        _capi.check(self._lib.apg_lidar_poll_error(self._h, C.byref(flags), 1))
+        self._steps_since_poll = 0
+        if flags.value & _capi.FLAG_NAN_ACTION:
+            raise ValueError("NaN values detected in action.")
+        if flags.value & _capi.FLAG_NAN_PRED:
+            raise ValueError("NaN values detected in prediction.")
+
+    def _maybe_poll(self, host_mode):
+        self._steps_since_poll += 1
+        if self._check_errors == "never":
+            return
+        if self._check_errors == "step" or host_mode or self._steps_since_poll >= 256:
+            self._poll()
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        if seed is None:
+            if self._has_reset:
+                raise NotImplementedError(
+                    "reset() without a seed after the first reset is not supported: every env autoresets on its own")
+            # like gymnasium's lazily seeded np_random: entropy from the OS
+            seed = int(np.random.SeedSequence().entropy % (2**63))
+        _capi.check(self._lib.apg_lidar_reset(self._h, C.c_uint64(int(seed))))
+        self._has_reset = True
+        as_numpy = self._numpy_mode or bool(options and options.get("numpy", False))
+        return self._obs(as_numpy), {"map_idx": self._out("map_idx", as_numpy)}
+
+    def step(self, action):
+        a, p = action["action"], action["prediction"]
+        host_mode = not _is_torch(a)
+        N = self.num_envs
+        if host_mode:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            p = np.ascontiguousarray(p, dtype=np.float32)
+            if a.shape != (N, 2) or p.shape != (N, 2):
+                raise ValueError(f"bad action/prediction shapes {a.shape} {p.shape}")
+            reward = np.empty(N, np.float32)
+            term = np.empty(N, np.bool_)
+            trunc = np.empty(N, np.bool_)
+            lidar = np.empty((N, self._B), np.float32)
+            _capi.check(self._lib.apg_lidar_step_host(self._h, _void(a), _void(p), _void(reward), _void(term),
+                                                      _void(trunc), _void(lidar)))
+            self._maybe_poll(True)
+            obs = self._obs(True)
+            obs["lidar"] = lidar
+            terminated, truncated = term, trunc
+        else:
+            if not (a.is_cuda and p.is_cuda and a.is_contiguous() and p.is_contiguous()
+                    and str(a.dtype) == "torch.float32" and str(p.dtype) == "torch.float32"):
+                raise ValueError("torch inputs must be contiguous float32 CUDA tensors")
+            if tuple(a.shape) != (N, 2) or tuple(p.shape) != (N, 2):
+                raise ValueError(f"bad action/prediction shapes {tuple(a.shape)} {tuple(p.shape)}")
+            _capi.check(self._lib.apg_lidar_step(self._h, a.data_ptr(), p.data_ptr()))
+            self._maybe_poll(False)
+            obs = self._obs(False)
+            reward = self._views["reward"]
+            terminated, truncated = self._views["terminated"], self._views["truncated"]
+        stepped = self._out("stepped", host_mode)
+        info = {
+            "base_reward": self._out("base_reward", host_mode), "_base_reward": stepped,
+            "prediction": {"target": self._out("target", host_mode), "_target": stepped,
+                           "loss": self._out("loss", host_mode), "_loss": stepped},
+            "_prediction": stepped,
+            "map_idx": self._out("map_idx", host_mode), "_map_idx": ~stepped,
+        }
+        return obs, reward, terminated, truncated, info
+
+    def rollout(self, actions, predictions, rewards=None, dones=None):
+        _capi.check(self._lib.apg_lidar_rollout(
+            self._h, actions.data_ptr(), predictions.data_ptr(), int(actions.shape[0]),
+            None if rewards is None else rewards.data_ptr(), None if dones is None else dones.data_ptr()))
+
+    def state(self):
+        out = {"pos": self._views["pos"], "initial_pos": self._views["initial_pos"]}
+        for k in ("cells", "dists"):
+            if k in self._views:
+                out[k] = self._views[k]
+        return out
+
+    def sync(self):
+        _capi.check(self._lib.apg_lidar_sync(self._h))
+
+    def render(self):
+        raise NotImplementedError("render() is host-side tooling outside the hot path (DESIGN.md, out of scope)")
+
+    def close(self):
+        if not getattr(self, "_closed", True):
+            self._closed = True
+            self._views = {}
+            self._lib.apg_lidar_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -1,0 +1,660 @@
+// Fused LIDAR-localisation step for sm_100a: one launch = one vector step of
+// `make_vec("LIDARLoc*-v0", N)` (SyncVectorEnv of TimeLimit(100)-wrapped LIDARLocalization2DEnv).
+//
+// Per environment (reference file:line in /root/reference/ap_gym):
+//   * NEXT_STEP per-env autoreset: map + start cell from the env's own numpy-compatible PCG64 streams
+//                                                          envs/lidar_localization2d.py:293-315,547-557 (+ gymnasium SyncVectorEnv)
+//   * pose integration, collision ray, wall slide           envs/lidar_localization2d.py:317-375
+//   * base reward, normalised-MSE loss, reward              envs/lidar_localization2d.py:330,377; loss_fn.py:100-110,261-267
+//   * TimeLimit termination + time_step obs                 time_limit.py:113-139
+//   * B-beam scan against the occupancy bitmap              envs/lidar_localization2d.py:238-277,496-536
+//
+// Mapping: a group of G = min(32, pow2 >= B) lanes owns one environment (a whole warp for B >= 32).  The
+// environment's bit-packed map rows are staged in shared memory once per step; the collision/slide rays are
+// evaluated redundantly by every lane of the group (uniform control flow, no divergence), then each lane casts
+// the beams b = lane, lane+G, ... and stores coalesced runs of the lidar row.
+//
+// Ray casting = the closed-cell grid walk of oracle/lidar_oracle.c, same IEEE operations in the same order
+// (file compiled with -fmad=false; the one fused operation is the explicit fma of the float64 dot product).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "apg_common.h"
+#include "apg_rng.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+struct LidarParams {
+  int N, W, H, words, B, G, T, M;
+  int static_map, static_idx, emit_cells;
+  int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams)
+  float range;
+  unsigned long long seed;  // mode 2: env i is seeded with seed + env_offset + i
+  long long env_offset;
+  const unsigned* bank;     // (M, H, words)
+  const float* dirs;        // (B, 2) lidar_directions
+  const float* action;
+  const float* pred;
+  // state
+  float* pos;               // (N,2)
+  float* init;              // (N,2)
+  unsigned char* aliased;   // (N)
+  int* elapsed;             // (N)
+  int* map_idx;             // (N)
+  unsigned char* prev_done; // (N)
+  apg::Pcg64* g0;           // (N) env-level Generator
+  apg::Pcg64* g2;           // (N) DatasetIterator Generator
+  // outputs
+  float* lidar;             // (N,B)
+  float* odometry;          // (N,2)
+  float* time_step;         // (N)
+  float* map_obs;           // (N,H,W) dynamic maps only
+  float* reward;
+  float* base_reward;
+  float* loss;
+  float* target;            // (N,2)
+  unsigned char* terminated;
+  unsigned char* truncated;
+  unsigned char* stepped;   // (N) 1 = this env took a real step (0 = autoreset step)
+  long long* map_idx_out;   // (N)
+  int* cells;               // (N,B,2) optional
+  float* dists;             // (N,B) optional raw distances
+  float* reward2;
+  unsigned char* done2;
+  unsigned* err;
+};
+
+struct MapView {
+  const unsigned* bits;  // shared memory, H*words
+  int W, H, words;
+};
+
+__device__ __forceinline__ int is_wall(const MapView& m, int x, int y) {
+  if (x < 0 || y < 0 || x >= m.W || y >= m.H) return 0;
+  return (int)((m.bits[y * m.words + (x >> 5)] >> (x & 31)) & 1u);
+}
+
+__device__ __forceinline__ float norm2f(float a, float b) {
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));
+}
+
+// oracle/lidar_oracle.c: apg_oracle_scan_one, operation for operation
+__device__ float scan_one(const MapView& m, float posx, float posy, float tx, float ty, int& cellx, int& celly) {
+  const double px = posx, py = posy;
+  const double dx = (double)tx - px, dy = (double)ty - py;
+  const int sx = dx > 0 ? 1 : (dx < 0 ? -1 : 0), sy = dy > 0 ? 1 : (dy < 0 ? -1 : 0);
+  const bool px_int = (px == floor(px)), py_int = (py == floor(py));
+  int cx = (int)floor(px), cy = (int)floor(py);
+  if (px_int && sx < 0) cx -= 1;
+  if (py_int && sy < 0) cy -= 1;
+  const bool nbx = (sx == 0 && px_int), nby = (sy == 0 && py_int);
+#define WALL(X, Y) (is_wall(m, (X), (Y)) || (nbx && is_wall(m, (X)-1, (Y))) || (nby && is_wall(m, (X), (Y)-1)))
+  int n_pos = 0, n_zero = 0;
+  bool have_first = false, in_iv = false;
+  double iv_t0 = 0.0, fex = 0.0, fey = 0.0;
+  if (WALL(cx, cy)) {
+    in_iv = true; have_first = true; fex = px; fey = py;
+  } else if (px_int || py_int) {
+    bool touch = false;
+    const int bx = cx - sx, by = cy - sy;
+    if (px_int && sx != 0) touch |= is_wall(m, bx, cy) || (nby && is_wall(m, bx, cy - 1));
+    if (py_int && sy != 0) touch |= is_wall(m, cx, by) || (nbx && is_wall(m, cx - 1, by));
+    if (px_int && py_int && sx != 0 && sy != 0) touch |= (bool)is_wall(m, bx, by);
+    if (touch) { n_zero = 1; have_first = true; fex = px; fey = py; }
+  }
+  // the crossing parameters are refreshed only for the axis that advanced: same values as recomputing both
+  double tX = INFINITY, tY = INFINITY, gx = 0.0, gy = 0.0;
+  if (sx != 0) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = __ddiv_rn(gx - px, dx); }
+  if (sy != 0) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = __ddiv_rn(gy - py, dy); }
+  for (;;) {
+    const double tN = tX < tY ? tX : tY;
+    if (!(tN <= 1.0)) break;
+    const bool stepx = tX <= tY, stepy = tY <= tX;
+    const int ncx = cx + (stepx ? sx : 0), ncy = cy + (stepy ? sy : 0);
+    const bool next_wall = WALL(ncx, ncy);
+    const bool side_wall = (stepx && stepy) && (is_wall(m, ncx, cy) || is_wall(m, cx, ncy));
+    if (in_iv) {
+      if (!next_wall) {
+        if (tN > iv_t0) n_pos++; else n_zero++;
+        in_iv = false;
+      }
+    } else if (next_wall || side_wall) {
+      if (!have_first) {
+        have_first = true;
+        fex = stepx ? gx : px + tN * dx;
+        fey = stepy ? gy : py + tN * dy;
+      }
+      if (next_wall) { in_iv = true; iv_t0 = tN; } else n_zero++;
+    }
+    cx = ncx; cy = ncy;
+    if (stepx) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = __ddiv_rn(gx - px, dx); }
+    if (stepy) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = __ddiv_rn(gy - py, dy); }
+    // a ray that has left the map and keeps moving away never meets another cell of the union
+    if (!in_iv && ((cx < 0 && sx <= 0) || (cx >= m.W && sx >= 0) || (cy < 0 && sy <= 0) || (cy >= m.H && sy >= 0)) &&
+        !nbx && !nby)
+      break;
+  }
+  if (in_iv) { if (iv_t0 < 1.0) n_pos++; else n_zero++; }
+#undef WALL
+  const float full = norm2f(__fsub_rn(tx, posx), __fsub_rn(ty, posy));
+  float dist;
+  int kind;
+  double c64x = 0, c64y = 0;
+  float c32x = 0, c32y = 0;
+  if (n_pos + n_zero == 0 || (n_pos > 0 && n_zero > 0)) {
+    dist = full; kind = 0;
+  } else if (n_pos == 1) {
+    const double ddx = fex - px, ddy = fey - py;
+    const double nrm = sqrt(__fma_rn(ddy, ddy, ddx * ddx));
+    dist = (float)fmax(nrm - 1e-3, 0.0);
+    kind = 1; c64x = fex; c64y = fey;
+  } else if (n_zero == 1) {
+    dist = 0.0f; kind = 2; c32x = posx; c32y = posy;
+  } else {
+    c32x = (float)fex; c32y = (float)fey;
+    const float d = norm2f(__fsub_rn(c32x, posx), __fsub_rn(c32y, posy));
+    dist = fmaxf(__fsub_rn(d, 1e-3f), 0.0f);
+    kind = 2;
+  }
+  cellx = -1; celly = -1;
+  if (kind != 0 && dist < full) {
+    if (kind == 1) {
+      double fx = floor(c64x), fy = floor(c64y);
+      if (fabs(fx - c64x) < 1e-5 && tx < posx) fx -= 1.0;
+      if (fabs(fy - c64y) < 1e-5 && ty < posy) fy -= 1.0;
+      cellx = (int)fx; celly = (int)fy;
+    } else {
+      float fx = floorf(c32x), fy = floorf(c32y);
+      if (fabsf(__fsub_rn(fx, c32x)) < 1e-5f && tx < posx) fx -= 1.0f;
+      if (fabsf(__fsub_rn(fy, c32y)) < 1e-5f && ty < posy) fy -= 1.0f;
+      cellx = (int)fx; celly = (int)fy;
+    }
+  }
+  return dist;
+}
+
+// start cell: the k-th free cell in row-major order (np.where(map == 0), lidar_localization2d.py:303-311)
+__device__ void kth_free_cell(const unsigned* bits, int W, int H, int words, unsigned k, int& col, int& row) {
+  col = 0; row = 0;
+  for (int y = 0; y < H; ++y) {
+    for (int w = 0; w < words; ++w) {
+      const int nb = min(32, W - w * 32);
+      const unsigned valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+      const unsigned freebits = ~bits[y * words + w] & valid;
+      const unsigned c = __popc(freebits);
+      if (k < c) {
+        row = y;
+        col = w * 32 + (__fns(freebits, 0, (int)k + 1));
+        return;
+      }
+      k -= c;
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int H, int words) {
+  unsigned n = 0;
+  for (int y = 0; y < H; ++y)
+    for (int w = 0; w < words; ++w) {
+      const int nb = min(32, W - w * 32);
+      const unsigned valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+      n += __popc(~bits[y * words + w] & valid);
+    }
+  return n;
+}
+
+__global__ void __launch_bounds__(kThreads) lidar_step_kernel(const LidarParams p) {
+  extern __shared__ unsigned smem_maps[];  // one (H*words) slot per group
+  const int tid = threadIdx.x;
+  const int groups_per_block = kThreads / p.G;
+  const int grp = tid / p.G;
+  const int li = tid - grp * p.G;
+  const int n = blockIdx.x * groups_per_block + grp;
+  const unsigned gmask = (p.G == 32) ? 0xffffffffu : (((1u << p.G) - 1u) << ((tid & 31) / p.G * p.G));
+  if (n >= p.N) return;
+  const int mw = p.H * p.words;
+  unsigned* smap = smem_maps + (size_t)grp * mw;
+  MapView mv{smap, p.W, p.H, p.words};
+  const float Wf = (float)p.W, Hf = (float)p.H;
+
+  const bool do_reset = (p.mode == 2) || (p.prev_done[n] != 0);
+  float posx, posy, initx, inity;
+  int elapsed;
+  int midx;
+  bool aliased;
+  unsigned err = 0;
+  unsigned char term = 0;
+
+  if (do_reset) {
+    // ---------------- reset path: streams advance exactly like the reference's per-env Generators
+    unsigned long long mi = 0;
+    if (li == 0) {
+      apg::Pcg64 g0, g2;
+      if (p.mode == 2) {
+        apg::pcg64_seed(g0, p.seed + (unsigned long long)(p.env_offset + n));
+        if (!p.static_map) {
+          const uint64_t s2 = apg::rng_integers_0_to_2p32_inclusive(g0);  // DatasetIterator seed (:552)
+          apg::pcg64_seed(g2, s2);
+        } else {
+          g2 = g0;
+        }
+      } else {
+        g0 = p.g0[n];
+        g2 = p.g2[n];
+      }
+      if (!p.static_map) mi = apg::rng_integers_below(g2, (uint64_t)p.M);  // dataset_iterator.py:30
+      else mi = (unsigned long long)p.static_idx;
+      p.g2[n] = g2;
+      p.g0[n] = g0;  // g0's start-cell draw happens below, after the map is staged
+    }
+    mi = __shfl_sync(gmask, mi, (tid & 31) - li);
+    midx = (int)mi;
+    const unsigned* gm = p.bank + (size_t)midx * mw;
+    for (int q = li; q < mw; q += p.G) smap[q] = gm[q];
+    __syncwarp(gmask);
+    int col = 0, row = 0;
+    if (li == 0) {
+      apg::Pcg64 g0 = p.g0[n];
+      const unsigned n_free = count_free(smap, p.W, p.H, p.words);
+      const unsigned k = (unsigned)apg::rng_integers_below(g0, (uint64_t)n_free);
+      kth_free_cell(smap, p.W, p.H, p.words, k, col, row);
+      p.g0[n] = g0;
+    }
+    col = __shfl_sync(gmask, col, (tid & 31) - li);
+    row = __shfl_sync(gmask, row, (tid & 31) - li);
+    posx = __fadd_rn((float)col, 0.5f);
+    posy = __fadd_rn((float)row, 0.5f);
+    initx = posx; inity = posy;
+    aliased = true;
+    elapsed = 0;
+    if (p.map_obs) {  // map.astype(f32)[..., None] / 255  -> {0, 1/255}
+      float* mo = p.map_obs + (size_t)n * p.H * p.W;
+      const float one = __fdiv_rn(1.0f, 255.0f);
+      for (int q = li; q < p.H * p.W; q += p.G) {
+        const int y = q / p.W, x = q - y * p.W;
+        mo[q] = ((smap[y * p.words + (x >> 5)] >> (x & 31)) & 1u) ? one : 0.0f;
+      }
+    }
+    if (li == 0) {
+      p.reward[n] = 0.0f;
+      p.base_reward[n] = 0.0f;
+      p.loss[n] = 0.0f;
+      p.target[2 * n] = 0.0f; p.target[2 * n + 1] = 0.0f;
+      p.stepped[n] = 0;
+      p.map_idx[n] = midx;
+      p.map_idx_out[n] = (long long)midx;
+      if (p.reward2) p.reward2[n] = 0.0f;
+    }
+  } else {
+    // ---------------- real step: every lane of the group computes the (uniform) move
+    midx = p.map_idx[n];
+    const unsigned* gm = p.bank + (size_t)midx * mw;
+    for (int q = li; q < mw; q += p.G) smap[q] = gm[q];
+    posx = p.pos[2 * n]; posy = p.pos[2 * n + 1];
+    initx = p.init[2 * n]; inity = p.init[2 * n + 1];
+    aliased = p.aliased[n] != 0;
+    elapsed = p.elapsed[n];
+    float a0 = p.action[2 * n], a1 = p.action[2 * n + 1];
+    const float q0 = p.pred[2 * n], q1 = p.pred[2 * n + 1];
+    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
+    if (isnan(q0) || isnan(q1)) err |= APG_FLAG_NAN_PRED;
+    __syncwarp(gmask);
+    const float lastx = posx, lasty = posy;
+    const float base = __fsub_rn(0.1f, __fmul_rn(1e-3f, __fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1))));
+    const float mag = norm2f(a0, a1);
+    if (mag > 1.0f) { a0 = __fdiv_rn(a0, mag); a1 = __fdiv_rn(a1, mag); }
+    const float tx = __fadd_rn(posx, a0), ty = __fadd_rn(posy, a1);
+    float dirx = __fsub_rn(tx, posx), diry = __fsub_rn(ty, posy);
+    const float total = norm2f(dirx, diry);
+    if (total > 0.0f) {
+      dirx = __fdiv_rn(dirx, total); diry = __fdiv_rn(diry, total);
+      int c0, c1;
+      const float d = scan_one(mv, posx, posy, tx, ty, c0, c1);
+      posx = __fadd_rn(posx, __fmul_rn(dirx, d));
+      posy = __fadd_rn(posy, __fmul_rn(diry, d));
+      const float rem = __fsub_rn(total, d);
+      if (rem > 1e-5f) {
+        const float rvx = __fmul_rn(dirx, rem), rvy = __fmul_rn(diry, rem);
+        const bool kx = rvx > 1e-5f, ky = rvy > 1e-5f;
+        if (kx || ky) {
+          const float v0 = (kx && ky) ? rvx : (kx ? rvx : rvy);
+          const float v1 = (kx && ky) ? rvy : (kx ? rvx : rvy);
+          const float d0 = scan_one(mv, posx, posy, __fadd_rn(posx, v0), __fadd_rn(posy, 0.0f), c0, c1);
+          const float d1 = scan_one(mv, posx, posy, __fadd_rn(posx, 0.0f), __fadd_rn(posy, v1), c0, c1);
+          if (d0 > 0.0f) {
+            const float nv = norm2f(v0, 0.0f);
+            posx = __fadd_rn(posx, __fmul_rn(__fdiv_rn(v0, nv), d0));
+            posy = __fadd_rn(posy, __fmul_rn(__fdiv_rn(0.0f, nv), d0));
+          } else {
+            const float nv = norm2f(0.0f, v1);
+            posx = __fadd_rn(posx, __fmul_rn(__fdiv_rn(0.0f, nv), d1));
+            posy = __fadd_rn(posy, __fmul_rn(__fdiv_rn(v1, nv), d1));
+          }
+        }
+      }
+    }
+    if (aliased) { initx = posx; inity = posy; }
+    const bool oob = (posx < 0.0f) || (posy < 0.0f) || (posx >= Wf) || (posy >= Hf);
+    posx = fminf(fmaxf(posx, 0.0f), Wf);
+    posy = fminf(fmaxf(posy, 0.0f), Hf);
+    aliased = false;
+    const float t0 = __fsub_rn(__fmul_rn(__fdiv_rn(lastx, Wf), 2.0f), 1.0f);
+    const float t1 = __fsub_rn(__fmul_rn(__fdiv_rn(lasty, Hf), 2.0f), 1.0f);
+    const float e0 = __fsub_rn(q0, t0), e1 = __fsub_rn(q1, t1);
+    const float mse = __fdiv_rn(__fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)), 2.0f);
+    const float loss = __fadd_rn(__fmul_rn(mse, 3.0f), 0.0f);
+    elapsed += 1;
+    term = (oob || elapsed >= p.T) ? 1 : 0;
+    if (li == 0) {
+      const float rew = __fsub_rn(base, loss);
+      p.reward[n] = rew;
+      p.base_reward[n] = base;
+      p.loss[n] = loss;
+      p.target[2 * n] = t0; p.target[2 * n + 1] = t1;
+      p.stepped[n] = 1;
+      p.map_idx_out[n] = (long long)midx;
+      if (p.reward2) p.reward2[n] = rew;
+    }
+  }
+
+  // ---------------- state write-back + scalar observations
+  if (li == 0) {
+    p.pos[2 * n] = posx; p.pos[2 * n + 1] = posy;
+    p.init[2 * n] = initx; p.init[2 * n + 1] = inity;
+    p.aliased[n] = aliased ? 1 : 0;
+    p.elapsed[n] = elapsed;
+    p.prev_done[n] = term;
+    p.terminated[n] = term;
+    p.truncated[n] = 0;
+    if (p.done2) p.done2[n] = term;
+    // TimeLimit._get_time_obs: float32(2.0 * elapsed / T - 1.0) evaluated in float64
+    p.time_step[n] = (float)(2.0 * (double)elapsed / (double)p.T - 1.0);
+    // odometry normalisation (:263-270)
+    p.odometry[2 * n] = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(posx, initx), -Wf), __fsub_rn(Wf, -Wf)), 2.0f), 1.0f);
+    p.odometry[2 * n + 1] = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(posy, inity), -Hf), __fsub_rn(Hf, -Hf)), 2.0f), 1.0f);
+    if (err) atomicOr(p.err, err);
+  }
+
+  // ---------------- observation scan: lane -> beams li, li+G, ...
+  for (int b = li; b < p.B; b += p.G) {
+    const float ddx = p.dirs[2 * b], ddy = p.dirs[2 * b + 1];
+    int c0, c1;
+    const float d = scan_one(mv, posx, posy, __fadd_rn(posx, ddx), __fadd_rn(posy, ddy), c0, c1);
+    p.lidar[(size_t)n * p.B + b] = fminf(fmaxf(__fdiv_rn(d, p.range), -1.0f), 1.0f);
+    if (p.cells) {
+      p.cells[((size_t)n * p.B + b) * 2] = c0;
+      p.cells[((size_t)n * p.B + b) * 2 + 1] = c1;
+      p.dists[(size_t)n * p.B + b] = d;
+    }
+  }
+}
+
+}  // namespace
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+struct apg_lidar_env {
+  apg_lidar_cfg cfg{};
+  cudaStream_t stream = nullptr;
+  int words = 0, G = 0;
+  size_t smem = 0;
+  unsigned* d_bank = nullptr;
+  int64_t n_maps = 0;
+  float* d_dirs = nullptr;
+  bool have_beams = false;
+  apg_lidar_buffers b{};
+  uint8_t* d_aliased = nullptr;
+  int32_t* d_elapsed = nullptr;
+  int32_t* d_map_idx = nullptr;
+  uint8_t* d_prev_done = nullptr;
+  apg::Pcg64* d_g0 = nullptr;
+  apg::Pcg64* d_g2 = nullptr;
+  unsigned* d_err = nullptr;
+  float* d_in_action = nullptr;
+  float* d_in_pred = nullptr;
+  bool has_reset = false;
+};
+
+namespace {
+
+int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_action, const float* d_pred, float* reward2,
+                 uint8_t* done2) {
+  const apg_lidar_cfg& c = e->cfg;
+  LidarParams p{};
+  p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
+  p.T = c.step_limit; p.M = (int)e->n_maps; p.static_map = c.static_map; p.static_idx = c.static_map_index;
+  p.emit_cells = c.emit_cells; p.mode = mode; p.range = c.lidar_range; p.seed = seed; p.env_offset = c.env_offset;
+  p.bank = e->d_bank; p.dirs = e->d_dirs; p.action = d_action; p.pred = d_pred;
+  p.pos = e->b.d_pos; p.init = e->b.d_initial_pos; p.aliased = e->d_aliased; p.elapsed = e->d_elapsed;
+  p.map_idx = e->d_map_idx; p.prev_done = e->d_prev_done; p.g0 = e->d_g0; p.g2 = e->d_g2;
+  p.lidar = e->b.d_lidar; p.odometry = e->b.d_odometry; p.time_step = e->b.d_time_step; p.map_obs = e->b.d_map;
+  p.reward = e->b.d_reward; p.base_reward = e->b.d_base_reward; p.loss = e->b.d_loss; p.target = e->b.d_target;
+  p.terminated = e->b.d_terminated; p.truncated = e->b.d_truncated; p.stepped = e->b.d_stepped;
+  p.map_idx_out = reinterpret_cast<long long*>(e->b.d_map_idx); p.cells = e->b.d_cells; p.dists = e->b.d_dists;
+  p.reward2 = reward2; p.done2 = done2; p.err = e->d_err;
+  const int groups_per_block = kThreads / e->G;
+  const int grid = apg::ceil_div(c.num_envs, groups_per_block);
+  lidar_step_kernel<<<grid, kThreads, e->smem, e->stream>>>(p);
+  APG_CUDA(cudaGetLastError());
+  apg::count_launch();
+  return APG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
+  APG_CHECK(cfg && out, APG_ERR_INVALID, "apg_lidar_create: null argument");
+  *out = nullptr;
+  APG_CHECK(cfg->num_envs > 0, APG_ERR_INVALID, "num_envs must be positive");
+  APG_CHECK(cfg->width > 0 && cfg->height > 0 && cfg->width <= 4096 && cfg->height <= 4096, APG_ERR_INVALID, "bad map size");
+  APG_CHECK(cfg->beam_count > 0 && cfg->beam_count <= 4096, APG_ERR_INVALID, "bad lidar_beam_count");
+  APG_CHECK(cfg->lidar_range > 0, APG_ERR_INVALID, "bad lidar_range");
+  APG_CHECK(cfg->step_limit > 0, APG_ERR_INVALID, "bad step_limit");
+  int ndev = 0;
+  cudaError_t de = cudaGetDeviceCount(&ndev);
+  if (de != cudaSuccess || ndev <= 0)
+    return apg::fail(APG_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                     cudaGetErrorString(de));
+  APG_CHECK(cfg->device >= 0 && cfg->device < ndev, APG_ERR_INVALID, "device %d out of range", cfg->device);
+  APG_CUDA(cudaSetDevice(cfg->device));
+  apg_lidar_env* e = new apg_lidar_env();
+  e->cfg = *cfg;
+  e->words = (cfg->width + 31) / 32;
+  int G = 1;
+  while (G < cfg->beam_count && G < 32) G <<= 1;
+  if (G < 4) G = 4;
+  e->G = G;
+  e->smem = (size_t)(kThreads / G) * cfg->height * e->words * sizeof(unsigned);
+  const size_t N = cfg->num_envs, B = cfg->beam_count;
+  cudaError_t err = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+  A(apg::dev_alloc(&e->b.d_lidar, N * B));
+  A(apg::dev_alloc(&e->b.d_odometry, N * 2));
+  A(apg::dev_alloc(&e->b.d_time_step, N));
+  if (!cfg->static_map) A(apg::dev_alloc(&e->b.d_map, N * cfg->height * cfg->width));
+  A(apg::dev_alloc(&e->b.d_reward, N));
+  A(apg::dev_alloc(&e->b.d_base_reward, N));
+  A(apg::dev_alloc(&e->b.d_loss, N));
+  A(apg::dev_alloc(&e->b.d_target, N * 2));
+  A(apg::dev_alloc(&e->b.d_terminated, N));
+  A(apg::dev_alloc(&e->b.d_truncated, N));
+  A(apg::dev_alloc(&e->b.d_stepped, N));
+  A(apg::dev_alloc(&e->b.d_map_idx, N));
+  A(apg::dev_alloc(&e->b.d_pos, N * 2));
+  A(apg::dev_alloc(&e->b.d_initial_pos, N * 2));
+  if (cfg->emit_cells) {
+    A(apg::dev_alloc(&e->b.d_cells, N * B * 2));
+    A(apg::dev_alloc(&e->b.d_dists, N * B));
+  }
+  A(apg::dev_alloc(&e->d_aliased, N));
+  A(apg::dev_alloc(&e->d_elapsed, N));
+  A(apg::dev_alloc(&e->d_map_idx, N));
+  A(apg::dev_alloc(&e->d_prev_done, N));
+  A(apg::dev_alloc(&e->d_g0, N));
+  A(apg::dev_alloc(&e->d_g2, N));
+  A(apg::dev_alloc(&e->d_err, 1));
+  A(apg::dev_alloc(&e->d_in_action, N * 2));
+  A(apg::dev_alloc(&e->d_in_pred, N * 2));
+  A(apg::dev_alloc(&e->d_dirs, B * 2));
+  if (err == cudaSuccess && e->smem > 48 * 1024)
+    A(cudaFuncSetAttribute(lidar_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  if (err != cudaSuccess) {
+    apg_lidar_destroy(e);
+    return apg::fail(APG_ERR_CUDA, "apg_lidar_create: allocation failed: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return APG_OK;
+}
+
+void apg_lidar_destroy(apg_lidar_env* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  apg::dev_free(e->d_bank); apg::dev_free(e->d_dirs);
+  apg::dev_free(e->b.d_lidar); apg::dev_free(e->b.d_odometry); apg::dev_free(e->b.d_time_step); apg::dev_free(e->b.d_map);
+  apg::dev_free(e->b.d_reward); apg::dev_free(e->b.d_base_reward); apg::dev_free(e->b.d_loss); apg::dev_free(e->b.d_target);
+  apg::dev_free(e->b.d_terminated); apg::dev_free(e->b.d_truncated); apg::dev_free(e->b.d_stepped);
+  apg::dev_free(e->b.d_map_idx); apg::dev_free(e->b.d_pos); apg::dev_free(e->b.d_initial_pos);
+  apg::dev_free(e->b.d_cells); apg::dev_free(e->b.d_dists);
+  apg::dev_free(e->d_aliased); apg::dev_free(e->d_elapsed); apg::dev_free(e->d_map_idx); apg::dev_free(e->d_prev_done);
+  apg::dev_free(e->d_g0); apg::dev_free(e->d_g2); apg::dev_free(e->d_err);
+  apg::dev_free(e->d_in_action); apg::dev_free(e->d_in_pred);
+  delete e;
+}
+
+int apg_lidar_set_stream(apg_lidar_env* e, void* cuda_stream) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  e->stream = static_cast<cudaStream_t>(cuda_stream);
+  return APG_OK;
+}
+
+int apg_lidar_set_map_bank(apg_lidar_env* e, const uint32_t* h_bits, int64_t n_maps) {
+  APG_CHECK(e && h_bits && n_maps > 0 && n_maps <= 0xFFFFFFFFll, APG_ERR_INVALID, "apg_lidar_set_map_bank: bad argument");
+  APG_CHECK(!e->cfg.static_map || e->cfg.static_map_index < n_maps, APG_ERR_INVALID, "static_map_index out of range");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  apg::dev_free(e->d_bank);
+  const size_t count = (size_t)n_maps * e->cfg.height * e->words;
+  // every map needs at least one free cell (the reference would raise in integers(0, 0))
+  for (int64_t m = 0; m < n_maps; ++m) {
+    bool any_free = false;
+    for (int y = 0; y < e->cfg.height && !any_free; ++y)
+      for (int x = 0; x < e->cfg.width; ++x)
+        if (!((h_bits[((size_t)m * e->cfg.height + y) * e->words + (x >> 5)] >> (x & 31)) & 1u)) { any_free = true; break; }
+    APG_CHECK(any_free, APG_ERR_INVALID, "map %lld has no free cell", (long long)m);
+  }
+  APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_bank), count * sizeof(uint32_t)));
+  APG_CUDA(cudaMemcpy(e->d_bank, h_bits, count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  e->n_maps = n_maps;
+  return APG_OK;
+}
+
+int apg_lidar_set_beams(apg_lidar_env* e, const float* h_dirs) {
+  APG_CHECK(e && h_dirs, APG_ERR_INVALID, "apg_lidar_set_beams: null argument");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaMemcpy(e->d_dirs, h_dirs, (size_t)e->cfg.beam_count * 2 * sizeof(float), cudaMemcpyHostToDevice));
+  e->have_beams = true;
+  return APG_OK;
+}
+
+int apg_lidar_reset(apg_lidar_env* e, uint64_t seed) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  APG_CHECK(e->d_bank && e->have_beams, APG_ERR_STATE, "apg_lidar_reset before set_map_bank / set_beams");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  int rc = lidar_launch(e, 2, seed, nullptr, nullptr, nullptr, nullptr);
+  if (rc != APG_OK) return rc;
+  e->has_reset = true;
+  return APG_OK;
+}
+
+int apg_lidar_step(apg_lidar_env* e, const float* d_action, const float* d_pred) {
+  APG_CHECK(e && d_action && d_pred, APG_ERR_INVALID, "apg_lidar_step: null argument");
+  APG_CHECK(e->has_reset, APG_ERR_STATE, "step before reset (the first reset must be seeded)");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  return lidar_launch(e, 0, 0, d_action, d_pred, nullptr, nullptr);
+}
+
+int apg_lidar_rollout(apg_lidar_env* e, const float* d_actions, const float* d_preds, int32_t n_steps, float* d_rewards,
+                      uint8_t* d_dones) {
+  APG_CHECK(e && d_actions && d_preds && n_steps >= 0, APG_ERR_INVALID, "apg_lidar_rollout: bad argument");
+  APG_CHECK(e->has_reset, APG_ERR_STATE, "rollout before reset");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  const size_t N = e->cfg.num_envs;
+  for (int k = 0; k < n_steps; ++k) {
+    int rc = lidar_launch(e, 0, 0, d_actions + (size_t)k * N * 2, d_preds + (size_t)k * N * 2,
+                          d_rewards ? d_rewards + (size_t)k * N : nullptr, d_dones ? d_dones + (size_t)k * N : nullptr);
+    if (rc != APG_OK) return rc;
+  }
+  return APG_OK;
+}
+
+int apg_lidar_step_host(apg_lidar_env* e, const float* h_action, const float* h_pred, float* h_reward,
+                        uint8_t* h_terminated, uint8_t* h_truncated, float* h_lidar) {
+  APG_CHECK(e && h_action && h_pred, APG_ERR_INVALID, "apg_lidar_step_host: null argument");
+  APG_CHECK(e->has_reset, APG_ERR_STATE, "step before reset");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  const size_t N = e->cfg.num_envs;
+  APG_CUDA(cudaMemcpyAsync(e->d_in_action, h_action, N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  APG_CUDA(cudaMemcpyAsync(e->d_in_pred, h_pred, N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  int rc = lidar_launch(e, 0, 0, e->d_in_action, e->d_in_pred, nullptr, nullptr);
+  if (rc != APG_OK) return rc;
+  if (h_reward) APG_CUDA(cudaMemcpyAsync(h_reward, e->b.d_reward, N * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (h_terminated) APG_CUDA(cudaMemcpyAsync(h_terminated, e->b.d_terminated, N, cudaMemcpyDeviceToHost, e->stream));
+  if (h_truncated) APG_CUDA(cudaMemcpyAsync(h_truncated, e->b.d_truncated, N, cudaMemcpyDeviceToHost, e->stream));
+  if (h_lidar)
+    APG_CUDA(cudaMemcpyAsync(h_lidar, e->b.d_lidar, N * e->cfg.beam_count * 4, cudaMemcpyDeviceToHost, e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  return APG_OK;
+}
+
+int apg_lidar_get_buffers(apg_lidar_env* e, apg_lidar_buffers* out) {
+  APG_CHECK(e && out, APG_ERR_INVALID, "null argument");
+  *out = e->b;
+  return APG_OK;
+}
+
+int apg_lidar_poll_error(apg_lidar_env* e, uint32_t* flags, int clear) {
+  APG_CHECK(e && flags, APG_ERR_INVALID, "null argument");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaMemcpyAsync(flags, e->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
+  if (clear) APG_CUDA(cudaMemsetAsync(e->d_err, 0, 4, e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  return APG_OK;
+}
+
+int apg_lidar_sync(apg_lidar_env* e) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  return APG_OK;
+}
+
+// ---- host-side test hook for the numpy-compatible random streams (apg_rng.h) -----------------------------
+// op: 0 next64, 1 next32, 2 integers(0, arg), 3 integers(0, 2**32, endpoint=True), 4 re-seed with SeedSequence(arg)
+int apg_rng_host_stream(uint64_t seed, int32_t n_ops, const int32_t* op, const uint64_t* arg, uint64_t* out) {
+  APG_CHECK(n_ops >= 0 && (n_ops == 0 || (op && arg && out)), APG_ERR_INVALID, "apg_rng_host_stream: bad argument");
+  apg::Pcg64 g;
+  apg::pcg64_seed(g, seed);
+  for (int i = 0; i < n_ops; ++i) {
+    switch (op[i]) {
+      case 0: out[i] = apg::pcg64_next64(g); break;
+      case 1: out[i] = apg::pcg64_next32(g); break;
+      case 2: out[i] = apg::rng_integers_below(g, arg[i]); break;
+      case 3: out[i] = apg::rng_integers_0_to_2p32_inclusive(g); break;
+      case 4: apg::pcg64_seed(g, arg[i]); out[i] = 0; break;
+      default: return apg::fail(APG_ERR_INVALID, "bad op %d", op[i]);
+    }
+  }
+  return APG_OK;
+}
+
+}  // extern "C"

@@ -147,6 +147,77 @@ int apg_image_poll_error(apg_image_env* env, uint32_t* flags, int clear);
 int apg_image_sync(apg_image_env* env);
 
 /* ------------------------------------------------------------------------------------------------------
+ * LIDAR localisation environments.  One handle = one shard of the vector env that
+ * `ap_gym.make_vec("LIDARLoc{Rooms,Maze}[Static]-v0", num_envs=N)` builds, i.e. it replaces
+ *   gymnasium.vector.SyncVectorEnv over N python envs (NEXT_STEP autoreset)  ap_gym/envs/registration.py:753-767
+ *   TimeLimit(max_episode_steps, issue_termination=True).step/reset          ap_gym/time_limit.py:113-152
+ *   ActivePerceptionEnv.step (loss + reward)                                 ap_gym/active_perception_env.py:101-121
+ *   LIDARLocalization2DEnv.reset/_step/__get_obs/__lidar_scan                ap_gym/envs/lidar_localization2d.py:238-536
+ *   the per-env numpy Generators of the reset path                            ap_gym/envs/lidar_localization2d.py:303-311,547-557
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct apg_lidar_env apg_lidar_env;
+
+typedef struct {
+  int32_t device;           /* CUDA device ordinal */
+  int32_t num_envs;         /* N of this shard */
+  int32_t width, height;    /* dataset.map_width / map_height */
+  int32_t beam_count;       /* lidar_beam_count */
+  float lidar_range;        /* lidar_range */
+  int32_t step_limit;       /* TimeLimit max_episode_steps (100 for the registered ids) */
+  int32_t static_map;       /* static_map */
+  int32_t static_map_index; /* static_map_index */
+  int32_t emit_cells;       /* also write the per-beam contact cells and raw distances (parity / rendering) */
+  int64_t env_offset;       /* global index of env 0 of this shard: env i is seeded with seed + env_offset + i */
+} apg_lidar_cfg;
+
+typedef struct {
+  float* d_lidar;        /* (N, B)      obs["lidar"]                                   */
+  float* d_odometry;     /* (N, 2)      obs["odometry"]                                */
+  float* d_time_step;    /* (N,)        obs["time_step"]                               */
+  float* d_map;          /* (N, H, W)   obs["map"] in {0, 1/255} (dynamic maps only; rewritten on reset) */
+  float* d_reward;       /* (N,)  0 on autoreset steps                                 */
+  float* d_base_reward;  /* (N,)  info["base_reward"]                                  */
+  float* d_loss;         /* (N,)  info["prediction"]["loss"]                           */
+  float* d_target;       /* (N,2) info["prediction"]["target"]                         */
+  uint8_t* d_terminated; /* (N,)                                                       */
+  uint8_t* d_truncated;  /* (N,)                                                       */
+  uint8_t* d_stepped;    /* (N,)  1 = real step, 0 = autoreset step (gymnasium's `_key` info masks) */
+  int64_t* d_map_idx;    /* (N,)  info["map_idx"]                                      */
+  float* d_pos;          /* (N,2) state: position in map cells (x, y)                  */
+  float* d_initial_pos;  /* (N,2) state: odometry origin                               */
+  int32_t* d_cells;      /* (N,B,2) contact cell (x, y) or (-1,-1) per beam (emit_cells) */
+  float* d_dists;        /* (N,B)   raw float32 scan distances (emit_cells)            */
+} apg_lidar_buffers;
+
+int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out);
+void apg_lidar_destroy(apg_lidar_env* env);
+int apg_lidar_set_stream(apg_lidar_env* env, void* cuda_stream);
+/* Upload the bit-packed occupancy bank: h_bits (n_maps, H, ceil(W/32)) uint32, bit x&31 of word x>>5 = wall.
+ * Replaces the per-episode dataset fetch + shapely union (lidar_localization2d.py:279-291,298). */
+int apg_lidar_set_map_bank(apg_lidar_env* env, const uint32_t* h_bits, int64_t n_maps);
+/* Upload lidar_directions (B,2) float32 = (cos, sin)(linspace(-pi, pi, B, endpoint=False)) * range, computed by
+ * the caller exactly like lidar_localization2d.py:180-187 (numpy float32 cos/sin). */
+int apg_lidar_set_beams(apg_lidar_env* env, const float* h_dirs);
+/* reset(seed=seed): seeds env i with seed + env_offset + i and resets every env.  Asynchronous. */
+int apg_lidar_reset(apg_lidar_env* env, uint64_t seed);
+/* One vector step, DEVICE inputs d_action (N,2), d_pred (N,2) float32.  One kernel launch, asynchronous. */
+int apg_lidar_step(apg_lidar_env* env, const float* d_action, const float* d_pred);
+int apg_lidar_rollout(apg_lidar_env* env, const float* d_actions, const float* d_preds, int32_t n_steps,
+                      float* d_rewards, uint8_t* d_dones);
+/* One vector step with HOST buffers in and out (reward f32, terminated/truncated u8, optional lidar); syncs. */
+int apg_lidar_step_host(apg_lidar_env* env, const float* h_action, const float* h_pred, float* h_reward,
+                        uint8_t* h_terminated, uint8_t* h_truncated, float* h_lidar);
+int apg_lidar_get_buffers(apg_lidar_env* env, apg_lidar_buffers* out);
+int apg_lidar_poll_error(apg_lidar_env* env, uint32_t* flags, int clear);
+int apg_lidar_sync(apg_lidar_env* env);
+
+/* Host-side test hook for the numpy-compatible random streams used on the device reset path (csrc/apg_rng.h):
+ * a Generator(PCG64(SeedSequence(seed))) driven by n_ops operations --
+ * op 0 next raw uint64, 1 next buffered uint32, 2 integers(0, arg), 3 integers(0, 2**32, endpoint=True),
+ * 4 re-seed with SeedSequence(arg).  out[i] receives the result of operation i. */
+int apg_rng_host_stream(uint64_t seed, int32_t n_ops, const int32_t* op, const uint64_t* arg, uint64_t* out);
+
+/* ------------------------------------------------------------------------------------------------------
  * DLPack export of engine-owned device memory (north_star: PyTorch only sees DLPack tensors).
  * Returns a malloc'ed DLManagedTensor* (DLPack v0.8 layout) whose deleter frees only the descriptor.
  * dtype_code: 0 int, 1 uint, 2 float (DLDataTypeCode); bits: 8/32/64.
