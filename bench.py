@@ -33,7 +33,13 @@ WORKLOADS = {
                   n_envs=65536, bytes_per_step=300),
     "tinyloc": dict(desc="TinyImageNetLoc-v0 shape: synthetic 100000x64x64x3 u8 bank, ImageLocalizationVectorEnv, S=10, T=16",
                     n_envs=131072, bytes_per_step=1930),
+    "lidar_rooms": dict(desc="LIDARLocRooms-v0: 4096 procedural 32x32 rooms maps (reference generator), 64 beams, range 5, T=100",
+                        n_envs=262144, bytes_per_step=510),
+    "lidar_maze": dict(desc="LIDARLocMaze-v0 large: 256 procedural 63x63 mazes (reference generator), 256 beams, range 5, T=100",
+                       n_envs=131072, bytes_per_step=1800),
 }
+LIDAR = {"lidar_rooms": ("maps_rooms32.npz", 64), "lidar_maze": ("maps_maze63.npz", 256)}
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def parse():
@@ -118,6 +124,8 @@ def cpu_oracle_run(workload: str, n_envs: int, steps: int, seed: int = 0):
         imgs, labels = synthetic_u8_bank(seed=0, M=512, H=64, W=64, C=3, K=200)
         env = ImageEnvOracle(imgs, labels, n_envs, task="loc", num_classes=200, sensor_size=(10, 10), track_overlay=False)
         pw = 2
+    elif workload in LIDAR:
+        return cpu_lidar_run(workload, n_envs, steps, seed)
     else:
         raise ValueError(workload)
     rng = np.random.default_rng(seed)
@@ -131,6 +139,28 @@ def cpu_oracle_run(workload: str, n_envs: int, steps: int, seed: int = 0):
         env.step(a[s], p[s])
     t0 = time.perf_counter()
     for s in range(steps):
+        env.step(a[s], p[s])
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def cpu_lidar_run(workload: str, n_envs: int, steps: int, seed: int = 0):
+    from oracle.lidar_oracle import LidarVecOracle
+
+    fname, beams = LIDAR[workload]
+    z = np.load(os.path.join(GOLDEN, fname))
+    W = int(z["width"])
+    x = np.arange(W)
+    maps = ((z["bits"][:64, :, x >> 5] >> (x & 31).astype(np.uint32)) & 1).astype(bool)
+    env = LidarVecOracle(maps, n_envs, beam_count=beams)
+    env.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-1, 1, (steps + 3, n_envs, 2)).astype(np.float32)
+    p = rng.uniform(-1, 1, (steps + 3, n_envs, 2)).astype(np.float32)
+    for s in range(3):
+        env.step(a[s], p[s])
+    t0 = time.perf_counter()
+    for s in range(3, steps + 3):
         env.step(a[s], p[s])
     dt = time.perf_counter() - t0
     return n_envs * steps / dt, dt
@@ -160,7 +190,7 @@ def run_reference_arm(args):
     w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
-    n_envs = 4096 if args.workload == "mnist" else 256
+    n_envs = {"mnist": 4096, "tinyloc": 256, "lidar_rooms": 1024, "lidar_maze": 128}[args.workload]
     steps_per = 17
     vals = []
     for _ in range(max(1, args.warmup // 17)):
@@ -172,7 +202,7 @@ def run_reference_arm(args):
         vals.append(v)
     wall = time.perf_counter() - t0
     value = float(np.median(vals))
-    sample = f"{procs} processes x {n_envs} envs x {steps_per} steps of the numpy restatement (oracle/), median of {reps}"
+    sample = f"{procs} processes x {n_envs} envs x {steps_per} steps of the CPU restatement (oracle/), median of {reps}"
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs * procs / value,
@@ -197,6 +227,12 @@ def build_env(args, rank, world, device):
         env = apg.ImageClassificationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
                                                check_errors="never", payload_ring=64)
         pw = 10
+    elif args.workload in LIDAR:
+        fname, beams = LIDAR[args.workload]
+        bank = apg.FloorMapBank.load_npz(os.path.join(GOLDEN, fname), args.bank or None)
+        env = apg.LIDARLocalization2DVectorEnv(n, bank, lidar_beam_count=beams, device=device, env_offset=rank * n,
+                                               check_errors="never")
+        pw = 2
     else:
         ds = apg.SyntheticImageDataset("tinyimagenet", length=args.bank or None, seed=0)
         cfg = apg.ImagePerceptionConfig(dataset=ds, sensor_size=(10, 10))
@@ -226,6 +262,7 @@ def main():
 
     w = WORKLOADS[args.workload]
     env, n, pw = build_env(args, rank, world, local_rank)
+    is_lidar = args.workload in LIDAR
     T = 16
     K, W = args.steps, args.warmup
     dev = torch.device("cuda", local_rank)
@@ -255,18 +292,20 @@ def main():
     # pre-draw the autoreset payloads of warm-up + timed region so the timed region is device-only
     run(0, W)
     barrier()
-    # queue as many payloads as the timed region needs (ring depth 64 >= K/17 + 1 for the default K)
-    b = env._buffers()
-    t_, need, resets = b.elapsed, bool(b.needs_reset), 0
-    for _ in range(K):
-        if need:
-            resets, t_, need = resets + 1, 0, False
-        else:
-            t_ += 1
-            need = t_ >= T
-    pre = min(resets, 64) - env._lib.apg_image_pending_payloads(env._h)
-    if pre > 0:
-        env.queue_autoreset_payloads(pre)
+    # queue as many payloads as the timed region needs (ring depth 64 >= K/17 + 1 for the default K);
+    # the LIDAR engine draws its resets on the device, nothing to stage
+    if not is_lidar:
+        b = env._buffers()
+        t_, need, resets = b.elapsed, bool(b.needs_reset), 0
+        for _ in range(K):
+            if need:
+                resets, t_, need = resets + 1, 0, False
+            else:
+                t_ += 1
+                need = t_ >= T
+        pre = min(resets, 64) - env._lib.apg_image_pending_payloads(env._h)
+        if pre > 0:
+            env.queue_autoreset_payloads(pre)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -299,6 +338,10 @@ def main():
     lib = _capi.lib()
 
     def e2e_step():
+        if is_lidar:
+            _capi.check(lib.apg_lidar_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
+                                                h_tr.data_ptr(), None))
+            return
         if env._buffers().needs_reset and lib.apg_image_pending_payloads(env._h) == 0:
             env.queue_autoreset_payloads(1)
         _capi.check(lib.apg_image_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
@@ -344,19 +387,19 @@ def main():
                        "l2": "per-step inputs are distinct and streamed from HBM (%.0f MB total > 126 MB L2); engine-owned obs buffers are rewritten every step" % (acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "apg_image_step_host (pinned host action/prediction in, reward/terminated/truncated out)"},
+                    "steps": Ke, "api": ("apg_lidar_step_host" if is_lidar else "apg_image_step_host") + " (pinned host action/prediction in, reward/terminated/truncated out)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "kernel": "image_step_kernel", "bytes_per_env_step": w["bytes_per_step"],
+                         "kernel": "lidar_step_kernel" if is_lidar else "image_step_kernel", "bytes_per_env_step": w["bytes_per_step"],
                          "avg_launch_us": avg_launch_s * 1e6},
             "final_stats_allreduce": {"mean_reward_last_step": float(stats[0] / stats[2]), "mean_loss_last_step": float(stats[1] / stats[2])},
         }
         if not args.no_cpu_baseline and world == 1:
-            n_cpu = 4096 if args.workload == "mnist" else 256
-            v, dt = cpu_oracle_run(args.workload, n_cpu, 34)
+            n_cpu, st_cpu = {"mnist": (4096, 680), "tinyloc": (256, 1020), "lidar_rooms": (2048, 303), "lidar_maze": (256, 808)}[args.workload]
+            v, dt = cpu_oracle_run(args.workload, n_cpu, st_cpu)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                    "sample": f"numpy restatement (oracle/image_oracle.py), 1 process, N={n_cpu} x 34 steps, {dt:.1f} s"}
+                                    "sample": f"CPU restatement (oracle/), 1 process, N={n_cpu} x {st_cpu} steps, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
