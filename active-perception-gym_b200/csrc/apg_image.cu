@@ -13,12 +13,11 @@
 //
 // Numerics: the file is compiled with -fmad=false, every float op below is a separately rounded IEEE op in
 // the order numpy performs it (see oracle/image_oracle.py).  uint8 banks are converted with the reference's
-// f32(u8)/255 through a 256-entry shared-memory table filled with __fdiv_rn.
+// f32(u8)/255, reproduced exactly by a multiply + two explicit fma corrections (px_to_f64).
 //
-// Thread mapping: a block owns E consecutive environments.  Phase A: thread e (< E) does the per-environment
-// scalar work and leaves tap rows/columns + float64 weights in shared memory.  Phase B: all threads sweep the
-// block's contiguous (E * S0*S1*C) output floats, 4 consecutive floats per thread -> one 128-bit coalesced
-// store each; bank taps are byte/float gathers served by L1/L2 (footprint (S0+1) x (S1+1) x C per glimpse).
+// Thread mapping: a group of g lanes owns one environment (see image_step_kernel): scalars are spread over /
+// replicated across the group, then lane = (column, channel) of the sensor window walks the sensor rows with a
+// two-deep software pipeline on the bank loads; loads are contiguous row segments, stores contiguous runs.
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -27,12 +26,12 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kMaxK = 4096;
 
 struct ImgParams {
   int N, H, W, C, S0, S1, P, K, task, invert, track, words, T;
-  int E;             // environments per block
+  int g, log2g;      // lanes per environment (power of two, <= 32)
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
   int t_stamp;       // overlay stamp slot of this step (pre-move time index), mode 0 only
   float time_obs;    // obs["time_step"] value after this step
@@ -90,276 +89,357 @@ __device__ __forceinline__ void tap(double coord, double off, int len, int& k_ou
   w_out = coord - ((double)k - off);
 }
 
-__device__ __forceinline__ float load_px(const unsigned char* img, long long o, const float* lut) {
-  return lut[__ldg(img + o)];
+// bank pixel -> the float64 value the reference blends with: float64(float32(u8) / 255) or float64(f32 pixel).
+// float32(u8)/255 is reproduced exactly (all 256 values, tests/test_capi_symbols.py) by q0 = u*r,
+// q = fma(fma(-255, q0, u), r, q0) with r = float32(1/255): no table, no division.
+__device__ __forceinline__ double px_to_f64(unsigned char u) {
+  const float r = 0.003921568859368563f;  // float32(1)/float32(255)
+  const float uf = (float)u;
+  const float q0 = __fmul_rn(uf, r);
+  const float e = __fmaf_rn(-255.0f, q0, uf);
+  return (double)__fmaf_rn(e, r, q0);
 }
-__device__ __forceinline__ float load_px(const float* img, long long o, const float*) { return __ldg(img + o); }
+__device__ __forceinline__ double px_to_f64(float v) { return (double)v; }
 
-template <typename BankT>
+// An environment is owned by a group of g = min(32, pow2 >= S1*C) lanes (a whole warp for a 10x10x3 sensor, 8 lanes
+// for a 5x5x1 one); a warp steps 32/g environments in lock-step.
+//   phase A  per-environment scalars, spread over the group: lane k reduces logit k (shuffle max/sum), lane i
+//            computes the tap of sensor row i, every lane its own column tap; the short scalar chain (move,
+//            reward, flags) is evaluated redundantly by all lanes of the group, the leader stores it.
+//   phase B  lane = (column, channel) of the sensor window; the group walks the S0 sensor rows.  Every bank load is
+//            one contiguous row segment per group, the bottom taps of row i are the top taps of row i+1, and the
+//            bottom row is fetched two iterations ahead (software pipeline) so the L2/HBM latency overlaps the
+//            float64 blend.  Output rows are stored as contiguous runs.  The blend is the reference's 4-term
+//            float64 sum in the same order (bit-exact pixels).
+template <typename BankT, int S0T, int CT>
 __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // shared layout: lut[256] | base[2E] (long long) | wy[2][E*S0] wx[2][E*S1] (double) | ti[2][E*S0] tj[2][E*S1] (int)
-  float* lut = reinterpret_cast<float*>(smem_raw);
-  long long* s_base = reinterpret_cast<long long*>(smem_raw + 1024);
-  double* s_wy = reinterpret_cast<double*>(s_base + p.E);
-  double* s_wx = s_wy + 2 * p.E * p.S0;
-  int* s_ti = reinterpret_cast<int*>(s_wx + 2 * p.E * p.S1);
-  int* s_tj = s_ti + 2 * p.E * p.S0;
-
   const int tid = threadIdx.x;
-  const int env0 = blockIdx.x * p.E;
-  const int nE = min(p.E, p.N - env0);
+  const int lane = tid & 31;
+  const int g = p.g;
+  const int li = lane & (g - 1);
+  const int gbase = lane - li;  // first lane of this group inside the warp
+  const int grp_in_block = tid >> p.log2g;
+  const int n = blockIdx.x * (kThreads >> p.log2g) + grp_in_block;
+  const bool act = n < p.N;
+  const int nn = act ? n : p.N - 1;  // inactive groups shadow the last environment but store nothing
+  const unsigned FULL = 0xffffffffu;
+  const bool lead = act && (li == 0);
   const bool two_sets = (p.task == APG_TASK_LOCALIZATION) && (p.mode != 0);
 
-  if (sizeof(BankT) == 1) lut[tid] = __fdiv_rn((float)tid, 255.0f);
+  // ------------------------------------------------------------------ phase A
+  unsigned err = 0;
+  double px, py;
+  int idx;
+  float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
+  double neg_loss_d = 0.0;
+  double tcx = 0.0, tcy = 0.0;
+  if (p.mode == 0) {
+    const double2 pp = reinterpret_cast<const double2*>(p.pos)[nn];
+    px = pp.x;
+    py = pp.y;
+    idx = p.st_idx[nn];
+  } else {
+    const long long ni = p.new_idx[nn];
+    idx = (int)ni;
+    const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[nn];
+    px = pp.x;
+    py = pp.y;
+    if (lead) {
+      p.st_idx[nn] = idx;
+      p.index[nn] = ni;
+    }
+  }
 
-  // ------------------------------------------------------------------ phase A: per-environment scalars
-  if (tid < nE) {
-    const int n = env0 + tid;
-    unsigned err = 0;
-    double px, py;
-    int idx;
-    float base = 0.0f;
-    float pq = 0.0f;
+  if (p.task == APG_TASK_CLASSIFICATION) {
+    int label;
+    unsigned char inv = 0;
     if (p.mode == 0) {
-      px = p.pos[2 * n];
-      py = p.pos[2 * n + 1];
-      idx = p.st_idx[n];
+      label = p.st_label[nn];
     } else {
-      const long long ni = p.new_idx[n];
-      idx = (int)ni;
-      px = p.new_pos[2 * n];
-      py = p.new_pos[2 * n + 1];
-      p.st_idx[n] = idx;
-      p.index[n] = ni;
+      label = p.bank_labels[idx];
+      if (p.invert) {
+        inv = p.new_inv[nn];
+        if (inv) label = p.K - label - 1;
+        if (lead) p.st_inv[nn] = inv;
+      }
+      if (lead) p.st_label[nn] = label;
     }
-
-    // ---- labels / targets and the loss (the reset step still charges a loss)
-    float loss_f = 0.0f;
-    double reward_d = 0.0;
-    if (p.task == APG_TASK_CLASSIFICATION) {
-      int label;
-      if (p.mode == 0) {
-        label = p.st_label[n];
-      } else {
-        label = p.bank_labels[idx];
-        unsigned char inv = 0;
-        if (p.invert) {
-          inv = p.new_inv[n];
-          if (inv) label = p.K - label - 1;
-          p.st_inv[n] = inv;
-        }
-        p.st_label[n] = label;
-      }
-      if (p.invert) p.inverted_label[n] = (p.mode == 0) ? 2 : (int)p.st_inv[n];
-      p.target_label[n] = label;
-      if (p.mode != 2) {
-        const float* x = p.pred + (size_t)n * p.K;
-        float mx = -INFINITY;
-        bool has_nan = false;
-        for (int k = 0; k < p.K; ++k) {
-          const float v = x[k];
-          has_nan |= isnan(v);
-          mx = fmaxf(mx, v);
-        }
-        if (has_nan) err |= APG_FLAG_NAN_PRED;
-        if (!isfinite(mx)) mx = 0.0f;
-        float s = 0.0f;
-        for (int k = 0; k < p.K; ++k) s = __fadd_rn(s, expf(__fsub_rn(x[k], mx)));
-        const float tl = __fsub_rn(x[label], mx);
-        const float ce = -__fsub_rn(tl, logf(s));           // -log_softmax(x)[label], float32 like scipy
-        pq = __fdiv_rn(expf(tl), s);                        // softmax(x)[label]
-        const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
-        loss_f = (float)loss_d;
-        // base (float32) - loss (float64) -> float64; on the reset step base is 0.0
-        reward_d = -loss_d;  // base added below once known
-      }
-    } else {
-      float t0 = 0.f, t1 = 0.f;
-      if (p.mode != 2) {
-        t0 = p.st_target[2 * n];
-        t1 = p.st_target[2 * n + 1];
-        const float q0 = p.pred[2 * n], q1 = p.pred[2 * n + 1];
-        if (isnan(q0) || isnan(q1)) err |= APG_FLAG_NAN_PRED;
-        const float d0 = __fsub_rn(q0, t0), d1 = __fsub_rn(q1, t1);
-        const float mse = __fdiv_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), 2.0f);
-        loss_f = __fadd_rn(__fmul_rn(mse, p.mse_scale), p.mse_offset);
-        if (p.mode == 0) {
-          // prediction quality 1 - ||pred - target|| / sqrt(4) (float64 because np.sqrt(4) is np.float64)
-          const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
-          pq = (float)fmin(fmax(1.0 - (double)nrm / 2.0, 0.0), 1.0);
-        }
-        p.target_xy[2 * n] = t0;
-        p.target_xy[2 * n + 1] = t1;
-      }
-      if (p.mode != 0) {
-        t0 = p.new_target[2 * n];
-        t1 = p.new_target[2 * n + 1];
-        p.st_target[2 * n] = t0;
-        p.st_target[2 * n + 1] = t1;
-        if (p.mode == 2) {
-          p.target_xy[2 * n] = t0;
-          p.target_xy[2 * n + 1] = t1;
-        }
-        // taps of the target glimpse (float32 target promoted to float64)
-        const double cx = (double)t0 * p.lim_x, cy = (double)t1 * p.lim_y;
-        for (int i = 0; i < p.S0; ++i) {
-          const double y = cy + ((double)i - p.half0) * p.scale;
-          if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
-          tap(y, p.offy, p.H, s_ti[(p.E + tid) * p.S0 + i], s_wy[(p.E + tid) * p.S0 + i]);
-        }
-        for (int j = 0; j < p.S1; ++j) {
-          const double x = cx + ((double)j - p.half1) * p.scale;
-          if (x < -p.offx || x > p.offx) err |= APG_FLAG_OUT_OF_GRID;
-          tap(x, p.offx, p.W, s_tj[(p.E + tid) * p.S1 + j], s_wx[(p.E + tid) * p.S1 + j]);
-        }
-      }
+    if (lead) {
+      if (p.invert) p.inverted_label[nn] = (p.mode == 0) ? 2 : (int)inv;
+      p.target_label[nn] = label;
     }
-
-    // ---- move (mode 0): overlay stamp of the PRE-move position, then the float64 position update
-    if (p.mode == 0) {
-      const float a0 = p.action[2 * n], a1 = p.action[2 * n + 1];
-      if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
-      if (p.track) {
-        const int cxr = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-        const int cyr = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
-        p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = cxr;
-        p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + n] = cyr;
-        p.stamp_q[(size_t)p.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
+    if (p.mode != 2) {
+      // log-softmax over K logits spread over the group (float32 like scipy.special.log_softmax)
+      const float* x = p.pred + (size_t)nn * p.K;
+      float mx = -INFINITY;
+      bool has_nan = false;
+      for (int k = li; k < p.K; k += g) {
+        const float v = x[k];
+        has_nan |= isnan(v);
+        mx = fmaxf(mx, v);
       }
-      const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
-      float q0 = a0, q1 = a1;
-      if (m > 1.0f) {
-        const float den = fmaxf(m, 1.0f);
-        q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
-        q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
+      for (int o = g >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+      if (has_nan) err |= APG_FLAG_NAN_PRED;
+      if (!isfinite(mx)) mx = 0.0f;
+      float s = 0.0f, tl = 0.0f;
+      for (int k = li; k < p.K; k += g) {
+        const float z = __fsub_rn(x[k], mx);
+        if (k == label) tl = z;
+        s = __fadd_rn(s, expf(z));
       }
-      px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
-      py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
-      base = __fmul_rn(-m, 1e-3f);
+      for (int o = g >> 1; o > 0; o >>= 1) {
+        s = __fadd_rn(s, __shfl_xor_sync(FULL, s, o));
+        tl = __fadd_rn(tl, __shfl_xor_sync(FULL, tl, o));  // exactly one lane holds a non-zero value
+      }
+      const float ce = -__fsub_rn(tl, logf(s));
+      pq = __fdiv_rn(expf(tl), s);  // softmax(x)[label], overlay colour only
+      const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
+      loss_f = (float)loss_d;
+      neg_loss_d = -loss_d;
     }
-    p.pos[2 * n] = px;
-    p.pos[2 * n + 1] = py;
+  } else {
+    float t0 = 0.f, t1 = 0.f;
+    if (p.mode != 2) {
+      const float2 tt = reinterpret_cast<const float2*>(p.st_target)[nn];
+      t0 = tt.x;
+      t1 = tt.y;
+      const float2 qq = reinterpret_cast<const float2*>(p.pred)[nn];
+      if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
+      const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
+      const float ss = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
+      loss_f = __fadd_rn(__fmul_rn(__fdiv_rn(ss, 2.0f), p.mse_scale), p.mse_offset);
+      if (p.mode == 0)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64), overlay colour only
+        pq = (float)fmin(fmax(1.0 - (double)__fsqrt_rn(ss) / 2.0, 0.0), 1.0);
+      if (lead) reinterpret_cast<float2*>(p.target_xy)[nn] = make_float2(t0, t1);
+    }
+    if (p.mode != 0) {
+      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[nn];
+      if (lead) {
+        reinterpret_cast<float2*>(p.st_target)[nn] = nt;
+        if (p.mode == 2) reinterpret_cast<float2*>(p.target_xy)[nn] = nt;
+      }
+      tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
+      tcy = (double)nt.y * p.lim_y;
+    }
+  }
 
+  if (p.mode == 0) {
+    const float2 aa = reinterpret_cast<const float2*>(p.action)[nn];
+    const float a0 = aa.x, a1 = aa.y;
+    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
+    if (p.track && lead) {  // overlay stamp of the PRE-move position (image_perception_module.py:196,219-234)
+      p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + nn] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
+      p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + nn] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
+      p.stamp_q[(size_t)p.t_stamp * p.N + nn] = fminf(fmaxf(pq, 0.0f), 1.0f);
+    }
+    const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+    float q0 = a0, q1 = a1;
+    if (m > 1.0f) {
+      const float den = fmaxf(m, 1.0f);
+      q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
+      q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
+    }
+    px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
+    py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
+    base = __fmul_rn(-m, 1e-3f);
+  }
+  if (lead) {
+    reinterpret_cast<double2*>(p.pos)[nn] = make_double2(px, py);
     if (p.mode != 2) {
       float reward_f;
-      if (p.task == APG_TASK_CLASSIFICATION) reward_f = (float)((double)base + reward_d);
+      // classification: float32 base - float64 loss -> float64; localization stays float32 except on the reset
+      // step, whose base reward is np.zeros(N) (float64)
+      if (p.task == APG_TASK_CLASSIFICATION) reward_f = (float)((double)base + neg_loss_d);
       else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
-      p.reward[n] = reward_f;
-      p.base_reward[n] = base;
-      p.loss[n] = loss_f;
-      if (p.reward2) p.reward2[n] = reward_f;
-      if (p.done2) p.done2[n] = p.terminated;
+      p.reward[nn] = reward_f;
+      p.base_reward[nn] = base;
+      p.loss[nn] = loss_f;
+      if (p.reward2) p.reward2[nn] = reward_f;
+      if (p.done2) p.done2[nn] = p.terminated;
     }
-    p.terminated_out[n] = p.terminated;
-    p.truncated_out[n] = 0;
-    p.glimpse_pos[2 * n] = (float)px;
-    p.glimpse_pos[2 * n + 1] = (float)py;
-    p.time_step[n] = p.time_obs;
-
-    // ---- taps of the observation glimpse at the (new) position
-    {
-      const double cx = px * p.lim_x, cy = py * p.lim_y;
-      for (int i = 0; i < p.S0; ++i) {
-        const double y = cy + ((double)i - p.half0) * p.scale;
-        if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
-        tap(y, p.offy, p.H, s_ti[tid * p.S0 + i], s_wy[tid * p.S0 + i]);
-      }
-      for (int j = 0; j < p.S1; ++j) {
-        const double x = cx + ((double)j - p.half1) * p.scale;
-        if (x < -p.offx || x > p.offx) err |= APG_FLAG_OUT_OF_GRID;
-        tap(x, p.offx, p.W, s_tj[tid * p.S1 + j], s_wx[tid * p.S1 + j]);
-      }
-      s_base[tid] = (long long)idx * p.H * p.W * p.C;
-    }
-
-    // ---- visited bitmask: every tap row/column of the glimpse just observed
-    if (p.track) {
-      unsigned* vm = p.visited + (size_t)n * p.H * p.words;
-      if (p.mode != 0)
-        for (int r = 0; r < p.H * p.words; ++r) vm[r] = 0u;
-      for (int w = 0; w < p.words; ++w) {
-        unsigned bits = 0u;
-        for (int j = 0; j < p.S1; ++j) {
-          const int c0 = s_tj[tid * p.S1 + j];
-          if ((c0 >> 5) == w) bits |= 1u << (c0 & 31);
-          if (((c0 + 1) >> 5) == w) bits |= 1u << ((c0 + 1) & 31);
-        }
-        if (bits) {
-          int last = -1;  // tap rows are non-decreasing: skip rows already OR-ed
-          for (int i = 0; i < p.S0; ++i) {
-            const int r0 = s_ti[tid * p.S0 + i];
-            if (r0 > last) vm[r0 * p.words + w] |= bits;
-            if (r0 + 1 > last) vm[(r0 + 1) * p.words + w] |= bits;
-            last = r0 + 1;
-          }
-        }
-      }
-    }
-    if (err) atomicOr(p.err, err);
+    p.terminated_out[nn] = p.terminated;
+    p.truncated_out[nn] = 0;
+    reinterpret_cast<float2*>(p.glimpse_pos)[nn] = make_float2((float)px, (float)py);
+    p.time_step[nn] = p.time_obs;
   }
-  __syncthreads();
 
-  // ------------------------------------------------------------------ phase B: resample, 4 floats / thread
-  const BankT* bank = static_cast<const BankT*>(p.bank);
-  const int WC = p.W * p.C;
-  const int S1C = p.S1 * p.C;
-  const int total = nE * p.P;
-  const int groups = (total + 3) >> 2;
+  // ------------------------------------------------------------------ phase B
+  const int S0 = S0T ? S0T : p.S0;
+  const int C = CT ? CT : p.C;
+  const BankT* img = static_cast<const BankT*>(p.bank) + (long long)idx * p.H * p.W * C;
+  const int G = p.S1 * C;
+  const int WC = p.W * C;
+  const int n_chunks = (G + 31) >> 5;
   const int n_sets = two_sets ? 2 : 1;
+  unsigned colbits0 = 0u, colbits1 = 0u;
+  int vis_row = 0;  // lane li < S0 keeps the tap row of sensor row li (observation glimpse) for the visited mask
+
   for (int set = 0; set < n_sets; ++set) {
-    float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
-    const int so = set * p.E;
-    for (int q = tid; q < groups; q += kThreads) {
-      int e = q << 2;
-      int el = e / p.P;
-      int r = e - el * p.P;
-      int i = r / S1C;
-      int r2 = r - i * S1C;
-      int j = r2 / p.C;
-      int c = r2 - j * p.C;
-      float v[4];
+    const double ccx = (set == 0) ? px * p.lim_x : tcx;
+    const double ccy = (set == 0) ? py * p.lim_y : tcy;
+    float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)nn * p.P;
+    // lane li owns the tap of sensor row li (rows >= g are recomputed on the fly below)
+    int my_i0 = 0;
+    double my_wy = 0.0;
+    if (li < S0) {
+      const double y = ccy + ((double)li - p.half0) * p.scale;
+      if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
+      tap(y, p.offy, p.H, my_i0, my_wy);
+    }
+    if (set == 0) vis_row = my_i0;
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int jc = (chunk << 5) + li;
+      const bool col_ok = jc < G;
+      const int j = (C == 1) ? jc : ((C == 3) ? (int)(((unsigned)jc * 43691u) >> 17) : jc / C);
+      const int c = jc - j * C;
+      int j0 = 0;
+      double wx = 0.0;
+      {
+        const double x = ccx + ((double)min(j, p.S1 - 1) - p.half1) * p.scale;
+        if (col_ok && (x < -p.offx || x > p.offx)) err |= APG_FLAG_OUT_OF_GRID;
+        tap(x, p.offx, p.W, j0, wx);
+      }
+      if (set == 0 && col_ok) {
+        if ((j0 >> 5) == 0) colbits0 |= 1u << (j0 & 31);
+        else if ((j0 >> 5) == 1) colbits1 |= 1u << (j0 & 31);
+        if (((j0 + 1) >> 5) == 0) colbits0 |= 1u << ((j0 + 1) & 31);
+        else if (((j0 + 1) >> 5) == 1) colbits1 |= 1u << ((j0 + 1) & 31);
+      }
+      const double omx = 1.0 - wx;
+      const BankT* colp = img + (j0 * C + (col_ok ? c : 0));
+      float* outc = out + jc;
+      const bool st_ok = act && col_ok;
+
+      if (S0T > 0) {
+        // ---- compile-time sensor height: every bank load of the glimpse is issued before the first blend
+        int i0s[S0T > 0 ? S0T : 1];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (e + u < total) {
-          const BankT* img = bank + s_base[el];
-          const int i0 = s_ti[(so + el) * p.S0 + i];
-          const int j0 = s_tj[(so + el) * p.S1 + j];
-          const double wy = s_wy[(so + el) * p.S0 + i];
-          const double wx = s_wx[(so + el) * p.S1 + j];
-          const long long o00 = (long long)i0 * WC + j0 * p.C + c;
-          const double p00 = (double)load_px(img, o00, lut);
-          const double p01 = (double)load_px(img, o00 + p.C, lut);
-          const double p10 = (double)load_px(img, o00 + WC, lut);
-          const double p11 = (double)load_px(img, o00 + WC + p.C, lut);
-          const double omy = 1.0 - wy, omx = 1.0 - wx;
-          double acc = 0.0 + p00 * (omy * omx);
+        for (int i = 0; i < S0T; ++i) i0s[i] = __shfl_sync(FULL, my_i0, gbase + i);
+        BankT bot0[S0T > 0 ? S0T : 1], bot1[S0T > 0 ? S0T : 1];
+        const BankT* r0 = colp + i0s[0] * WC;
+        const BankT top0 = __ldg(r0), top1 = __ldg(r0 + C);
+#pragma unroll
+        for (int i = 0; i < S0T; ++i) {
+          const BankT* rp = colp + (i0s[i] + 1) * WC;
+          bot0[i] = __ldg(rp);
+          bot1[i] = __ldg(rp + C);
+        }
+        double p00 = px_to_f64(top0), p01 = px_to_f64(top1);
+#pragma unroll
+        for (int i = 0; i < S0T; ++i) {
+          const double wy = __shfl_sync(FULL, my_wy, gbase + i);
+          if (i > 0 && i0s[i] != i0s[i - 1] + 1) {  // clamped border: previous bottom row is not this top row
+            const BankT* rp = colp + i0s[i] * WC;
+            p00 = px_to_f64(__ldg(rp));
+            p01 = px_to_f64(__ldg(rp + C));
+          }
+          const double p10 = px_to_f64(bot0[i]), p11 = px_to_f64(bot1[i]);
+          const double omy = 1.0 - wy;
+          double acc = p00 * (omy * omx);  // 0.0 + x == x for x >= 0
           acc = acc + p01 * (omy * wx);
           acc = acc + p10 * (wy * omx);
           acc = acc + p11 * (wy * wx);
-          v[u] = (float)fmin(fmax(acc, 0.0), 1.0);
-          // advance (c, j, i, el) to the next output float
-          if (++c == p.C) {
-            c = 0;
-            if (++j == p.S1) {
-              j = 0;
-              if (++i == p.S0) {
-                i = 0;
-                ++el;
-              }
-            }
-          }
-        } else {
-          v[u] = 0.0f;
+          // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
+          const float v = (sizeof(BankT) == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
+          if (st_ok) outc[i * G] = v;
+          p00 = p10;
+          p01 = p11;
         }
-      }
-      if (e + 3 < total) {
-        *reinterpret_cast<float4*>(out + e) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
-        for (int u = 0; u < 4 && e + u < total; ++u) out[e + u] = v[u];
+        // ---- generic sensor height: two-deep software pipeline over the rows
+        auto row_tap = [&](int i, int& i0, double& wy) {
+          if (S0 <= g) {
+            i0 = __shfl_sync(FULL, my_i0, gbase + min(i, g - 1));
+            wy = __shfl_sync(FULL, my_wy, gbase + min(i, g - 1));
+          } else {
+            tap(ccy + ((double)i - p.half0) * p.scale, p.offy, p.H, i0, wy);
+          }
+        };
+        int i0_cur, i0_n1 = 0, i0_n2 = 0;
+        double wy_cur, wy_n1 = 0.0, wy_n2 = 0.0;
+        row_tap(0, i0_cur, wy_cur);
+        row_tap(1, i0_n1, wy_n1);
+        BankT top0 = __ldg(colp + i0_cur * WC);
+        BankT top1 = __ldg(colp + i0_cur * WC + C);
+        BankT bot0_a = __ldg(colp + (i0_cur + 1) * WC);
+        BankT bot1_a = __ldg(colp + (i0_cur + 1) * WC + C);
+        BankT bot0_b = bot0_a, bot1_b = bot1_a;
+        if (1 < S0) {
+          bot0_b = __ldg(colp + (i0_n1 + 1) * WC);
+          bot1_b = __ldg(colp + (i0_n1 + 1) * WC + C);
+        }
+        double p00 = px_to_f64(top0), p01 = px_to_f64(top1);
+        int prev_i0 = i0_cur - 1;
+        for (int i = 0; i < S0; ++i) {
+          BankT bot0_c = bot0_b, bot1_c = bot1_b;
+          if (i + 2 < S0) {
+            row_tap(i + 2, i0_n2, wy_n2);
+            bot0_c = __ldg(colp + (i0_n2 + 1) * WC);
+            bot1_c = __ldg(colp + (i0_n2 + 1) * WC + C);
+          }
+          if (i0_cur != prev_i0 + 1) {
+            p00 = px_to_f64(__ldg(colp + i0_cur * WC));
+            p01 = px_to_f64(__ldg(colp + i0_cur * WC + C));
+          }
+          const double p10 = px_to_f64(bot0_a), p11 = px_to_f64(bot1_a);
+          const double omy = 1.0 - wy_cur;
+          double acc = 0.0 + p00 * (omy * omx);
+          acc = acc + p01 * (omy * wx);
+          acc = acc + p10 * (wy_cur * omx);
+          acc = acc + p11 * (wy_cur * wx);
+          if (st_ok) outc[i * G] = (float)fmin(fmax(acc, 0.0), 1.0);
+          p00 = p10;
+          p01 = p11;
+          prev_i0 = i0_cur;
+          i0_cur = i0_n1; wy_cur = wy_n1;
+          i0_n1 = i0_n2; wy_n1 = wy_n2;
+          bot0_a = bot0_b; bot1_a = bot1_b;
+          bot0_b = bot0_c; bot1_b = bot1_c;
+        }
       }
     }
   }
+
+  // ------------------------------------------------------------------ visited bitmask (observation glimpse)
+  if (p.track) {
+    unsigned* vm = p.visited + (size_t)nn * p.H * p.words;
+    if (p.mode != 0) {
+      if (act)
+        for (int h = li; h < p.H * p.words; h += g) vm[h] = 0u;
+      __syncwarp(FULL);
+    }
+    for (int w = 0; w < p.words; ++w) {
+      unsigned my = (w == 0) ? colbits0 : ((w == 1) ? colbits1 : 0u);
+      if (w >= 2) {  // wide images: recompute this word's column bits
+        for (int jj = li; jj < p.S1; jj += g) {
+          int j0;
+          double wx;
+          tap(px * p.lim_x + ((double)jj - p.half1) * p.scale, p.offx, p.W, j0, wx);
+          if ((j0 >> 5) == w) my |= 1u << (j0 & 31);
+          if (((j0 + 1) >> 5) == w) my |= 1u << ((j0 + 1) & 31);
+        }
+      }
+      unsigned bits = my;
+      if (g == 32) bits = __reduce_or_sync(FULL, my);
+      else
+        for (int o = g >> 1; o > 0; o >>= 1) bits |= __shfl_xor_sync(FULL, bits, o);
+      // rows {i0, i0+1} of every sensor row; duplicate rows store identical values (benign)
+      for (int r0 = 0; r0 < 2 * S0; r0 += g) {
+        const int rr = r0 + li;
+        const int i = (rr < S0) ? rr : rr - S0;
+        int row;
+        if (S0 <= g) {
+          row = __shfl_sync(FULL, vis_row, gbase + min(max(i, 0), g - 1));
+        } else {
+          double wy;
+          tap(py * p.lim_y + ((double)min(i, S0 - 1) - p.half0) * p.scale, p.offy, p.H, row, wy);
+        }
+        if (rr >= S0) row += 1;
+        if (act && bits && rr < 2 * S0) vm[row * p.words + w] |= bits;
+      }
+    }
+  }
+  if (err && act) atomicOr(p.err, err);
 }
 
 }  // namespace
@@ -370,7 +450,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 struct apg_image_env {
   apg_image_cfg cfg{};
   cudaStream_t stream = nullptr;
-  int P = 0, words = 0, E = 0;
+  int P = 0, words = 0, g = 0;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -443,7 +523,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.g = e->g; p.log2g = 31 - __builtin_clz(e->g); p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -491,11 +571,23 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   p.index = reinterpret_cast<long long*>(e->b.d_index); p.reward2 = reward2; p.done2 = done2;
   p.stamp_xy = e->b.d_stamp_xy; p.stamp_q = e->b.d_stamp_q; p.visited = e->b.d_visited; p.err = e->d_err;
 
-  const int grid = apg::ceil_div(c.num_envs, e->E);
-  if (c.bank_dtype == APG_BANK_U8)
-    image_step_kernel<unsigned char><<<grid, kThreads, e->smem, e->stream>>>(p);
-  else
-    image_step_kernel<float><<<grid, kThreads, e->smem, e->stream>>>(p);
+  const int grid = apg::ceil_div(c.num_envs, kThreads / e->g);
+#define APG_IMG_LAUNCH(S0T, CT)                                                                   \
+  do {                                                                                            \
+    if (c.bank_dtype == APG_BANK_U8)                                                              \
+      image_step_kernel<unsigned char, S0T, CT><<<grid, kThreads, 0, e->stream>>>(p);             \
+    else                                                                                          \
+      image_step_kernel<float, S0T, CT><<<grid, kThreads, 0, e->stream>>>(p);                     \
+  } while (0)
+  // compile-time sensor heights for the registered environments (5x5 and 10x10 sensors); the unrolled path
+  // needs every sensor row's tap in a lane of the group (S0 <= g)
+  const bool fast = c.sensor_h <= e->g;
+  if (fast && c.sensor_h == 5 && c.channels == 1) APG_IMG_LAUNCH(5, 1);
+  else if (fast && c.sensor_h == 5 && c.channels == 3) APG_IMG_LAUNCH(5, 3);
+  else if (fast && c.sensor_h == 10 && c.channels == 3) APG_IMG_LAUNCH(10, 3);
+  else if (fast && c.sensor_h == 10 && c.channels == 1) APG_IMG_LAUNCH(10, 1);
+  else APG_IMG_LAUNCH(0, 0);
+#undef APG_IMG_LAUNCH
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
   e->t = t_after;
@@ -551,8 +643,12 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   const size_t N = cfg->num_envs;
   e->P = cfg->sensor_h * cfg->sensor_w * cfg->channels;
   e->words = (cfg->width + 31) / 32;
-  e->E = e->P <= 32 ? 128 : (e->P <= 128 ? 64 : 32);
-  e->smem = 1024 + (size_t)e->E * 8 + 2 * (size_t)e->E * (cfg->sensor_h + cfg->sensor_w) * (8 + 4);
+  {
+    int g = 4;
+    while (g < cfg->sensor_w * cfg->channels && g < 32) g <<= 1;
+    e->g = g;
+  }
+  e->smem = 0;
   e->pred_width = cfg->task == APG_TASK_CLASSIFICATION ? cfg->num_classes : 2;
   const bool loc = cfg->task == APG_TASK_LOCALIZATION;
   cudaError_t err = cudaSuccess;
@@ -593,10 +689,6 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     A(apg::dev_alloc(&s.d_inv, N));
     A(cudaMallocHost(reinterpret_cast<void**>(&s.h_pin), slot_bytes(e)));
     A(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
-  }
-  if (err == cudaSuccess && e->smem > 48 * 1024) {
-    A(cudaFuncSetAttribute(image_step_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    A(cudaFuncSetAttribute(image_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   }
   if (err != cudaSuccess) {
     apg_image_destroy(e);

@@ -108,6 +108,48 @@ def test_engine_matches_oracle_seeded_mnist_2048():
     env.close()
 
 
+@pytest.mark.parametrize("geom", [
+    dict(H=64, W=64, C=1, sensor_size=(36, 36), sensor_scale=1.0),   # more sensor rows than lanes per env, 2 chunks
+    dict(H=40, W=48, C=3, sensor_size=(14, 14), sensor_scale=1.0),   # wide sensor: 42 floats per row, two chunks
+    dict(H=70, W=72, C=3, sensor_size=(10, 10), sensor_scale=1.0),   # image wider than 64 px: 3 mask words
+    dict(H=33, W=35, C=1, sensor_size=(5, 5), sensor_scale=2.5),     # scaled sensor: non-consecutive tap rows
+    dict(H=28, W=28, C=3, sensor_size=(5, 5), sensor_scale=1.0),     # unrolled 5x5x3 path
+    dict(H=40, W=40, C=1, sensor_size=(10, 10), sensor_scale=1.0),   # unrolled 10x10x1 path
+])
+@pytest.mark.parametrize("task", ["cls", "loc"])
+def test_engine_matches_oracle_odd_geometries(geom, task):
+    """Sensor / image geometries that exercise every code path of the kernel (generic row loop, column chunks,
+    wide visited masks, clamped and scaled taps) against the oracle: bit-exact pixels, masks, positions."""
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+    import ap_gym_b200 as apg
+
+    N, K = 96, 5
+    imgs, labels = synthetic_u8_bank(seed=21, M=64, H=geom["H"], W=geom["W"], C=geom["C"], K=K)
+    kw = dict(sensor_size=geom["sensor_size"], sensor_scale=geom["sensor_scale"], step_limit=6, max_step_length=0.5)
+    oracle = ImageEnvOracle(imgs, labels, N, task=task, num_classes=K, track_overlay=False, **kw)
+    cls = apg.ImageClassificationVectorEnv if task == "cls" else apg.ImageLocalizationVectorEnv
+    env = cls(N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K), **kw), output="numpy")
+    rng = np.random.default_rng(4)
+    tgt = rng.uniform(-1, 1, (N, 2)).astype(np.float32) if task == "loc" else None
+    oo, _ = oracle.reset(seed=2, explicit_targets=tgt)
+    eo, _ = env.reset(seed=2, options={"prediction_target": tgt} if task == "loc" else None)
+    for k in oo:
+        assert np.array_equal(eo[k], oo[k]), f"reset obs {k}"
+    for s in range(16):
+        a = (rng.uniform(-1, 1, (N, 2)) * 1.5).astype(np.float32)
+        p = rng.standard_normal((N, K if task == "cls" else 2)).astype(np.float32)
+        oo, orw, ote, _, oinf = oracle.step(a, p)
+        eo, erw, ete, _, einf = env.step({"action": a, "prediction": p})
+        for k in oo:
+            assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+        assert np.array_equal(_np(env.state()["pos"]), oracle.pos)
+        assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited), f"step {s} visited"
+        assert np.array_equal(ete, ote)
+        assert_close(erw, orw, RTOL, ATOL, f"step {s} reward")
+    env.close()
+
+
 def test_error_conventions():
     import ap_gym_b200 as apg
     from oracle.datasets import synthetic_u8_bank
