@@ -15,10 +15,13 @@
 // the order numpy performs it (see oracle/image_oracle.py).  uint8 banks are converted with the reference's
 // f32(u8)/255, reproduced exactly by a multiply + two explicit fma corrections (px_to_f64).
 //
-// Thread mapping: a group of g lanes owns one environment (see image_step_kernel): scalars are spread over /
-// replicated across the group, then lane = (column, channel) of the sensor window walks the sensor rows with a
-// two-deep software pipeline on the bank loads; loads are contiguous row segments, stores contiguous runs.
+// Thread mapping: a block owns E environments; thread = environment for the scalar work and for issuing the
+// asynchronous (cp.async) staging of the glimpse's bank footprint into a shared-memory tile, then warp = environment
+// and lane = sensor element for the blend (see image_step_kernel).
+#include <cuda_pipeline.h>
+
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -26,12 +29,16 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kMaxK = 4096;
 
 struct ImgParams {
   int N, H, W, C, S0, S1, P, K, task, invert, track, words, T;
-  int g, log2g;      // lanes per environment (power of two, <= 32)
+  int E;             // environments per block
+  int bank_pitch;    // bytes per bank image row (W*C*elem rounded up to 16: every row is 16-byte aligned)
+  int pitch;         // bytes per staged tile row
+  int tile_rows;     // staged rows per environment
+  int tile_bytes;    // pitch * tile_rows
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
   int t_stamp;       // overlay stamp slot of this step (pre-move time index), mode 0 only
   float time_obs;    // obs["time_step"] value after this step
@@ -90,8 +97,8 @@ __device__ __forceinline__ void tap(double coord, double off, int len, int& k_ou
 }
 
 // bank pixel -> the float64 value the reference blends with: float64(float32(u8) / 255) or float64(f32 pixel).
-// float32(u8)/255 is reproduced exactly (all 256 values, tests/test_capi_symbols.py) by q0 = u*r,
-// q = fma(fma(-255, q0, u), r, q0) with r = float32(1/255): no table, no division.
+// float32(u8)/255 is reproduced exactly for all 256 values by q0 = u*r, q = fma(fma(-255, q0, u), r, q0) with
+// r = float32(1/255): no table, no division.
 __device__ __forceinline__ double px_to_f64(unsigned char u) {
   const float r = 0.003921568859368563f;  // float32(1)/float32(255)
   const float uf = (float)u;
@@ -101,345 +108,313 @@ __device__ __forceinline__ double px_to_f64(unsigned char u) {
 }
 __device__ __forceinline__ double px_to_f64(float v) { return (double)v; }
 
-// An environment is owned by a group of g = min(32, pow2 >= S1*C) lanes (a whole warp for a 10x10x3 sensor, 8 lanes
-// for a 5x5x1 one); a warp steps 32/g environments in lock-step.
-//   phase A  per-environment scalars, spread over the group: lane k reduces logit k (shuffle max/sum), lane i
-//            computes the tap of sensor row i, every lane its own column tap; the short scalar chain (move,
-//            reward, flags) is evaluated redundantly by all lanes of the group, the leader stores it.
-//   phase B  lane = (column, channel) of the sensor window; the group walks the S0 sensor rows.  Every bank load is
-//            one contiguous row segment per group, the bottom taps of row i are the top taps of row i+1, and the
-//            bottom row is fetched two iterations ahead (software pipeline) so the L2/HBM latency overlaps the
-//            float64 blend.  Output rows are stored as contiguous runs.  The blend is the reference's 4-term
-//            float64 sum in the same order (bit-exact pixels).
-template <typename BankT, int S0T, int CT>
+struct __align__(16) Tap {
+  double w;  // normalised distance to the lower grid point
+  int k;     // tap index relative to the staged tile (row) / absolute column
+  int pad;
+};
+
+struct __align__(16) EnvHdr {
+  int lead;     // byte offset of the tile's first needed column inside the staged (aligned-down) row
+  int cmin;     // first tap column of the tile
+  int rmin;     // first tap row of the tile
+  int nrows;    // staged rows
+};
+
+// A block owns E consecutive environments and works in three phases per glimpse set:
+//   A  thread e: the per-environment scalars (move, loss, reward, flags, overlay stamp), the S0+S1 bilinear
+//      taps (-> shared memory) and the asynchronous staging (cp.async, LDGSTS) of the glimpse's bank footprint
+//      -- rows [i0[0], i0[S0-1]+1] x the aligned byte range covering columns [j0[0], j0[S1-1]+1] -- into the
+//      block's shared-memory tile.  All E footprints of the block are in flight at once (no registers held), which
+//      is what hides the HBM/L2 latency of the random bank gather.
+//   B  warp w walks environments w, w+4, ...; lane = (row-in-pass, column, channel) of the sensor window.  Taps come
+//      from the tile (LDS.U8), with one sensor row per pass the bottom taps of row i are the top taps of row i+1;
+//      the blend is the reference's 4-term float64 sum in the same order (bit-exact pixels); each output row is one
+//      contiguous run of stores.  The visited bitmask rows of the environment are updated by the warp.
+template <typename BankT>
 __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EnvHdr* s_hdr = reinterpret_cast<EnvHdr*>(smem_raw);
+  Tap* s_taps = reinterpret_cast<Tap*>(smem_raw + (size_t)p.E * sizeof(EnvHdr));
+  unsigned char* s_tile = smem_raw + (size_t)p.E * sizeof(EnvHdr) + (size_t)p.E * (p.S0 + p.S1) * sizeof(Tap);
+
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int g = p.g;
-  const int li = lane & (g - 1);
-  const int gbase = lane - li;  // first lane of this group inside the warp
-  const int grp_in_block = tid >> p.log2g;
-  const int n = blockIdx.x * (kThreads >> p.log2g) + grp_in_block;
-  const bool act = n < p.N;
-  const int nn = act ? n : p.N - 1;  // inactive groups shadow the last environment but store nothing
-  const unsigned FULL = 0xffffffffu;
-  const bool lead = act && (li == 0);
+  const int warp = tid >> 5;
+  const int env0 = blockIdx.x * p.E;
+  const int nE = min(p.E, p.N - env0);
   const bool two_sets = (p.task == APG_TASK_LOCALIZATION) && (p.mode != 0);
-
-  // ------------------------------------------------------------------ phase A
-  unsigned err = 0;
-  double px, py;
-  int idx;
-  float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
-  double neg_loss_d = 0.0;
-  double tcx = 0.0, tcy = 0.0;
-  if (p.mode == 0) {
-    const double2 pp = reinterpret_cast<const double2*>(p.pos)[nn];
-    px = pp.x;
-    py = pp.y;
-    idx = p.st_idx[nn];
-  } else {
-    const long long ni = p.new_idx[nn];
-    idx = (int)ni;
-    const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[nn];
-    px = pp.x;
-    py = pp.y;
-    if (lead) {
-      p.st_idx[nn] = idx;
-      p.index[nn] = ni;
-    }
-  }
-
-  if (p.task == APG_TASK_CLASSIFICATION) {
-    int label;
-    unsigned char inv = 0;
-    if (p.mode == 0) {
-      label = p.st_label[nn];
-    } else {
-      label = p.bank_labels[idx];
-      if (p.invert) {
-        inv = p.new_inv[nn];
-        if (inv) label = p.K - label - 1;
-        if (lead) p.st_inv[nn] = inv;
-      }
-      if (lead) p.st_label[nn] = label;
-    }
-    if (lead) {
-      if (p.invert) p.inverted_label[nn] = (p.mode == 0) ? 2 : (int)inv;
-      p.target_label[nn] = label;
-    }
-    if (p.mode != 2) {
-      // log-softmax over K logits spread over the group (float32 like scipy.special.log_softmax)
-      const float* x = p.pred + (size_t)nn * p.K;
-      float mx = -INFINITY;
-      bool has_nan = false;
-      for (int k = li; k < p.K; k += g) {
-        const float v = x[k];
-        has_nan |= isnan(v);
-        mx = fmaxf(mx, v);
-      }
-      for (int o = g >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-      if (has_nan) err |= APG_FLAG_NAN_PRED;
-      if (!isfinite(mx)) mx = 0.0f;
-      float s = 0.0f, tl = 0.0f;
-      for (int k = li; k < p.K; k += g) {
-        const float z = __fsub_rn(x[k], mx);
-        if (k == label) tl = z;
-        s = __fadd_rn(s, expf(z));
-      }
-      for (int o = g >> 1; o > 0; o >>= 1) {
-        s = __fadd_rn(s, __shfl_xor_sync(FULL, s, o));
-        tl = __fadd_rn(tl, __shfl_xor_sync(FULL, tl, o));  // exactly one lane holds a non-zero value
-      }
-      const float ce = -__fsub_rn(tl, logf(s));
-      pq = __fdiv_rn(expf(tl), s);  // softmax(x)[label], overlay colour only
-      const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
-      loss_f = (float)loss_d;
-      neg_loss_d = -loss_d;
-    }
-  } else {
-    float t0 = 0.f, t1 = 0.f;
-    if (p.mode != 2) {
-      const float2 tt = reinterpret_cast<const float2*>(p.st_target)[nn];
-      t0 = tt.x;
-      t1 = tt.y;
-      const float2 qq = reinterpret_cast<const float2*>(p.pred)[nn];
-      if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
-      const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
-      const float ss = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
-      loss_f = __fadd_rn(__fmul_rn(__fdiv_rn(ss, 2.0f), p.mse_scale), p.mse_offset);
-      if (p.mode == 0)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64), overlay colour only
-        pq = (float)fmin(fmax(1.0 - (double)__fsqrt_rn(ss) / 2.0, 0.0), 1.0);
-      if (lead) reinterpret_cast<float2*>(p.target_xy)[nn] = make_float2(t0, t1);
-    }
-    if (p.mode != 0) {
-      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[nn];
-      if (lead) {
-        reinterpret_cast<float2*>(p.st_target)[nn] = nt;
-        if (p.mode == 2) reinterpret_cast<float2*>(p.target_xy)[nn] = nt;
-      }
-      tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
-      tcy = (double)nt.y * p.lim_y;
-    }
-  }
-
-  if (p.mode == 0) {
-    const float2 aa = reinterpret_cast<const float2*>(p.action)[nn];
-    const float a0 = aa.x, a1 = aa.y;
-    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
-    if (p.track && lead) {  // overlay stamp of the PRE-move position (image_perception_module.py:196,219-234)
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + nn] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + nn] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
-      p.stamp_q[(size_t)p.t_stamp * p.N + nn] = fminf(fmaxf(pq, 0.0f), 1.0f);
-    }
-    const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
-    float q0 = a0, q1 = a1;
-    if (m > 1.0f) {
-      const float den = fmaxf(m, 1.0f);
-      q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
-      q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
-    }
-    px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
-    py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
-    base = __fmul_rn(-m, 1e-3f);
-  }
-  if (lead) {
-    reinterpret_cast<double2*>(p.pos)[nn] = make_double2(px, py);
-    if (p.mode != 2) {
-      float reward_f;
-      // classification: float32 base - float64 loss -> float64; localization stays float32 except on the reset
-      // step, whose base reward is np.zeros(N) (float64)
-      if (p.task == APG_TASK_CLASSIFICATION) reward_f = (float)((double)base + neg_loss_d);
-      else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
-      p.reward[nn] = reward_f;
-      p.base_reward[nn] = base;
-      p.loss[nn] = loss_f;
-      if (p.reward2) p.reward2[nn] = reward_f;
-      if (p.done2) p.done2[nn] = p.terminated;
-    }
-    p.terminated_out[nn] = p.terminated;
-    p.truncated_out[nn] = 0;
-    reinterpret_cast<float2*>(p.glimpse_pos)[nn] = make_float2((float)px, (float)py);
-    p.time_step[nn] = p.time_obs;
-  }
-
-  // ------------------------------------------------------------------ phase B
-  const int S0 = S0T ? S0T : p.S0;
-  const int C = CT ? CT : p.C;
-  const BankT* img = static_cast<const BankT*>(p.bank) + (long long)idx * p.H * p.W * C;
-  const int G = p.S1 * C;
-  const int WC = p.W * C;
-  const int n_chunks = (G + 31) >> 5;
   const int n_sets = two_sets ? 2 : 1;
-  unsigned colbits0 = 0u, colbits1 = 0u;
-  int vis_row = 0;  // lane li < S0 keeps the tap row of sensor row li (observation glimpse) for the visited mask
+  constexpr int ES = (int)sizeof(BankT);
+  const int row_bytes = p.bank_pitch;
+
+  // per-thread environment state that survives across the two glimpse sets
+  double px = 0.0, py = 0.0, tcx = 0.0, tcy = 0.0;
+  int idx = 0;
 
   for (int set = 0; set < n_sets; ++set) {
-    const double ccx = (set == 0) ? px * p.lim_x : tcx;
-    const double ccy = (set == 0) ? py * p.lim_y : tcy;
-    float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)nn * p.P;
-    // lane li owns the tap of sensor row li (rows >= g are recomputed on the fly below)
-    int my_i0 = 0;
-    double my_wy = 0.0;
-    if (li < S0) {
-      const double y = ccy + ((double)li - p.half0) * p.scale;
-      if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
-      tap(y, p.offy, p.H, my_i0, my_wy);
-    }
-    if (set == 0) vis_row = my_i0;
-    for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      const int jc = (chunk << 5) + li;
-      const bool col_ok = jc < G;
-      const int j = (C == 1) ? jc : ((C == 3) ? (int)(((unsigned)jc * 43691u) >> 17) : jc / C);
-      const int c = jc - j * C;
-      int j0 = 0;
-      double wx = 0.0;
-      {
-        const double x = ccx + ((double)min(j, p.S1 - 1) - p.half1) * p.scale;
-        if (col_ok && (x < -p.offx || x > p.offx)) err |= APG_FLAG_OUT_OF_GRID;
-        tap(x, p.offx, p.W, j0, wx);
-      }
-      if (set == 0 && col_ok) {
-        if ((j0 >> 5) == 0) colbits0 |= 1u << (j0 & 31);
-        else if ((j0 >> 5) == 1) colbits1 |= 1u << (j0 & 31);
-        if (((j0 + 1) >> 5) == 0) colbits0 |= 1u << ((j0 + 1) & 31);
-        else if (((j0 + 1) >> 5) == 1) colbits1 |= 1u << ((j0 + 1) & 31);
-      }
-      const double omx = 1.0 - wx;
-      const BankT* colp = img + (j0 * C + (col_ok ? c : 0));
-      float* outc = out + jc;
-      const bool st_ok = act && col_ok;
-
-      if (S0T > 0) {
-        // ---- compile-time sensor height: every bank load of the glimpse is issued before the first blend
-        int i0s[S0T > 0 ? S0T : 1];
-#pragma unroll
-        for (int i = 0; i < S0T; ++i) i0s[i] = __shfl_sync(FULL, my_i0, gbase + i);
-        BankT bot0[S0T > 0 ? S0T : 1], bot1[S0T > 0 ? S0T : 1];
-        const BankT* r0 = colp + i0s[0] * WC;
-        const BankT top0 = __ldg(r0), top1 = __ldg(r0 + C);
-#pragma unroll
-        for (int i = 0; i < S0T; ++i) {
-          const BankT* rp = colp + (i0s[i] + 1) * WC;
-          bot0[i] = __ldg(rp);
-          bot1[i] = __ldg(rp + C);
-        }
-        double p00 = px_to_f64(top0), p01 = px_to_f64(top1);
-#pragma unroll
-        for (int i = 0; i < S0T; ++i) {
-          const double wy = __shfl_sync(FULL, my_wy, gbase + i);
-          if (i > 0 && i0s[i] != i0s[i - 1] + 1) {  // clamped border: previous bottom row is not this top row
-            const BankT* rp = colp + i0s[i] * WC;
-            p00 = px_to_f64(__ldg(rp));
-            p01 = px_to_f64(__ldg(rp + C));
-          }
-          const double p10 = px_to_f64(bot0[i]), p11 = px_to_f64(bot1[i]);
-          const double omy = 1.0 - wy;
-          double acc = p00 * (omy * omx);  // 0.0 + x == x for x >= 0
-          acc = acc + p01 * (omy * wx);
-          acc = acc + p10 * (wy * omx);
-          acc = acc + p11 * (wy * wx);
-          // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
-          const float v = (sizeof(BankT) == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
-          if (st_ok) outc[i * G] = v;
-          p00 = p10;
-          p01 = p11;
-        }
-      } else {
-        // ---- generic sensor height: two-deep software pipeline over the rows
-        auto row_tap = [&](int i, int& i0, double& wy) {
-          if (S0 <= g) {
-            i0 = __shfl_sync(FULL, my_i0, gbase + min(i, g - 1));
-            wy = __shfl_sync(FULL, my_wy, gbase + min(i, g - 1));
-          } else {
-            tap(ccy + ((double)i - p.half0) * p.scale, p.offy, p.H, i0, wy);
-          }
-        };
-        int i0_cur, i0_n1 = 0, i0_n2 = 0;
-        double wy_cur, wy_n1 = 0.0, wy_n2 = 0.0;
-        row_tap(0, i0_cur, wy_cur);
-        row_tap(1, i0_n1, wy_n1);
-        BankT top0 = __ldg(colp + i0_cur * WC);
-        BankT top1 = __ldg(colp + i0_cur * WC + C);
-        BankT bot0_a = __ldg(colp + (i0_cur + 1) * WC);
-        BankT bot1_a = __ldg(colp + (i0_cur + 1) * WC + C);
-        BankT bot0_b = bot0_a, bot1_b = bot1_a;
-        if (1 < S0) {
-          bot0_b = __ldg(colp + (i0_n1 + 1) * WC);
-          bot1_b = __ldg(colp + (i0_n1 + 1) * WC + C);
-        }
-        double p00 = px_to_f64(top0), p01 = px_to_f64(top1);
-        int prev_i0 = i0_cur - 1;
-        for (int i = 0; i < S0; ++i) {
-          BankT bot0_c = bot0_b, bot1_c = bot1_b;
-          if (i + 2 < S0) {
-            row_tap(i + 2, i0_n2, wy_n2);
-            bot0_c = __ldg(colp + (i0_n2 + 1) * WC);
-            bot1_c = __ldg(colp + (i0_n2 + 1) * WC + C);
-          }
-          if (i0_cur != prev_i0 + 1) {
-            p00 = px_to_f64(__ldg(colp + i0_cur * WC));
-            p01 = px_to_f64(__ldg(colp + i0_cur * WC + C));
-          }
-          const double p10 = px_to_f64(bot0_a), p11 = px_to_f64(bot1_a);
-          const double omy = 1.0 - wy_cur;
-          double acc = 0.0 + p00 * (omy * omx);
-          acc = acc + p01 * (omy * wx);
-          acc = acc + p10 * (wy_cur * omx);
-          acc = acc + p11 * (wy_cur * wx);
-          if (st_ok) outc[i * G] = (float)fmin(fmax(acc, 0.0), 1.0);
-          p00 = p10;
-          p01 = p11;
-          prev_i0 = i0_cur;
-          i0_cur = i0_n1; wy_cur = wy_n1;
-          i0_n1 = i0_n2; wy_n1 = wy_n2;
-          bot0_a = bot0_b; bot1_a = bot1_b;
-          bot0_b = bot0_c; bot1_b = bot1_c;
-        }
-      }
-    }
-  }
-
-  // ------------------------------------------------------------------ visited bitmask (observation glimpse)
-  if (p.track) {
-    unsigned* vm = p.visited + (size_t)nn * p.H * p.words;
-    if (p.mode != 0) {
-      if (act)
-        for (int h = li; h < p.H * p.words; h += g) vm[h] = 0u;
-      __syncwarp(FULL);
-    }
-    for (int w = 0; w < p.words; ++w) {
-      unsigned my = (w == 0) ? colbits0 : ((w == 1) ? colbits1 : 0u);
-      if (w >= 2) {  // wide images: recompute this word's column bits
-        for (int jj = li; jj < p.S1; jj += g) {
-          int j0;
-          double wx;
-          tap(px * p.lim_x + ((double)jj - p.half1) * p.scale, p.offx, p.W, j0, wx);
-          if ((j0 >> 5) == w) my |= 1u << (j0 & 31);
-          if (((j0 + 1) >> 5) == w) my |= 1u << ((j0 + 1) & 31);
-        }
-      }
-      unsigned bits = my;
-      if (g == 32) bits = __reduce_or_sync(FULL, my);
-      else
-        for (int o = g >> 1; o > 0; o >>= 1) bits |= __shfl_xor_sync(FULL, bits, o);
-      // rows {i0, i0+1} of every sensor row; duplicate rows store identical values (benign)
-      for (int r0 = 0; r0 < 2 * S0; r0 += g) {
-        const int rr = r0 + li;
-        const int i = (rr < S0) ? rr : rr - S0;
-        int row;
-        if (S0 <= g) {
-          row = __shfl_sync(FULL, vis_row, gbase + min(max(i, 0), g - 1));
+    // ------------------------------------------------------------------ phase A: thread = environment
+    for (int el = tid; el < nE; el += kThreads) {
+      const int n = env0 + el;
+      unsigned err = 0;
+      if (set == 0) {
+        float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
+        double neg_loss_d = 0.0;
+        if (p.mode == 0) {
+          const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
+          px = pp.x;
+          py = pp.y;
+          idx = p.st_idx[n];
         } else {
-          double wy;
-          tap(py * p.lim_y + ((double)min(i, S0 - 1) - p.half0) * p.scale, p.offy, p.H, row, wy);
+          const long long ni = p.new_idx[n];
+          idx = (int)ni;
+          const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[n];
+          px = pp.x;
+          py = pp.y;
+          p.st_idx[n] = idx;
+          p.index[n] = ni;
         }
-        if (rr >= S0) row += 1;
-        if (act && bits && rr < 2 * S0) vm[row * p.words + w] |= bits;
+        // ---- labels / targets and the loss (the reset step still charges a loss)
+        if (p.task == APG_TASK_CLASSIFICATION) {
+          int label;
+          unsigned char inv = 0;
+          if (p.mode == 0) {
+            label = p.st_label[n];
+          } else {
+            label = p.bank_labels[idx];
+            if (p.invert) {
+              inv = p.new_inv[n];
+              if (inv) label = p.K - label - 1;
+            }
+            p.st_label[n] = label;
+          }
+          if (p.invert) p.inverted_label[n] = (p.mode == 0) ? 2 : (int)inv;
+          p.target_label[n] = label;
+          if (p.mode != 2) {
+            const float* x = p.pred + (size_t)n * p.K;
+            float mx = -INFINITY;
+            bool has_nan = false;
+            for (int k = 0; k < p.K; ++k) {
+              const float v = x[k];
+              has_nan |= isnan(v);
+              mx = fmaxf(mx, v);
+            }
+            if (has_nan) err |= APG_FLAG_NAN_PRED;
+            if (!isfinite(mx)) mx = 0.0f;
+            float s = 0.0f;
+            for (int k = 0; k < p.K; ++k) s = __fadd_rn(s, expf(__fsub_rn(x[k], mx)));
+            const float tl = __fsub_rn(x[label], mx);
+            const float ce = -__fsub_rn(tl, logf(s));  // -log_softmax(x)[label], float32 like scipy
+            pq = __fdiv_rn(expf(tl), s);               // softmax(x)[label], overlay colour only
+            const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
+            loss_f = (float)loss_d;
+            neg_loss_d = -loss_d;
+          }
+        } else {
+          float t0 = 0.f, t1 = 0.f;
+          if (p.mode != 2) {
+            const float2 tt = reinterpret_cast<const float2*>(p.st_target)[n];
+            t0 = tt.x;
+            t1 = tt.y;
+            const float2 qq = reinterpret_cast<const float2*>(p.pred)[n];
+            if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
+            const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
+            const float ss = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
+            loss_f = __fadd_rn(__fmul_rn(__fdiv_rn(ss, 2.0f), p.mse_scale), p.mse_offset);
+            if (p.mode == 0 && p.track)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64)
+              pq = (float)fmin(fmax(1.0 - (double)__fsqrt_rn(ss) / 2.0, 0.0), 1.0);
+            reinterpret_cast<float2*>(p.target_xy)[n] = make_float2(t0, t1);
+          }
+          if (p.mode != 0) {
+            const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
+            reinterpret_cast<float2*>(p.st_target)[n] = nt;
+            if (p.mode == 2) reinterpret_cast<float2*>(p.target_xy)[n] = nt;
+            tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
+            tcy = (double)nt.y * p.lim_y;
+          }
+        }
+        // ---- move (mode 0): overlay stamp of the PRE-move position, then the float64 position update
+        if (p.mode == 0) {
+          const float2 aa = reinterpret_cast<const float2*>(p.action)[n];
+          const float a0 = aa.x, a1 = aa.y;
+          if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
+          if (p.track) {
+            p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
+            p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
+            p.stamp_q[(size_t)p.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
+          }
+          const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+          float q0 = a0, q1 = a1;
+          if (m > 1.0f) {
+            const float den = fmaxf(m, 1.0f);
+            q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
+            q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
+          }
+          px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
+          py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
+          base = __fmul_rn(-m, 1e-3f);
+        }
+        reinterpret_cast<double2*>(p.pos)[n] = make_double2(px, py);
+        if (p.mode != 2) {
+          float reward_f;
+          // classification: float32 base - float64 loss -> float64; localization stays float32 except on the reset
+          // step, whose base reward is np.zeros(N) (float64)
+          if (p.task == APG_TASK_CLASSIFICATION) reward_f = (float)((double)base + neg_loss_d);
+          else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
+          p.reward[n] = reward_f;
+          p.base_reward[n] = base;
+          p.loss[n] = loss_f;
+          if (p.reward2) p.reward2[n] = reward_f;
+          if (p.done2) p.done2[n] = p.terminated;
+        }
+        p.terminated_out[n] = p.terminated;
+        p.truncated_out[n] = 0;
+        reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
+        p.time_step[n] = p.time_obs;
+      }
+
+      // ---- taps of this set's glimpse and the asynchronous staging of its bank footprint
+      const double ccx = (set == 0) ? px * p.lim_x : tcx;
+      const double ccy = (set == 0) ? py * p.lim_y : tcy;
+      Tap* rows = s_taps + (size_t)el * (p.S0 + p.S1);
+      Tap* cols = rows + p.S0;
+      int rmin = 0, rmax = 0, cmin = 0, cmax = 0;
+      for (int i = 0; i < p.S0; ++i) {
+        const double y = ccy + ((double)i - p.half0) * p.scale;
+        if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
+        int k;
+        double w;
+        tap(y, p.offy, p.H, k, w);
+        if (i == 0) rmin = k;
+        rmax = k + 1;
+        rows[i].w = w;
+        rows[i].k = k - rmin;
+      }
+      for (int j = 0; j < p.S1; ++j) {
+        const double x = ccx + ((double)j - p.half1) * p.scale;
+        if (x < -p.offx || x > p.offx) err |= APG_FLAG_OUT_OF_GRID;
+        int k;
+        double w;
+        tap(x, p.offx, p.W, k, w);
+        if (j == 0) cmin = k;
+        cmax = k + 1;
+        cols[j].w = w;
+        cols[j].k = k;
+      }
+      const int nrows = min(rmax - rmin + 1, p.tile_rows);
+      const int first_byte = cmin * p.C * ES;
+      const int lead = first_byte & 15;
+      const int start = first_byte - lead;                               // aligned down to the 16-byte copy granule
+      int span = (cmax + 1) * p.C * ES - start;                          // bytes needed from `start`
+      span = min((span + 15) & ~15, min(row_bytes - start, p.pitch));
+      EnvHdr h;
+      h.lead = lead; h.cmin = cmin; h.rmin = rmin; h.nrows = nrows;
+      s_hdr[el] = h;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bank) + (long long)idx * p.H * row_bytes +
+                                 (long long)rmin * row_bytes + start;
+      unsigned char* dst = s_tile + (size_t)el * p.tile_bytes;
+      for (int r = 0; r < nrows; ++r) {
+        for (int b = 0; b < span; b += 16) __pipeline_memcpy_async(dst + b, src + b, 16);
+        src += row_bytes;
+        dst += p.pitch;
+      }
+      if (err) atomicOr(p.err, err);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase B: warp = environment, lane = sensor element
+    const int G = p.S1 * p.C;
+    const int cpp = min(G, 32);
+    const int R = (G <= 32) ? (32 / G) : 1;
+    const int n_chunks = (G + 31) >> 5;
+    const int r_sub = lane / cpp;
+    const int jc0 = lane - r_sub * cpp;
+    float* out_set = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
+    for (int el = warp; el < nE; el += kThreads / 32) {
+      const EnvHdr h = s_hdr[el];
+      const Tap* rows = s_taps + (size_t)el * (p.S0 + p.S1);
+      const Tap* cols = rows + p.S0;
+      const unsigned char* tile = s_tile + (size_t)el * p.tile_bytes;
+      float* out = out_set + (size_t)el * p.P;
+      unsigned colbits0 = 0u, colbits1 = 0u;
+      for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int jc = (chunk << 5) + jc0;
+        const bool col_ok = (jc < G) && (r_sub < R);
+        const int j = (p.C == 1) ? jc : ((p.C == 3) ? (int)(((unsigned)jc * 43691u) >> 17) : jc / p.C);
+        const int c = jc - j * p.C;
+        const Tap ct = cols[min(j, p.S1 - 1)];
+        const double wx = ct.w, omx = 1.0 - ct.w;
+        if (set == 0 && col_ok && r_sub == 0) {
+          const int j0 = ct.k;
+          if ((j0 >> 5) == 0) colbits0 |= 1u << (j0 & 31);
+          else if ((j0 >> 5) == 1) colbits1 |= 1u << (j0 & 31);
+          if (((j0 + 1) >> 5) == 0) colbits0 |= 1u << ((j0 + 1) & 31);
+          else if (((j0 + 1) >> 5) == 1) colbits1 |= 1u << ((j0 + 1) & 31);
+        }
+        const BankT* colp = reinterpret_cast<const BankT*>(tile + h.lead) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
+        const int pitch_e = p.pitch / ES;
+        float* outp = out + r_sub * G + jc;
+        const int out_step = R * G;
+        int prev_k = -4;
+        double b0 = 0.0, b1 = 0.0;
+        for (int i = r_sub; i < p.S0; i += R, outp += out_step) {
+          if (col_ok) {
+            const Tap rt = rows[i];
+            const BankT* rp = colp + rt.k * pitch_e;
+            double p00, p01;
+            if (R == 1 && rt.k == prev_k + 1) {
+              p00 = b0;
+              p01 = b1;
+            } else {
+              p00 = px_to_f64(rp[0]);
+              p01 = px_to_f64(rp[p.C]);
+            }
+            rp += pitch_e;
+            const double p10 = px_to_f64(rp[0]), p11 = px_to_f64(rp[p.C]);
+            b0 = p10;
+            b1 = p11;
+            prev_k = rt.k;
+            const double wy = rt.w, omy = 1.0 - rt.w;
+            double acc = 0.0 + p00 * (omy * omx);
+            acc = acc + p01 * (omy * wx);
+            acc = acc + p10 * (wy * omx);
+            acc = acc + p11 * (wy * wx);
+            // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
+            *outp = (ES == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
+          }
+        }
+      }
+      // ---- visited bitmask of the observation glimpse: rows {i0, i0+1} x columns {j0, j0+1}
+      if (p.track && set == 0) {
+        unsigned* vm = p.visited + (size_t)(env0 + el) * p.H * p.words;
+        if (p.mode != 0) {
+          for (int q = lane; q < p.H * p.words; q += 32) vm[q] = 0u;
+          __syncwarp();
+        }
+        for (int w = 0; w < p.words; ++w) {
+          unsigned my = (w == 0) ? colbits0 : ((w == 1) ? colbits1 : 0u);
+          if (w >= 2) {  // images wider than 64 px
+            for (int jj = lane; jj < p.S1; jj += 32) {
+              const int j0 = cols[jj].k;
+              if ((j0 >> 5) == w) my |= 1u << (j0 & 31);
+              if (((j0 + 1) >> 5) == w) my |= 1u << ((j0 + 1) & 31);
+            }
+          }
+          const unsigned bits = __reduce_or_sync(0xffffffffu, my);
+          if (bits) {
+            for (int rr = lane; rr < 2 * p.S0; rr += 32) {
+              const int row = h.rmin + ((rr < p.S0) ? rows[rr].k : rows[rr - p.S0].k + 1);
+              atomicOr(vm + row * p.words + w, bits);  // no return value -> RED: nothing waits for the old word
+            }
+          }
+        }
+        __syncwarp();
       }
     }
+    if (set + 1 < n_sets) __syncthreads();  // the tile and the taps are reused by the target glimpse
   }
-  if (err && act) atomicOr(p.err, err);
 }
 
 }  // namespace
@@ -450,7 +425,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 struct apg_image_env {
   apg_image_cfg cfg{};
   cudaStream_t stream = nullptr;
-  int P = 0, words = 0, g = 0;
+  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -523,7 +498,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.g = e->g; p.log2g = 31 - __builtin_clz(e->g); p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -571,23 +546,11 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   p.index = reinterpret_cast<long long*>(e->b.d_index); p.reward2 = reward2; p.done2 = done2;
   p.stamp_xy = e->b.d_stamp_xy; p.stamp_q = e->b.d_stamp_q; p.visited = e->b.d_visited; p.err = e->d_err;
 
-  const int grid = apg::ceil_div(c.num_envs, kThreads / e->g);
-#define APG_IMG_LAUNCH(S0T, CT)                                                                   \
-  do {                                                                                            \
-    if (c.bank_dtype == APG_BANK_U8)                                                              \
-      image_step_kernel<unsigned char, S0T, CT><<<grid, kThreads, 0, e->stream>>>(p);             \
-    else                                                                                          \
-      image_step_kernel<float, S0T, CT><<<grid, kThreads, 0, e->stream>>>(p);                     \
-  } while (0)
-  // compile-time sensor heights for the registered environments (5x5 and 10x10 sensors); the unrolled path
-  // needs every sensor row's tap in a lane of the group (S0 <= g)
-  const bool fast = c.sensor_h <= e->g;
-  if (fast && c.sensor_h == 5 && c.channels == 1) APG_IMG_LAUNCH(5, 1);
-  else if (fast && c.sensor_h == 5 && c.channels == 3) APG_IMG_LAUNCH(5, 3);
-  else if (fast && c.sensor_h == 10 && c.channels == 3) APG_IMG_LAUNCH(10, 3);
-  else if (fast && c.sensor_h == 10 && c.channels == 1) APG_IMG_LAUNCH(10, 1);
-  else APG_IMG_LAUNCH(0, 0);
-#undef APG_IMG_LAUNCH
+  const int grid = apg::ceil_div(c.num_envs, e->E);
+if (c.bank_dtype == APG_BANK_U8)
+    image_step_kernel<unsigned char><<<grid, kThreads, e->smem, e->stream>>>(p);
+  else
+    image_step_kernel<float><<<grid, kThreads, e->smem, e->stream>>>(p);
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
   e->t = t_after;
@@ -644,11 +607,35 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   e->P = cfg->sensor_h * cfg->sensor_w * cfg->channels;
   e->words = (cfg->width + 31) / 32;
   {
-    int g = 4;
-    while (g < cfg->sensor_w * cfg->channels && g < 32) g <<= 1;
-    e->g = g;
+    // staged tile geometry: rows [i0[0], i0[S0-1]+1], the aligned byte range covering columns [j0[0], j0[S1-1]+1]
+    const int es = cfg->bank_dtype == APG_BANK_U8 ? 1 : 4;
+    const int row_bytes = (cfg->width * cfg->channels * es + 15) & ~15;  // padded bank rows: 16-byte aligned
+    e->bank_pitch = row_bytes;
+    const int span_cols = (int)std::ceil((cfg->sensor_w - 1) * cfg->sensor_scale) + 3;
+    const int span_rows = (int)std::ceil((cfg->sensor_h - 1) * cfg->sensor_scale) + 3;
+    int pitch = span_cols * cfg->channels * es + 16;  // + lead bytes of the aligned-down start
+    pitch = (pitch + 15) & ~15;
+    if (pitch > row_bytes) pitch = row_bytes;
+    e->pitch = pitch;
+    e->tile_rows = span_rows < cfg->height ? span_rows : cfg->height;
+    const size_t per_env = 16 + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->pitch * e->tile_rows;
+    int E = (int)((72 * 1024) / per_env);  // ~3 blocks of 72 KB per SM keep >= 190 footprints in flight
+    // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
+    // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
+    E = E > 64 ? 64 : E;
+    if (per_env > 768 && E > 32) E = 32;
+    if (const char* ov = getenv("APG_IMG_ENVS_PER_BLOCK")) {
+      const int v = atoi(ov);
+      if (v >= 1 && v <= kThreads && (size_t)v * per_env <= 200 * 1024) E = v;
+    }
+    E = E >= 8 ? (E & ~7) : (E >= 4 ? 4 : (E >= 2 ? 2 : 1));
+    e->E = E;
+    e->smem = per_env * E;
+    if (e->smem > 200 * 1024) {
+      delete e;
+      return apg::fail(APG_ERR_INVALID, "sensor window too large for the shared-memory tile (%zu bytes)", e->smem);
+    }
   }
-  e->smem = 0;
   e->pred_width = cfg->task == APG_TASK_CLASSIFICATION ? cfg->num_classes : 2;
   const bool loc = cfg->task == APG_TASK_LOCALIZATION;
   cudaError_t err = cudaSuccess;
@@ -689,6 +676,10 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     A(apg::dev_alloc(&s.d_inv, N));
     A(cudaMallocHost(reinterpret_cast<void**>(&s.h_pin), slot_bytes(e)));
     A(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+  }
+  if (err == cudaSuccess && e->smem > 48 * 1024) {
+    A(cudaFuncSetAttribute(image_step_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    A(cudaFuncSetAttribute(image_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   }
   if (err != cudaSuccess) {
     apg_image_destroy(e);
@@ -738,16 +729,22 @@ int apg_image_set_bank(apg_image_env* e, const void* bank, const int32_t* labels
     cudaFree(e->d_bank_labels);
   }
   e->d_bank = nullptr; e->d_bank_labels = nullptr; e->own_bank = false;
-  const size_t px = (size_t)e->cfg.height * e->cfg.width * e->cfg.channels;
-  const size_t bytes = (size_t)n_items * px * (e->cfg.bank_dtype == APG_BANK_U8 ? 1 : 4);
+  const size_t es = e->cfg.bank_dtype == APG_BANK_U8 ? 1 : 4;
+  const size_t row = (size_t)e->cfg.width * e->cfg.channels * es;   // tight row as supplied
+  const size_t rows_total = (size_t)n_items * e->cfg.height;
   if (on_device) {
+    APG_CHECK(row == (size_t)e->bank_pitch, APG_ERR_INVALID,
+              "adopting a device bank needs 16-byte aligned rows (W*C*elem = %zu); upload from the host instead", row);
+    APG_CHECK((reinterpret_cast<uintptr_t>(bank) & 15) == 0, APG_ERR_INVALID, "device bank must be 16-byte aligned");
     e->d_bank = const_cast<void*>(bank);
     e->d_bank_labels = const_cast<int32_t*>(labels);
   } else {
-    APG_CUDA(cudaMalloc(&e->d_bank, bytes));
+    // rows are re-pitched to a multiple of 16 bytes so that every footprint can be staged with 16-byte cp.async
+    APG_CUDA(cudaMalloc(&e->d_bank, rows_total * e->bank_pitch + 64));
     e->own_bank = true;
     APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_bank_labels), (size_t)n_items * 4));
-    APG_CUDA(cudaMemcpy(e->d_bank, bank, bytes, cudaMemcpyHostToDevice));
+    APG_CUDA(cudaMemset(e->d_bank, 0, rows_total * e->bank_pitch + 64));
+    APG_CUDA(cudaMemcpy2D(e->d_bank, e->bank_pitch, bank, row, row, rows_total, cudaMemcpyHostToDevice));
     APG_CUDA(cudaMemcpy(e->d_bank_labels, labels, (size_t)n_items * 4, cudaMemcpyHostToDevice));
   }
   e->n_items = n_items;
