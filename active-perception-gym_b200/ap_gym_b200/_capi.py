@@ -14,6 +14,7 @@ FLAG_NAN_ACTION, FLAG_NAN_PRED, FLAG_OUT_OF_GRID = 1, 2, 4
 TASK_CLASSIFICATION, TASK_LOCALIZATION = 0, 1
 BANK_U8, BANK_F32 = 0, 1
 PAYLOAD_RING_DEFAULT, PAYLOAD_RING_MAX = 4, 64
+NUM_STATS = 8
 
 
 class ApgError(RuntimeError):
@@ -41,6 +42,8 @@ class ImageBuffers(C.Structure):
         ("d_target_xy", C.c_void_p), ("d_terminated", C.c_void_p), ("d_truncated", C.c_void_p),
         ("d_index", C.c_void_p), ("d_pos", C.c_void_p), ("d_cur_target_xy", C.c_void_p),
         ("d_visited", C.c_void_p), ("d_stamp_xy", C.c_void_p), ("d_stamp_q", C.c_void_p),
+        ("d_ep_avg1", C.c_void_p), ("d_ep_final1", C.c_void_p), ("d_ep_avg2", C.c_void_p), ("d_ep_final2", C.c_void_p),
+        ("d_ep_return", C.c_void_p), ("d_first_correct", C.c_void_p), ("d_last_incorrect", C.c_void_p),
         ("stamp_count", C.c_int32), ("elapsed", C.c_int32), ("needs_reset", C.c_int32),
     ]
 
@@ -57,7 +60,8 @@ class LidarCfg(C.Structure):
 class LidarBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_lidar", "d_odometry", "d_time_step", "d_map", "d_reward", "d_base_reward", "d_loss", "d_target",
-        "d_terminated", "d_truncated", "d_stepped", "d_map_idx", "d_pos", "d_initial_pos", "d_cells", "d_dists")]
+        "d_terminated", "d_truncated", "d_stepped", "d_map_idx", "d_pos", "d_initial_pos",
+        "d_ep_avg1", "d_ep_final1", "d_ep_avg2", "d_ep_final2", "d_ep_return", "d_cells", "d_dists")]
 
 
 # name -> (restype, argtypes); every symbol include/apg_b200.h declares must be listed here
@@ -77,6 +81,7 @@ SYMBOLS = {
     "apg_image_rollout": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "apg_image_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "apg_image_get_buffers": (C.c_int, [_P, C.POINTER(ImageBuffers)]),
+    "apg_image_get_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "apg_image_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),
     "apg_image_sync": (C.c_int, [_P]),
     "apg_lidar_create": (C.c_int, [C.POINTER(LidarCfg), C.POINTER(_P)]),
@@ -89,6 +94,7 @@ SYMBOLS = {
     "apg_lidar_rollout": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "apg_lidar_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "apg_lidar_get_buffers": (C.c_int, [_P, C.POINTER(LidarBuffers)]),
+    "apg_lidar_get_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "apg_lidar_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),
     "apg_lidar_sync": (C.c_int, [_P]),
     "apg_rng_host_stream": (C.c_int, [C.c_uint64, C.c_int32, _P, _P, _P]),

@@ -137,6 +137,10 @@ class _ImageVectorEnvBase:
             "index": t(b.d_index, dev, "int", 64, (N,)),
             "pos": t(b.d_pos, dev, "float", 64, (N, 2)),
         }
+        for k in ("ep_avg1", "ep_final1", "ep_avg2", "ep_final2", "ep_return"):
+            v[k] = t(getattr(b, "d_" + k), dev, "float", 32, (N,))
+        v["first_correct"] = t(b.d_first_correct, dev, "int", 32, (N,))
+        v["last_incorrect"] = t(b.d_last_incorrect, dev, "int", 32, (N,))
         if b.d_target_glimpse:
             v["target_glimpse"] = t(b.d_target_glimpse, dev, "float", 32, (N, S0, S1, Cn))
             v["target_xy"] = t(b.d_target_xy, dev, "float", 32, (N, 2))
@@ -301,7 +305,37 @@ class _ImageVectorEnvBase:
             "base_reward": self._out("base_reward", host_mode),
             "prediction": {"target": self._out(self._TARGET_VIEW, host_mode), "loss": self._out("loss", host_mode)},
         }
+        if self._buffers().needs_reset:  # this step ended every episode: the LogWrapper's info["stats"]
+            info["stats"] = self._stats_info(host_mode, terminated)
         return obs, reward, terminated, truncated, info
+
+    def _stats_info(self, as_numpy, done):
+        m1, m2 = self._METRICS
+        scalar = {f"avg_{m1}": self._out("ep_avg1", as_numpy), f"final_{m1}": self._out("ep_final1", as_numpy),
+                  f"avg_{m2}": self._out("ep_avg2", as_numpy), f"final_{m2}": self._out("ep_final2", as_numpy),
+                  "return": self._out("ep_return", as_numpy)}
+        if self._TASK == _capi.TASK_CLASSIFICATION:
+            fc, li = self._out("first_correct", as_numpy), self._out("last_incorrect", as_numpy)
+            scalar.update({"first_correct": fc, "_first_correct": fc >= 0, "last_incorrect": li, "_last_incorrect": li >= 0})
+        return {"scalar": scalar, "_scalar": done}
+
+    def episode_stats(self, reduce: bool = True, clear: bool = False) -> dict[str, float]:
+        """Means over all episodes finished so far (this shard, or all ranks with `reduce=True` inside an initialised
+        torch.distributed group: ONE all-reduce of 8 float64 -- the only collective of the data path)."""
+        import torch
+
+        from .distributed import reduce_stats
+
+        h = (C.c_double * _capi.NUM_STATS)()
+        _capi.check(self._lib.apg_image_get_stats(self._h, h, int(clear)))
+        t = torch.tensor(list(h), dtype=torch.float64, device=torch.device("cuda", self._device))
+        if reduce:
+            reduce_stats(t)
+        t = t.cpu().tolist()
+        ep = max(t[0], 1.0)
+        m1, m2 = self._METRICS
+        return {"episodes": t[0], f"avg_{m1}": t[1] / ep, f"final_{m1}": t[2] / ep, f"avg_{m2}": t[3] / ep,
+                f"final_{m2}": t[4] / ep, "return": t[5] / ep}
 
     def rollout(self, actions, predictions, rewards=None, dones=None):
         """`n_steps` consecutive steps from stacked CUDA tensors (n_steps, N, 2) / (n_steps, N, K|2); per-step
@@ -387,6 +421,7 @@ class ImageClassificationVectorEnv(_ImageVectorEnvBase):
 
     _TASK = _capi.TASK_CLASSIFICATION
     _TARGET_VIEW = "target_label"
+    _METRICS = ("correct_label_prob", "accuracy")
 
     def _explicit_targets(self, options, idx, pos):
         return None
@@ -402,6 +437,7 @@ class ImageLocalizationVectorEnv(_ImageVectorEnvBase):
 
     _TASK = _capi.TASK_LOCALIZATION
     _TARGET_VIEW = "target_xy"
+    _METRICS = ("euclidean_distance", "mse")
 
     def __init__(self, *args, target_sampling: Literal["uniform"] = "uniform", **kwargs):
         super().__init__(*args, **kwargs)

@@ -116,6 +116,8 @@ class LIDARLocalization2DVectorEnv:
             "pos": t(b.d_pos, dev, "float", 32, (N, 2)),
             "initial_pos": t(b.d_initial_pos, dev, "float", 32, (N, 2)),
         }
+        for k in ("ep_avg1", "ep_final1", "ep_avg2", "ep_final2", "ep_return"):
+            v[k] = t(getattr(b, "d_" + k), dev, "float", 32, (N,))
         if b.d_map:
             v["map"] = t(b.d_map, dev, "float", 32, (N, self._H, self._W, 1))
         if b.d_cells:
@@ -196,8 +198,30 @@ class LIDARLocalization2DVectorEnv:
                            "loss": self._out("loss", host_mode), "_loss": stepped},
             "_prediction": stepped,
             "map_idx": self._out("map_idx", host_mode), "_map_idx": ~stepped,
+            # ActiveRegressionLogWrapper's info["stats"]: valid for the envs whose `terminated` flag is set
+            "stats": {"scalar": {"avg_euclidean_distance": self._out("ep_avg1", host_mode),
+                                 "final_euclidean_distance": self._out("ep_final1", host_mode),
+                                 "avg_mse": self._out("ep_avg2", host_mode), "final_mse": self._out("ep_final2", host_mode),
+                                 "return": self._out("ep_return", host_mode)},
+                      "_scalar": terminated},
         }
         return obs, reward, terminated, truncated, info
+
+    def episode_stats(self, reduce: bool = True, clear: bool = False) -> dict[str, float]:
+        """Means over all episodes finished so far (see ImageClassificationVectorEnv.episode_stats)."""
+        import torch
+
+        from .distributed import reduce_stats
+
+        h = (C.c_double * _capi.NUM_STATS)()
+        _capi.check(self._lib.apg_lidar_get_stats(self._h, h, int(clear)))
+        t = torch.tensor(list(h), dtype=torch.float64, device=torch.device("cuda", self._device))
+        if reduce:
+            reduce_stats(t)
+        t = t.cpu().tolist()
+        ep = max(t[0], 1.0)
+        return {"episodes": t[0], "avg_euclidean_distance": t[1] / ep, "final_euclidean_distance": t[2] / ep,
+                "avg_mse": t[3] / ep, "final_mse": t[4] / ep, "return": t[5] / ep}
 
     def rollout(self, actions, predictions, rewards=None, dones=None):
         _capi.check(self._lib.apg_lidar_rollout(

@@ -79,6 +79,12 @@ struct ImgParams {
   long long* index;
   float* reward2;           // optional per-step rollout outputs
   unsigned char* done2;
+  // episode statistics
+  float* acc1; float* acc2; float* acc_ret;   // per-env running sums of the current episode
+  float* ep_avg1; float* ep_final1; float* ep_avg2; float* ep_final2; float* ep_return;
+  int* first_correct; int* last_incorrect;
+  double* stats;            // (APG_NUM_STATS) shard-wide sums
+  float inv_k;              // float32(1 / num_classes)
   // overlay
   int* stamp_xy;
   float* stamp_q;
@@ -151,6 +157,10 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
   // per-thread environment state that survives across the two glimpse sets
   double px = 0.0, py = 0.0, tcx = 0.0, tcy = 0.0;
   int idx = 0;
+  __shared__ double s_stats[6];
+  const bool ep_end = (p.mode == 0) && p.terminated;  // this step finishes every episode of the vector env
+  if (ep_end && tid < 6) s_stats[tid] = 0.0;
+  if (ep_end) __syncthreads();
 
   for (int set = 0; set < n_sets; ++set) {
     // ------------------------------------------------------------------ phase A: thread = environment
@@ -159,6 +169,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
       unsigned err = 0;
       if (set == 0) {
         float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
+        float m1 = 0.0f, m2 = 0.0f;  // LogWrapper metrics of this step
         double neg_loss_d = 0.0;
         if (p.mode == 0) {
           const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
@@ -209,6 +220,8 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
             const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
             loss_f = (float)loss_d;
             neg_loss_d = -loss_d;
+            m1 = pq;                            // correct_label_prob (active_classification_env.py:157-161)
+            m2 = (pq > p.inv_k) ? 1.0f : 0.0f;  // accuracy (:166-168)
           }
         } else {
           float t0 = 0.f, t1 = 0.f;
@@ -221,6 +234,8 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
             const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
             const float ss = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
             loss_f = __fadd_rn(__fmul_rn(__fdiv_rn(ss, 2.0f), p.mse_scale), p.mse_offset);
+            m1 = __fsqrt_rn(ss);       // euclidean_distance (active_regression_env.py:211)
+            m2 = __fdiv_rn(ss, 2.0f);  // mse (:212)
             if (p.mode == 0 && p.track)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64)
               pq = (float)fmin(fmax(1.0 - (double)__fsqrt_rn(ss) / 2.0, 0.0), 1.0);
             reinterpret_cast<float2*>(p.target_xy)[n] = make_float2(t0, t1);
@@ -266,6 +281,28 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
           p.loss[n] = loss_f;
           if (p.reward2) p.reward2[n] = reward_f;
           if (p.done2) p.done2[n] = p.terminated;
+          // ---- episode statistics (the *VectorLogWrapper loops): real steps only, cleared by the reset step
+          if (p.mode == 0) {
+            const float a1 = __fadd_rn(p.t_stamp == 0 ? 0.0f : p.acc1[n], m1);
+            const float a2 = __fadd_rn(p.t_stamp == 0 ? 0.0f : p.acc2[n], m2);
+            const float ar = __fadd_rn(p.t_stamp == 0 ? 0.0f : p.acc_ret[n], reward_f);
+            if (p.task == APG_TASK_CLASSIFICATION) {
+              int fc = p.t_stamp == 0 ? -1 : p.first_correct[n];
+              int lic = p.t_stamp == 0 ? -1 : p.last_incorrect[n];
+              if (m2 > 0.5f) { if (fc < 0) fc = p.t_stamp; } else lic = p.t_stamp;
+              p.first_correct[n] = fc;
+              p.last_incorrect[n] = lic;
+            }
+            if (ep_end) {
+              const float nt = (float)(p.t_stamp + 1);
+              const float avg1 = __fdiv_rn(a1, nt), avg2 = __fdiv_rn(a2, nt);
+              p.ep_avg1[n] = avg1; p.ep_final1[n] = m1; p.ep_avg2[n] = avg2; p.ep_final2[n] = m2; p.ep_return[n] = ar;
+              atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)avg1); atomicAdd(&s_stats[2], (double)m1);
+              atomicAdd(&s_stats[3], (double)avg2); atomicAdd(&s_stats[4], (double)m2); atomicAdd(&s_stats[5], (double)ar);
+            } else {
+              p.acc1[n] = a1; p.acc2[n] = a2; p.acc_ret[n] = ar;
+            }
+          }
         }
         p.terminated_out[n] = p.terminated;
         p.truncated_out[n] = 0;
@@ -323,6 +360,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
     __pipeline_commit();
     __pipeline_wait_prior(0);
     __syncthreads();
+    if (ep_end && set == 0 && tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
 
     // ------------------------------------------------------------------ phase B: warp = environment, lane = sensor element
     const int G = p.S1 * p.C;
@@ -434,6 +472,8 @@ struct apg_image_env {
   bool own_bank = false;
   // outputs / state
   apg_image_buffers b{};
+  float* d_acc1 = nullptr; float* d_acc2 = nullptr; float* d_acc_ret = nullptr;
+  double* d_stats = nullptr;
   int32_t* d_st_idx = nullptr;
   int32_t* d_st_label = nullptr;
   uint8_t* d_st_inv = nullptr;
@@ -545,6 +585,10 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   p.target_xy = e->b.d_target_xy; p.terminated_out = e->b.d_terminated; p.truncated_out = e->b.d_truncated;
   p.index = reinterpret_cast<long long*>(e->b.d_index); p.reward2 = reward2; p.done2 = done2;
   p.stamp_xy = e->b.d_stamp_xy; p.stamp_q = e->b.d_stamp_q; p.visited = e->b.d_visited; p.err = e->d_err;
+  p.acc1 = e->d_acc1; p.acc2 = e->d_acc2; p.acc_ret = e->d_acc_ret; p.ep_avg1 = e->b.d_ep_avg1; p.ep_final1 = e->b.d_ep_final1;
+  p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return;
+  p.first_correct = e->b.d_first_correct; p.last_incorrect = e->b.d_last_incorrect; p.stats = e->d_stats;
+  p.inv_k = (float)(1.0 / (double)(c.num_classes > 0 ? c.num_classes : 1));
 
   const int grid = apg::ceil_div(c.num_envs, e->E);
 if (c.bank_dtype == APG_BANK_U8)
@@ -660,6 +704,11 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     A(apg::dev_alloc(&e->b.d_stamp_xy, (size_t)cfg->step_limit * 2 * N));
     A(apg::dev_alloc(&e->b.d_stamp_q, (size_t)cfg->step_limit * N));
   }
+  A(apg::dev_alloc(&e->d_acc1, N)); A(apg::dev_alloc(&e->d_acc2, N)); A(apg::dev_alloc(&e->d_acc_ret, N));
+  A(apg::dev_alloc(&e->b.d_ep_avg1, N)); A(apg::dev_alloc(&e->b.d_ep_final1, N)); A(apg::dev_alloc(&e->b.d_ep_avg2, N));
+  A(apg::dev_alloc(&e->b.d_ep_final2, N)); A(apg::dev_alloc(&e->b.d_ep_return, N));
+  A(apg::dev_alloc(&e->b.d_first_correct, N)); A(apg::dev_alloc(&e->b.d_last_incorrect, N));
+  A(apg::dev_alloc(&e->d_stats, (size_t)APG_NUM_STATS));
   A(apg::dev_alloc(&e->d_st_idx, N));
   A(apg::dev_alloc(&e->d_st_label, N));
   A(apg::dev_alloc(&e->d_st_inv, N));
@@ -701,6 +750,9 @@ void apg_image_destroy(apg_image_env* e) {
   apg::dev_free(e->b.d_target_xy); apg::dev_free(e->b.d_terminated); apg::dev_free(e->b.d_truncated);
   apg::dev_free(e->b.d_index); apg::dev_free(e->b.d_pos); apg::dev_free(e->b.d_cur_target_xy);
   apg::dev_free(e->b.d_visited); apg::dev_free(e->b.d_stamp_xy); apg::dev_free(e->b.d_stamp_q);
+  apg::dev_free(e->d_acc1); apg::dev_free(e->d_acc2); apg::dev_free(e->d_acc_ret); apg::dev_free(e->d_stats);
+  apg::dev_free(e->b.d_ep_avg1); apg::dev_free(e->b.d_ep_final1); apg::dev_free(e->b.d_ep_avg2); apg::dev_free(e->b.d_ep_final2);
+  apg::dev_free(e->b.d_ep_return); apg::dev_free(e->b.d_first_correct); apg::dev_free(e->b.d_last_incorrect);
   apg::dev_free(e->d_st_idx); apg::dev_free(e->d_st_label); apg::dev_free(e->d_st_inv); apg::dev_free(e->d_err);
   apg::dev_free(e->d_in_action); apg::dev_free(e->d_in_pred);
   for (auto& s : e->ring) {
@@ -841,6 +893,15 @@ int apg_image_get_buffers(apg_image_env* e, apg_image_buffers* out) {
   out->stamp_count = e->needs_reset ? e->cfg.step_limit : e->t;
   out->elapsed = e->t;
   out->needs_reset = e->needs_reset ? 1 : 0;
+  return APG_OK;
+}
+
+int apg_image_get_stats(apg_image_env* e, double* h_stats, int clear) {
+  APG_CHECK(e && h_stats, APG_ERR_INVALID, "null argument");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaMemcpyAsync(h_stats, e->d_stats, APG_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (clear) APG_CUDA(cudaMemsetAsync(e->d_stats, 0, APG_NUM_STATS * sizeof(double), e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
   return APG_OK;
 }
 

@@ -65,6 +65,10 @@ struct LidarParams {
   float* dists;             // (N,B) optional raw distances
   float* reward2;
   unsigned char* done2;
+  // episode statistics (ActiveRegressionLogWrapper): running sums, per-env results at `terminated`, shard sums
+  float* acc1; float* acc2; float* acc_ret;
+  float* ep_avg1; float* ep_final1; float* ep_avg2; float* ep_final2; float* ep_return;
+  double* stats;
   unsigned* err;
 };
 
@@ -351,6 +355,20 @@ __global__ void __launch_bounds__(kThreads) lidar_step_kernel(const LidarParams 
     term = (oob || elapsed >= p.T) ? 1 : 0;
     if (li == 0) {
       const float rew = __fsub_rn(base, loss);
+      // euclidean_distance = ||target - prediction|| (float32, no axis), mse = mean((target - prediction)^2)
+      const float m1 = norm2f(e0, e1), m2 = mse;
+      const bool first = (elapsed == 1);
+      const float s1 = __fadd_rn(first ? 0.0f : p.acc1[n], m1);
+      const float s2 = __fadd_rn(first ? 0.0f : p.acc2[n], m2);
+      const float sr = __fadd_rn(first ? 0.0f : p.acc_ret[n], rew);
+      if (term) {
+        const float avg1 = __fdiv_rn(s1, (float)elapsed), avg2 = __fdiv_rn(s2, (float)elapsed);
+        p.ep_avg1[n] = avg1; p.ep_final1[n] = m1; p.ep_avg2[n] = avg2; p.ep_final2[n] = m2; p.ep_return[n] = sr;
+        atomicAdd(p.stats + 0, 1.0); atomicAdd(p.stats + 1, (double)avg1); atomicAdd(p.stats + 2, (double)m1);
+        atomicAdd(p.stats + 3, (double)avg2); atomicAdd(p.stats + 4, (double)m2); atomicAdd(p.stats + 5, (double)sr);
+      } else {
+        p.acc1[n] = s1; p.acc2[n] = s2; p.acc_ret[n] = sr;
+      }
       p.reward[n] = rew;
       p.base_reward[n] = base;
       p.loss[n] = loss;
@@ -417,6 +435,8 @@ struct apg_lidar_env {
   unsigned* d_err = nullptr;
   float* d_in_action = nullptr;
   float* d_in_pred = nullptr;
+  float* d_acc1 = nullptr; float* d_acc2 = nullptr; float* d_acc_ret = nullptr;
+  double* d_stats = nullptr;
   bool has_reset = false;
 };
 
@@ -437,6 +457,8 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   p.terminated = e->b.d_terminated; p.truncated = e->b.d_truncated; p.stepped = e->b.d_stepped;
   p.map_idx_out = reinterpret_cast<long long*>(e->b.d_map_idx); p.cells = e->b.d_cells; p.dists = e->b.d_dists;
   p.reward2 = reward2; p.done2 = done2; p.err = e->d_err;
+  p.acc1 = e->d_acc1; p.acc2 = e->d_acc2; p.acc_ret = e->d_acc_ret; p.ep_avg1 = e->b.d_ep_avg1; p.ep_final1 = e->b.d_ep_final1;
+  p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return; p.stats = e->d_stats;
   const int groups_per_block = kThreads / e->G;
   const int grid = apg::ceil_div(c.num_envs, groups_per_block);
   lidar_step_kernel<<<grid, kThreads, e->smem, e->stream>>>(p);
@@ -493,6 +515,10 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
     A(apg::dev_alloc(&e->b.d_cells, N * B * 2));
     A(apg::dev_alloc(&e->b.d_dists, N * B));
   }
+  A(apg::dev_alloc(&e->d_acc1, N)); A(apg::dev_alloc(&e->d_acc2, N)); A(apg::dev_alloc(&e->d_acc_ret, N));
+  A(apg::dev_alloc(&e->b.d_ep_avg1, N)); A(apg::dev_alloc(&e->b.d_ep_final1, N)); A(apg::dev_alloc(&e->b.d_ep_avg2, N));
+  A(apg::dev_alloc(&e->b.d_ep_final2, N)); A(apg::dev_alloc(&e->b.d_ep_return, N));
+  A(apg::dev_alloc(&e->d_stats, (size_t)APG_NUM_STATS));
   A(apg::dev_alloc(&e->d_aliased, N));
   A(apg::dev_alloc(&e->d_elapsed, N));
   A(apg::dev_alloc(&e->d_map_idx, N));
@@ -523,6 +549,9 @@ void apg_lidar_destroy(apg_lidar_env* e) {
   apg::dev_free(e->b.d_terminated); apg::dev_free(e->b.d_truncated); apg::dev_free(e->b.d_stepped);
   apg::dev_free(e->b.d_map_idx); apg::dev_free(e->b.d_pos); apg::dev_free(e->b.d_initial_pos);
   apg::dev_free(e->b.d_cells); apg::dev_free(e->b.d_dists);
+  apg::dev_free(e->d_acc1); apg::dev_free(e->d_acc2); apg::dev_free(e->d_acc_ret); apg::dev_free(e->d_stats);
+  apg::dev_free(e->b.d_ep_avg1); apg::dev_free(e->b.d_ep_final1); apg::dev_free(e->b.d_ep_avg2); apg::dev_free(e->b.d_ep_final2);
+  apg::dev_free(e->b.d_ep_return);
   apg::dev_free(e->d_aliased); apg::dev_free(e->d_elapsed); apg::dev_free(e->d_map_idx); apg::dev_free(e->d_prev_done);
   apg::dev_free(e->d_g0); apg::dev_free(e->d_g2); apg::dev_free(e->d_err);
   apg::dev_free(e->d_in_action); apg::dev_free(e->d_in_pred);
@@ -619,6 +648,15 @@ int apg_lidar_step_host(apg_lidar_env* e, const float* h_action, const float* h_
 int apg_lidar_get_buffers(apg_lidar_env* e, apg_lidar_buffers* out) {
   APG_CHECK(e && out, APG_ERR_INVALID, "null argument");
   *out = e->b;
+  return APG_OK;
+}
+
+int apg_lidar_get_stats(apg_lidar_env* e, double* h_stats, int clear) {
+  APG_CHECK(e && h_stats, APG_ERR_INVALID, "null argument");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaMemcpyAsync(h_stats, e->d_stats, APG_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (clear) APG_CUDA(cudaMemsetAsync(e->d_stats, 0, APG_NUM_STATS * sizeof(double), e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
   return APG_OK;
 }
 

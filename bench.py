@@ -362,11 +362,8 @@ def main():
     h2d = n * (2 + pw) * 4
     d2h = n * (4 + 1 + 1)
 
-    # ---- final NCCL reduce of run statistics (the only collective of the data path)
-    stats = torch.stack([env._views["reward"].double().sum(), env._views["loss"].double().sum(),
-                         torch.tensor(float(n), device=dev, dtype=torch.float64)])
-    if world > 1:
-        dist.all_reduce(stats)
+    # ---- final NCCL reduce of the device-side episode statistics (the only collective of the data path)
+    stats = env.episode_stats(reduce=True)
     env.sync()
 
     if rank == 0:
@@ -393,7 +390,7 @@ def main():
                          "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel": "lidar_step_kernel" if is_lidar else "image_step_kernel", "bytes_per_env_step": w["bytes_per_step"],
                          "avg_launch_us": avg_launch_s * 1e6},
-            "final_stats_allreduce": {"mean_reward_last_step": float(stats[0] / stats[2]), "mean_loss_last_step": float(stats[1] / stats[2])},
+            "episode_stats_allreduce": stats,
         }
         if not args.no_cpu_baseline and world == 1:
             n_cpu, st_cpu = {"mnist": (4096, 680), "tinyloc": (256, 1020), "lidar_rooms": (2048, 303), "lidar_maze": (256, 808)}[args.workload]

@@ -98,6 +98,17 @@ typedef struct {
   uint32_t* d_visited;       /* (N, H, ceil(W/32)) image-resolution visited bitmask              */
   int32_t* d_stamp_xy;       /* (T, 2, N) overlay stamp log: render-resolution rectangle centres */
   float* d_stamp_q;          /* (T, N)    overlay stamp log: clipped prediction quality          */
+  /* per-env episode statistics, valid for envs whose `terminated` flag is set by the step (they replace the
+   * python loops of ActiveClassification/RegressionVectorLogWrapper, active_classification_env.py:149-197,
+   * active_regression_env.py:204-227): metric 1 = correct_label_prob | euclidean_distance,
+   * metric 2 = accuracy | mse; avg over the episode's real steps and the final step's value */
+  float* d_ep_avg1;          /* (N,) */
+  float* d_ep_final1;        /* (N,) */
+  float* d_ep_avg2;          /* (N,) */
+  float* d_ep_final2;        /* (N,) */
+  float* d_ep_return;        /* (N,) sum of rewards over the episode's real steps */
+  int32_t* d_first_correct;  /* (N,) classification: first step with accuracy 1, -1 if none */
+  int32_t* d_last_incorrect; /* (N,) classification: last step with accuracy 0, -1 if none */
   int32_t stamp_count;       /* number of valid stamps of the current episode (host mirror)      */
   int32_t elapsed;           /* current time step t of the (shared) episode clock                */
   int32_t needs_reset;       /* 1 when the next step is the NEXT_STEP autoreset step             */
@@ -142,6 +153,12 @@ int apg_image_step_host(apg_image_env* env, const float* h_action, const float* 
                         uint8_t* h_terminated, uint8_t* h_truncated, float* h_glimpse);
 
 int apg_image_get_buffers(apg_image_env* env, apg_image_buffers* out);
+/* Episode statistics accumulated on the device since creation / the last clear, summed over this shard's envs
+ * (the payload of the final NCCL reduce): h_stats[0] = finished episodes, [1] = sum of per-episode avg metric 1,
+ * [2] = sum of final metric 1, [3] = sum of avg metric 2, [4] = sum of final metric 2, [5] = sum of episode
+ * returns, [6], [7] reserved (0).  Synchronises the stream. */
+#define APG_NUM_STATS 8
+int apg_image_get_stats(apg_image_env* env, double* h_stats, int clear);
 /* Reads (and with clear!=0 resets) the sticky device error flags; synchronises the stream. */
 int apg_image_poll_error(apg_image_env* env, uint32_t* flags, int clear);
 int apg_image_sync(apg_image_env* env);
@@ -185,6 +202,11 @@ typedef struct {
   int64_t* d_map_idx;    /* (N,)  info["map_idx"]                                      */
   float* d_pos;          /* (N,2) state: position in map cells (x, y)                  */
   float* d_initial_pos;  /* (N,2) state: odometry origin                               */
+  float* d_ep_avg1;      /* (N,) episode statistics (valid where `terminated`): avg / final euclidean_distance, */
+  float* d_ep_final1;    /* (N,)   avg / final mse, episode return -- ActiveRegressionLogWrapper,               */
+  float* d_ep_avg2;      /* (N,)   active_regression_env.py:141-157                                             */
+  float* d_ep_final2;    /* (N,) */
+  float* d_ep_return;    /* (N,) */
   int32_t* d_cells;      /* (N,B,2) contact cell (x, y) or (-1,-1) per beam (emit_cells) */
   float* d_dists;        /* (N,B)   raw float32 scan distances (emit_cells)            */
 } apg_lidar_buffers;
@@ -208,6 +230,7 @@ int apg_lidar_rollout(apg_lidar_env* env, const float* d_actions, const float* d
 int apg_lidar_step_host(apg_lidar_env* env, const float* h_action, const float* h_pred, float* h_reward,
                         uint8_t* h_terminated, uint8_t* h_truncated, float* h_lidar);
 int apg_lidar_get_buffers(apg_lidar_env* env, apg_lidar_buffers* out);
+int apg_lidar_get_stats(apg_lidar_env* env, double* h_stats, int clear); /* same layout as apg_image_get_stats */
 int apg_lidar_poll_error(apg_lidar_env* env, uint32_t* flags, int clear);
 int apg_lidar_sync(apg_lidar_env* env);
 
