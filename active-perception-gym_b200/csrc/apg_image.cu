@@ -39,6 +39,7 @@ struct ImgParams {
   int pitch;         // bytes per staged tile row
   int tile_rows;     // staged rows per environment
   int tile_bytes;    // pitch * tile_rows
+  int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
   int t_stamp;       // overlay stamp slot of this step (pre-move time index), mode 0 only
   float time_obs;    // obs["time_step"] value after this step
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 
   for (int set = 0; set < n_sets; ++set) {
     // ------------------------------------------------------------------ phase A: thread = environment
-    for (int el = tid; el < nE; el += kThreads) {
+    for (int el = tid; el < nE; el += blockDim.x) {
       const int n = env0 + el;
       unsigned err = 0;
       if (set == 0) {
@@ -309,12 +310,11 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
         p.time_step[n] = p.time_obs;
       }
-
       // ---- taps of this set's glimpse and the asynchronous staging of its bank footprint
       const double ccx = (set == 0) ? px * p.lim_x : tcx;
       const double ccy = (set == 0) ? py * p.lim_y : tcy;
-      Tap* rows = s_taps + (size_t)el * (p.S0 + p.S1);
-      Tap* cols = rows + p.S0;
+      Tap* rows = s_taps + el;                 // tap k of this env: rows[k * E]
+      Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
       int rmin = 0, rmax = 0, cmin = 0, cmax = 0;
       for (int i = 0; i < p.S0; ++i) {
         const double y = ccy + ((double)i - p.half0) * p.scale;
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         tap(y, p.offy, p.H, k, w);
         if (i == 0) rmin = k;
         rmax = k + 1;
-        rows[i].w = w;
-        rows[i].k = k - rmin;
+        rows[i * p.E].w = w;
+        rows[i * p.E].k = k - rmin;
       }
       for (int j = 0; j < p.S1; ++j) {
         const double x = ccx + ((double)j - p.half1) * p.scale;
@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         tap(x, p.offx, p.W, k, w);
         if (j == 0) cmin = k;
         cmax = k + 1;
-        cols[j].w = w;
-        cols[j].k = k;
+        cols[j * p.E].w = w;
+        cols[j * p.E].k = k;
       }
       const int nrows = min(rmax - rmin + 1, p.tile_rows);
       const int first_byte = cmin * p.C * ES;
@@ -362,6 +362,86 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
     __syncthreads();
     if (ep_end && set == 0 && tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
 
+    if (p.thread_blend) {
+      // -------------------------------------------------------------- phase B (small glimpses): thread = environment
+      // A 5x5 glimpse is too small to occupy a warp; every thread blends its own environment's window from its tile
+      // (no redundant work, no per-environment warp overhead), parks the floats in shared memory with an odd stride
+      // (conflict-free) and the block then streams them out as one contiguous, fully coalesced run.
+      float* s_out = reinterpret_cast<float*>(s_tile + (size_t)p.E * p.tile_bytes);
+      const int Pp = p.P | 1;  // odd stride in floats
+      for (int el = tid; el < nE; el += blockDim.x) {
+        const EnvHdr h = s_hdr[el];
+        const Tap* rows = s_taps + el;
+        const Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
+        const BankT* tile = reinterpret_cast<const BankT*>(s_tile + (size_t)el * p.tile_bytes + h.lead);
+        const int pitch_e = p.pitch / ES;
+        float* o = s_out + (size_t)el * Pp;
+        for (int j = 0; j < p.S1; ++j) {
+          const Tap ct = cols[j * p.E];
+          const double wx = ct.w, omx = 1.0 - ct.w;
+          const BankT* colp = tile + (ct.k - h.cmin) * p.C;
+          for (int c = 0; c < p.C; ++c) {
+            int prev_k = -4;
+            double b0 = 0.0, b1 = 0.0;
+            for (int i = 0; i < p.S0; ++i) {
+              const Tap rt = rows[i * p.E];
+              const BankT* rp = colp + rt.k * pitch_e + c;
+              double p00, p01;
+              if (rt.k == prev_k + 1) {
+                p00 = b0;
+                p01 = b1;
+              } else {
+                p00 = px_to_f64(rp[0]);
+                p01 = px_to_f64(rp[p.C]);
+              }
+              const double p10 = px_to_f64(rp[pitch_e]), p11 = px_to_f64(rp[pitch_e + p.C]);
+              b0 = p10;
+              b1 = p11;
+              prev_k = rt.k;
+              const double wy = rt.w, omy = 1.0 - rt.w;
+              double acc = 0.0 + p00 * (omy * omx);
+              acc = acc + p01 * (omy * wx);
+              acc = acc + p10 * (wy * omx);
+              acc = acc + p11 * (wy * wx);
+              o[(i * p.S1 + j) * p.C + c] = (ES == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
+            }
+          }
+        }
+        if (p.track && set == 0) {
+          unsigned* vm = p.visited + (size_t)(env0 + el) * p.H * p.words;
+          if (p.mode != 0)
+            for (int q = 0; q < p.H * p.words; ++q) vm[q] = 0u;
+          for (int w = 0; w < p.words; ++w) {
+            unsigned bits = 0u;
+            for (int jj = 0; jj < p.S1; ++jj) {
+              const int j0 = cols[jj * p.E].k;
+              if ((j0 >> 5) == w) bits |= 1u << (j0 & 31);
+              if (((j0 + 1) >> 5) == w) bits |= 1u << ((j0 + 1) & 31);
+            }
+            if (!bits) continue;
+            int last = -1;  // tap rows are non-decreasing
+            for (int i = 0; i < p.S0; ++i) {
+              const int r0 = h.rmin + rows[i * p.E].k;
+              if (r0 > last) atomicOr(vm + r0 * p.words + w, bits);
+              if (r0 + 1 > last) atomicOr(vm + (r0 + 1) * p.words + w, bits);
+              last = r0 + 1;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      float* out_blk = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
+      const int total = nE * p.P;
+      int el_c = tid / p.P, off_c = tid - el_c * p.P;  // (environment, float) of flat index q, advanced incrementally
+      for (int q = tid; q < total; q += blockDim.x) {
+        out_blk[q] = s_out[el_c * Pp + off_c];
+        off_c += blockDim.x;
+        while (off_c >= p.P) { off_c -= p.P; ++el_c; }
+      }
+      if (set + 1 < n_sets) __syncthreads();
+      continue;
+    }
+
     // ------------------------------------------------------------------ phase B: warp = environment, lane = sensor element
     const int G = p.S1 * p.C;
     const int cpp = min(G, 32);
@@ -370,10 +450,10 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
     const int r_sub = lane / cpp;
     const int jc0 = lane - r_sub * cpp;
     float* out_set = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
-    for (int el = warp; el < nE; el += kThreads / 32) {
+    for (int el = warp; el < nE; el += blockDim.x >> 5) {
       const EnvHdr h = s_hdr[el];
-      const Tap* rows = s_taps + (size_t)el * (p.S0 + p.S1);
-      const Tap* cols = rows + p.S0;
+      const Tap* rows = s_taps + el;
+      const Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
       const unsigned char* tile = s_tile + (size_t)el * p.tile_bytes;
       float* out = out_set + (size_t)el * p.P;
       unsigned colbits0 = 0u, colbits1 = 0u;
@@ -382,7 +462,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         const bool col_ok = (jc < G) && (r_sub < R);
         const int j = (p.C == 1) ? jc : ((p.C == 3) ? (int)(((unsigned)jc * 43691u) >> 17) : jc / p.C);
         const int c = jc - j * p.C;
-        const Tap ct = cols[min(j, p.S1 - 1)];
+        const Tap ct = cols[min(j, p.S1 - 1) * p.E];
         const double wx = ct.w, omx = 1.0 - ct.w;
         if (set == 0 && col_ok && r_sub == 0) {
           const int j0 = ct.k;
@@ -399,7 +479,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         double b0 = 0.0, b1 = 0.0;
         for (int i = r_sub; i < p.S0; i += R, outp += out_step) {
           if (col_ok) {
-            const Tap rt = rows[i];
+            const Tap rt = rows[i * p.E];
             const BankT* rp = colp + rt.k * pitch_e;
             double p00, p01;
             if (R == 1 && rt.k == prev_k + 1) {
@@ -435,7 +515,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
           unsigned my = (w == 0) ? colbits0 : ((w == 1) ? colbits1 : 0u);
           if (w >= 2) {  // images wider than 64 px
             for (int jj = lane; jj < p.S1; jj += 32) {
-              const int j0 = cols[jj].k;
+              const int j0 = cols[jj * p.E].k;
               if ((j0 >> 5) == w) my |= 1u << (j0 & 31);
               if (((j0 + 1) >> 5) == w) my |= 1u << ((j0 + 1) & 31);
             }
@@ -443,7 +523,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
           const unsigned bits = __reduce_or_sync(0xffffffffu, my);
           if (bits) {
             for (int rr = lane; rr < 2 * p.S0; rr += 32) {
-              const int row = h.rmin + ((rr < p.S0) ? rows[rr].k : rows[rr - p.S0].k + 1);
+              const int row = h.rmin + ((rr < p.S0) ? rows[rr * p.E].k : rows[(rr - p.S0) * p.E].k + 1);
               atomicOr(vm + row * p.words + w, bits);  // no return value -> RED: nothing waits for the old word
             }
           }
@@ -463,7 +543,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 struct apg_image_env {
   apg_image_cfg cfg{};
   cudaStream_t stream = nullptr;
-  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0;
+  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -538,7 +618,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -592,9 +672,9 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
 
   const int grid = apg::ceil_div(c.num_envs, e->E);
 if (c.bank_dtype == APG_BANK_U8)
-    image_step_kernel<unsigned char><<<grid, kThreads, e->smem, e->stream>>>(p);
+    image_step_kernel<unsigned char><<<grid, e->threads, e->smem, e->stream>>>(p);
   else
-    image_step_kernel<float><<<grid, kThreads, e->smem, e->stream>>>(p);
+    image_step_kernel<float><<<grid, e->threads, e->smem, e->stream>>>(p);
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
   e->t = t_after;
@@ -662,15 +742,28 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     if (pitch > row_bytes) pitch = row_bytes;
     e->pitch = pitch;
     e->tile_rows = span_rows < cfg->height ? span_rows : cfg->height;
-    const size_t per_env = 16 + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->pitch * e->tile_rows;
-    int E = (int)((72 * 1024) / per_env);  // ~3 blocks of 72 KB per SM keep >= 190 footprints in flight
-    // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
-    // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
-    E = E > 64 ? 64 : E;
-    if (per_env > 768 && E > 32) E = 32;
+    size_t per_env = sizeof(EnvHdr) + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->pitch * e->tile_rows;
+    // small glimpses (<= 96 floats, e.g. 5x5x1 / 5x5x3): one thread blends a whole environment
+    e->thread_blend = e->P <= 96 ? 1 : 0;
+    if (const char* ov = getenv("APG_IMG_THREAD_BLEND")) e->thread_blend = atoi(ov) ? 1 : 0;
+    int E;
+    if (e->thread_blend) {
+      per_env += (size_t)(e->P | 1) * 4;  // parked output floats
+      E = (int)((64 * 1024) / per_env);
+      E = E >= 64 ? 64 : 32;  // swept on B200: 64 beats 32 and 128 for the 5x5x1 MNIST glimpse
+      e->threads = E;
+    } else {
+      // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
+      // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
+      E = (int)((72 * 1024) / per_env);
+      E = E > 64 ? 64 : E;
+      if (per_env > 768 && E > 32) E = 32;
+      e->threads = kThreads;
+    }
     if (const char* ov = getenv("APG_IMG_ENVS_PER_BLOCK")) {
       const int v = atoi(ov);
       if (v >= 1 && v <= kThreads && (size_t)v * per_env <= 200 * 1024) E = v;
+      if (e->thread_blend) e->threads = ((E + 31) / 32) * 32;
     }
     E = E >= 8 ? (E & ~7) : (E >= 4 ? 4 : (E >= 2 ? 2 : 1));
     e->E = E;

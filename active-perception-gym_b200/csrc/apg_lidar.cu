@@ -78,7 +78,7 @@ struct MapView {
 };
 
 __device__ __forceinline__ int is_wall(const MapView& m, int x, int y) {
-  if (x < 0 || y < 0 || x >= m.W || y >= m.H) return 0;
+  if ((unsigned)x >= (unsigned)m.W || (unsigned)y >= (unsigned)m.H) return 0;
   return (int)((m.bits[y * m.words + (x >> 5)] >> (x & 31)) & 1u);
 }
 
@@ -91,6 +91,8 @@ __device__ float scan_one(const MapView& m, float posx, float posy, float tx, fl
   const double px = posx, py = posy;
   const double dx = (double)tx - px, dy = (double)ty - py;
   const int sx = dx > 0 ? 1 : (dx < 0 ? -1 : 0), sy = dy > 0 ? 1 : (dy < 0 ? -1 : 0);
+  // one IEEE reciprocal per ray and axis; every crossing parameter is (g - p) * inv (oracle/lidar_oracle.c)
+  const double inv_dx = sx != 0 ? __ddiv_rn(1.0, dx) : 0.0, inv_dy = sy != 0 ? __ddiv_rn(1.0, dy) : 0.0;
   const bool px_int = (px == floor(px)), py_int = (py == floor(py));
   int cx = (int)floor(px), cy = (int)floor(py);
   if (px_int && sx < 0) cx -= 1;
@@ -112,8 +114,8 @@ __device__ float scan_one(const MapView& m, float posx, float posy, float tx, fl
   }
   // the crossing parameters are refreshed only for the axis that advanced: same values as recomputing both
   double tX = INFINITY, tY = INFINITY, gx = 0.0, gy = 0.0;
-  if (sx != 0) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = __ddiv_rn(gx - px, dx); }
-  if (sy != 0) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = __ddiv_rn(gy - py, dy); }
+  if (sx != 0) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = (gx - px) * inv_dx; }
+  if (sy != 0) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = (gy - py) * inv_dy; }
   for (;;) {
     const double tN = tX < tY ? tX : tY;
     if (!(tN <= 1.0)) break;
@@ -135,8 +137,8 @@ __device__ float scan_one(const MapView& m, float posx, float posy, float tx, fl
       if (next_wall) { in_iv = true; iv_t0 = tN; } else n_zero++;
     }
     cx = ncx; cy = ncy;
-    if (stepx) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = __ddiv_rn(gx - px, dx); }
-    if (stepy) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = __ddiv_rn(gy - py, dy); }
+    if (stepx) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = (gx - px) * inv_dx; }
+    if (stepy) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = (gy - py) * inv_dy; }
     // a ray that has left the map and keeps moving away never meets another cell of the union
     if (!in_iv && ((cx < 0 && sx <= 0) || (cx >= m.W && sx >= 0) || (cy < 0 && sy <= 0) || (cy >= m.H && sy >= 0)) &&
         !nbx && !nby)
@@ -211,7 +213,7 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
   return n;
 }
 
-__global__ void __launch_bounds__(kThreads) lidar_step_kernel(const LidarParams p) {
+__global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarParams p) {
   extern __shared__ unsigned smem_maps[];  // one (H*words) slot per group
   const int tid = threadIdx.x;
   const int groups_per_block = kThreads / p.G;

@@ -16,7 +16,8 @@
  *
  * Geometry model (identical in oracle/shim/shapely/__init__.py and in the CUDA kernel):
  *   the segment p->t (float64 copies of the float32 end points) is walked cell by cell; the parameter of every
- *   grid-line crossing is (g - p) / d, one IEEE division; crossings with tX == tY are lattice corners where the
+ *   grid-line crossing is (g - p) * (1 / d) with the reciprocal taken once per segment and axis; crossings with
+ *   tX == tY are lattice corners where the
  *   two side cells touch the segment in a single point.  The walk yields the parameter intervals of the
  *   intersection with the union of closed wall cells: `n_pos` intervals of positive length, `n_zero` isolated
  *   points, and the entry vertex of the first one (crossed coordinate snapped to the integer grid line).
@@ -51,6 +52,7 @@ float apg_oracle_scan_one(const uint32_t* bits, int W, int H, int words, float p
   const double px = posx, py = posy;
   const double dx = (double)tx - px, dy = (double)ty - py;
   const int sx = dx > 0 ? 1 : (dx < 0 ? -1 : 0), sy = dy > 0 ? 1 : (dy < 0 ? -1 : 0);
+  const double inv_dx = sx != 0 ? 1.0 / dx : 0.0, inv_dy = sy != 0 ? 1.0 / dy : 0.0;
   const int px_int = (px == floor(px)), py_int = (py == floor(py));
   int cx = (int)floor(px), cy = (int)floor(py);
   if (px_int && sx < 0) cx -= 1;
@@ -76,8 +78,8 @@ float apg_oracle_scan_one(const uint32_t* bits, int W, int H, int words, float p
 
   for (;;) {
     double tX = INFINITY, tY = INFINITY, gx = 0.0, gy = 0.0;
-    if (sx != 0) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = (gx - px) / dx; }
-    if (sy != 0) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = (gy - py) / dy; }
+    if (sx != 0) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = (gx - px) * inv_dx; }
+    if (sy != 0) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = (gy - py) * inv_dy; }
     const double tN = tX < tY ? tX : tY;
     if (!(tN <= 1.0)) break; /* the segment ends inside the current cell */
     const int stepx = tX <= tY, stepy = tY <= tX;

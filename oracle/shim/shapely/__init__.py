@@ -12,8 +12,9 @@ closed unit squares; it is NOT GEOS.  LIDAR parity against real GEOS therefore s
 Geometry model (shared with oracle/lidar_oracle.c and the CUDA kernel):
   * wall cells are CLOSED unit squares [cx, cx+1] x [cy, cy+1];
   * the segment p->t is clipped against every wall cell near its bounding box with Liang-Barsky in
-    float64, every line parameter being computed as (grid_line - p) / d  (one IEEE division, the
-    same expression the DDA uses, so both produce bit-identical parameters);
+    float64, every line parameter being computed as (grid_line - p) * (1 / d)  (the reciprocal of each
+    direction component is taken once per segment; the same expression the DDA uses, so both produce
+    bit-identical parameters);
   * touching/overlapping parameter intervals are merged; a merged interval with t0 == t1 is a Point,
     otherwise a LineString; pieces are ordered and oriented along the ray;
   * the entry vertex of a piece is p + t0 * d with the coordinate(s) on the crossed grid line(s)
@@ -106,7 +107,8 @@ class _Cells(_G):
                             break
                         par.append(None)
                     else:
-                        a, b = (lo - p) / d, (hi - p) / d
+                        inv = 1.0 / d
+                        a, b = (lo - p) * inv, (hi - p) * inv
                         ga, gb = float(lo), float(hi)
                         if a > b:
                             a, b, ga, gb = b, a, gb, ga
