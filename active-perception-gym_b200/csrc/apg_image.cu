@@ -128,6 +128,41 @@ struct __align__(16) EnvHdr {
   int nrows;    // staged rows
 };
 
+// One lane's column of the sensor window (warp-per-environment path): walks the sensor rows i_first, i_first +
+// i_step, ... of one (column, channel), blending from the staged tile.  With one sensor row per pass (VREUSE) the
+// bottom taps of row i are the top taps of row i+1 unless the taps are not consecutive (clamped border / scaled
+// sensor), which is uniform across the warp.  CT > 0 fixes the channel count at compile time.
+template <typename BankT, int CT, bool VREUSE>
+__device__ __forceinline__ void blend_column(const BankT* __restrict__ colp, const Tap* __restrict__ tp, int tap_step,
+                                             int pitch_e, int c_rt, int n_rows, double wx, double omx,
+                                             float* __restrict__ outp, int out_step, bool store_ok) {
+  const int C = CT ? CT : c_rt;
+  int prev_k = -4;
+  double b0 = 0.0, b1 = 0.0;
+  for (int i = 0; i < n_rows; ++i, tp += tap_step, outp += out_step) {
+    const Tap rt = *tp;
+    const BankT* rp = colp + rt.k * pitch_e;
+    double p00 = b0, p01 = b1;
+    if (!VREUSE || rt.k != prev_k + 1) {
+      p00 = px_to_f64(rp[0]);
+      p01 = px_to_f64(rp[C]);
+    }
+    rp += pitch_e;
+    const double p10 = px_to_f64(rp[0]), p11 = px_to_f64(rp[C]);
+    b0 = p10;
+    b1 = p11;
+    prev_k = rt.k;
+    const double wy = rt.w, omy = 1.0 - rt.w;
+    double acc = p00 * (omy * omx);  // the reference's leading `0.0 +` is an exact no-op for products >= +0
+    acc = acc + p01 * (omy * wx);
+    acc = acc + p10 * (wy * omx);
+    acc = acc + p11 * (wy * wx);
+    // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
+    const float v = (sizeof(BankT) == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
+    if (store_ok) *outp = v;
+  }
+}
+
 // A block owns E consecutive environments and works in three phases per glimpse set:
 //   A  thread e: the per-environment scalars (move, loss, reward, flags, overlay stamp), the S0+S1 bilinear
 //      taps (-> shared memory) and the asynchronous staging (cp.async, LDGSTS) of the glimpse's bank footprint
@@ -473,36 +508,20 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         }
         const BankT* colp = reinterpret_cast<const BankT*>(tile + h.lead) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
         const int pitch_e = p.pitch / ES;
-        float* outp = out + r_sub * G + jc;
-        const int out_step = R * G;
-        int prev_k = -4;
-        double b0 = 0.0, b1 = 0.0;
-        for (int i = r_sub; i < p.S0; i += R, outp += out_step) {
-          if (col_ok) {
-            const Tap rt = rows[i * p.E];
-            const BankT* rp = colp + rt.k * pitch_e;
-            double p00, p01;
-            if (R == 1 && rt.k == prev_k + 1) {
-              p00 = b0;
-              p01 = b1;
-            } else {
-              p00 = px_to_f64(rp[0]);
-              p01 = px_to_f64(rp[p.C]);
-            }
-            rp += pitch_e;
-            const double p10 = px_to_f64(rp[0]), p11 = px_to_f64(rp[p.C]);
-            b0 = p10;
-            b1 = p11;
-            prev_k = rt.k;
-            const double wy = rt.w, omy = 1.0 - rt.w;
-            double acc = 0.0 + p00 * (omy * omx);
-            acc = acc + p01 * (omy * wx);
-            acc = acc + p10 * (wy * omx);
-            acc = acc + p11 * (wy * wx);
-            // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
-            *outp = (ES == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
-          }
-        }
+        float* outp = out + min(r_sub, p.S0 - 1) * G + (col_ok ? jc : 0);
+        // lanes without a column (or a row) run the same loads on valid addresses and skip the store
+        const int first = min(r_sub, p.S0 - 1);
+        const int n_rows = (p.S0 - first + R - 1) / R;
+        const Tap* tp = rows + first * p.E;
+        if (R == 1 && p.C == 3)
+          blend_column<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wx, omx, outp, G, col_ok);
+        else if (R == 1 && p.C == 1)
+          blend_column<BankT, 1, true>(colp, tp, p.E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
+        else if (R == 1)
+          blend_column<BankT, 0, true>(colp, tp, p.E, pitch_e, p.C, n_rows, wx, omx, outp, G, col_ok);
+        else
+          blend_column<BankT, 0, false>(colp, tp, R * p.E, pitch_e, p.C, n_rows, wx, omx, outp, R * G,
+                                        col_ok && r_sub < p.S0);
       }
       // ---- visited bitmask of the observation glimpse: rows {i0, i0+1} x columns {j0, j0+1}
       if (p.track && set == 0) {
