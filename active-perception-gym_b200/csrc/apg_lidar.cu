@@ -9,10 +9,10 @@
 //   * TimeLimit termination + time_step obs                 time_limit.py:113-139
 //   * B-beam scan against the occupancy bitmap              envs/lidar_localization2d.py:238-277,496-536
 //
-// Mapping: a group of G = min(32, pow2 >= B) lanes owns one environment (a whole warp for B >= 32).  The
-// environment's bit-packed map rows are staged in shared memory once per step; the collision/slide rays are
-// evaluated redundantly by every lane of the group (uniform control flow, no divergence), then each lane casts
-// the beams b = lane, lane+G, ... and stores coalesced runs of the lidar row.
+// Mapping: a block owns 32 environments.  Their bit-packed maps are staged in shared memory once per step; the
+// serial part of an environment's step (collision ray, then up to two wall-slide rays) runs with lane = environment,
+// so 32 environments advance in parallel; the B beams then run with a group of G = min(32, pow2 >= B) lanes per
+// environment, lane l casting beams l, l+G, ... and storing coalesced runs of the lidar row (see lidar_step_kernel).
 //
 // Ray casting = the closed-cell grid walk of oracle/lidar_oracle.c, same IEEE operations in the same order
 // (file compiled with -fmad=false; the one fused operation is the explicit fma of the float64 dot product).
@@ -27,6 +27,7 @@ namespace {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kEnvsPerBlock = 32;
 
 struct LidarParams {
   int N, W, H, words, B, G, T, M;
@@ -86,63 +87,66 @@ __device__ __forceinline__ float norm2f(float a, float b) {
   return __fsqrt_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));
 }
 
-// oracle/lidar_oracle.c: apg_oracle_scan_one, operation for operation
+// oracle/lidar_oracle.c: apg_oracle_scan_one -- same arithmetic, written branch-light: the walk state is updated
+// with selects, the rare cases (rays along a grid line, lattice-corner ties, start on a grid line) take side paths.
 __device__ float scan_one(const MapView& m, float posx, float posy, float tx, float ty, int& cellx, int& celly) {
   const double px = posx, py = posy;
   const double dx = (double)tx - px, dy = (double)ty - py;
   const int sx = dx > 0 ? 1 : (dx < 0 ? -1 : 0), sy = dy > 0 ? 1 : (dy < 0 ? -1 : 0);
   // one IEEE reciprocal per ray and axis; every crossing parameter is (g - p) * inv (oracle/lidar_oracle.c)
   const double inv_dx = sx != 0 ? __ddiv_rn(1.0, dx) : 0.0, inv_dy = sy != 0 ? __ddiv_rn(1.0, dy) : 0.0;
-  const bool px_int = (px == floor(px)), py_int = (py == floor(py));
-  int cx = (int)floor(px), cy = (int)floor(py);
+  const double fpx = floor(px), fpy = floor(py);
+  const bool px_int = (px == fpx), py_int = (py == fpy);
+  int cx = (int)fpx, cy = (int)fpy;
   if (px_int && sx < 0) cx -= 1;
   if (py_int && sy < 0) cy -= 1;
   const bool nbx = (sx == 0 && px_int), nby = (sy == 0 && py_int);
-#define WALL(X, Y) (is_wall(m, (X), (Y)) || (nbx && is_wall(m, (X)-1, (Y))) || (nby && is_wall(m, (X), (Y)-1)))
+  const bool nb_any = nbx || nby;  // the ray runs along a grid line: the cells on its other side touch it too
+#define WALL(X, Y) (is_wall(m, (X), (Y)) || (nb_any && ((nbx && is_wall(m, (X)-1, (Y))) || (nby && is_wall(m, (X), (Y)-1)))))
   int n_pos = 0, n_zero = 0;
-  bool have_first = false, in_iv = false;
-  double iv_t0 = 0.0, fex = 0.0, fey = 0.0;
-  if (WALL(cx, cy)) {
-    in_iv = true; have_first = true; fex = px; fey = py;
-  } else if (px_int || py_int) {
+  bool have_first = false;
+  bool in_iv = WALL(cx, cy);
+  double iv_t0 = 0.0, fex = px, fey = py;
+  if (in_iv) {
+    have_first = true;
+  } else if (px_int || py_int) {  // start point on a grid line: the cells behind it touch the segment at t = 0
     bool touch = false;
     const int bx = cx - sx, by = cy - sy;
     if (px_int && sx != 0) touch |= is_wall(m, bx, cy) || (nby && is_wall(m, bx, cy - 1));
     if (py_int && sy != 0) touch |= is_wall(m, cx, by) || (nbx && is_wall(m, cx - 1, by));
     if (px_int && py_int && sx != 0 && sy != 0) touch |= (bool)is_wall(m, bx, by);
-    if (touch) { n_zero = 1; have_first = true; fex = px; fey = py; }
+    if (touch) { n_zero = 1; have_first = true; }
   }
-  // the crossing parameters are refreshed only for the axis that advanced: same values as recomputing both
-  double tX = INFINITY, tY = INFINITY, gx = 0.0, gy = 0.0;
-  if (sx != 0) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = (gx - px) * inv_dx; }
-  if (sy != 0) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = (gy - py) * inv_dy; }
+  const double sxd = (double)sx, syd = (double)sy;
+  double gx = (double)(sx > 0 ? cx + 1 : cx), gy = (double)(sy > 0 ? cy + 1 : cy);  // next grid lines (exact integers)
+  double tX = sx != 0 ? (gx - px) * inv_dx : INFINITY;
+  double tY = sy != 0 ? (gy - py) * inv_dy : INFINITY;
   for (;;) {
-    const double tN = tX < tY ? tX : tY;
-    if (!(tN <= 1.0)) break;
     const bool stepx = tX <= tY, stepy = tY <= tX;
+    const double tN = stepx ? tX : tY;
+    if (!(tN <= 1.0)) break;  // the segment ends inside the current cell
     const int ncx = cx + (stepx ? sx : 0), ncy = cy + (stepy ? sy : 0);
     const bool next_wall = WALL(ncx, ncy);
-    const bool side_wall = (stepx && stepy) && (is_wall(m, ncx, cy) || is_wall(m, cx, ncy));
-    if (in_iv) {
-      if (!next_wall) {
-        if (tN > iv_t0) n_pos++; else n_zero++;
-        in_iv = false;
-      }
-    } else if (next_wall || side_wall) {
-      if (!have_first) {
-        have_first = true;
-        fex = stepx ? gx : px + tN * dx;
-        fey = stepy ? gy : py + tN * dy;
-      }
-      if (next_wall) { in_iv = true; iv_t0 = tN; } else n_zero++;
+    bool side_wall = false;
+    if (stepx && stepy) side_wall = is_wall(m, ncx, cy) || is_wall(m, cx, ncy);  // lattice corner
+    const bool opens = !in_iv && next_wall;
+    const bool touches = !in_iv && !next_wall && side_wall;
+    const bool closes = in_iv && !next_wall;
+    if ((opens || touches) && !have_first) {  // entry vertex of the first piece: crossed coordinates are integral
+      have_first = true;
+      fex = stepx ? gx : px + tN * dx;
+      fey = stepy ? gy : py + tN * dy;
     }
+    const bool pos_len = tN > iv_t0;
+    n_pos += (closes && pos_len) ? 1 : 0;
+    n_zero += ((closes && !pos_len) ? 1 : 0) + (touches ? 1 : 0);
+    iv_t0 = opens ? tN : iv_t0;
+    in_iv = next_wall;
     cx = ncx; cy = ncy;
-    if (stepx) { gx = (double)(sx > 0 ? cx + 1 : cx); tX = (gx - px) * inv_dx; }
-    if (stepy) { gy = (double)(sy > 0 ? cy + 1 : cy); tY = (gy - py) * inv_dy; }
-    // a ray that has left the map and keeps moving away never meets another cell of the union
-    if (!in_iv && ((cx < 0 && sx <= 0) || (cx >= m.W && sx >= 0) || (cy < 0 && sy <= 0) || (cy >= m.H && sy >= 0)) &&
-        !nbx && !nby)
-      break;
+    if (stepx) { gx += sxd; tX = (gx - px) * inv_dx; }
+    if (stepy) { gy += syd; tY = (gy - py) * inv_dy; }
+    // positions lie inside the map, so a ray whose current cell is outside has left it for good
+    if (!in_iv && ((unsigned)cx >= (unsigned)m.W || (unsigned)cy >= (unsigned)m.H) && !nb_any) break;
   }
   if (in_iv) { if (iv_t0 < 1.0) n_pos++; else n_zero++; }
 #undef WALL
@@ -213,32 +217,37 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
   return n;
 }
 
+// A block owns kEnvsPerBlock = 32 consecutive environments.
+//   phase 1  warp 0, lane = environment: autoreset decision; resetting environments draw their map from the env's own
+//            numpy-compatible stream (SeedSequence/PCG64/Lemire, apg_rng.h);
+//   phase 2  all threads stage the 32 bit-packed maps in shared memory (coalesced);
+//   phase 3  warp 0, lane = environment: start-cell draw (reset) or pose integration + collision ray + wall-slide
+//            rays (step) -- 32 environments advance in parallel instead of one warp re-evaluating one environment's
+//            serial ray chain 32 times -- then loss, reward, TimeLimit, episode statistics, state write-back;
+//   phase 4  the block writes the map observation of the environments that reset;
+//   phase 5  beams: a group of G = min(32, pow2 >= B) lanes owns one environment, lane l casts beams l, l+G, ...
+//            and stores coalesced runs of the lidar row.
 __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarParams p) {
-  extern __shared__ unsigned smem_maps[];  // one (H*words) slot per group
+  extern __shared__ unsigned smem_maps[];  // kEnvsPerBlock x (H*words)
+  __shared__ float s_posx[kEnvsPerBlock], s_posy[kEnvsPerBlock];
+  __shared__ int s_midx[kEnvsPerBlock];
+  __shared__ unsigned char s_reset[kEnvsPerBlock];
   const int tid = threadIdx.x;
-  const int groups_per_block = kThreads / p.G;
-  const int grp = tid / p.G;
-  const int li = tid - grp * p.G;
-  const int n = blockIdx.x * groups_per_block + grp;
-  const unsigned gmask = (p.G == 32) ? 0xffffffffu : (((1u << p.G) - 1u) << ((tid & 31) / p.G * p.G));
-  if (n >= p.N) return;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int env0 = blockIdx.x * kEnvsPerBlock;
+  const int nE = min(kEnvsPerBlock, p.N - env0);
   const int mw = p.H * p.words;
-  unsigned* smap = smem_maps + (size_t)grp * mw;
-  MapView mv{smap, p.W, p.H, p.words};
   const float Wf = (float)p.W, Hf = (float)p.H;
 
-  const bool do_reset = (p.mode == 2) || (p.prev_done[n] != 0);
-  float posx, posy, initx, inity;
-  int elapsed;
-  int midx;
-  bool aliased;
-  unsigned err = 0;
-  unsigned char term = 0;
-
-  if (do_reset) {
-    // ---------------- reset path: streams advance exactly like the reference's per-env Generators
-    unsigned long long mi = 0;
-    if (li == 0) {
+  // ---------------------------------------------------------------- phase 1
+  bool do_reset = false;
+  const int n = env0 + lane;          // warp 0's environment
+  const bool act = (warp == 0) && (lane < nE);
+  if (act) {
+    do_reset = (p.mode == 2) || (p.prev_done[n] != 0);
+    int midx;
+    if (do_reset) {
       apg::Pcg64 g0, g2;
       if (p.mode == 2) {
         apg::pcg64_seed(g0, p.seed + (unsigned long long)(p.env_offset + n));
@@ -248,114 +257,111 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
         } else {
           g2 = g0;
         }
+        p.g0[n] = g0;
       } else {
-        g0 = p.g0[n];
         g2 = p.g2[n];
       }
-      if (!p.static_map) mi = apg::rng_integers_below(g2, (uint64_t)p.M);  // dataset_iterator.py:30
-      else mi = (unsigned long long)p.static_idx;
+      if (!p.static_map) midx = (int)apg::rng_integers_below(g2, (uint64_t)p.M);  // dataset_iterator.py:30
+      else midx = p.static_idx;
       p.g2[n] = g2;
-      p.g0[n] = g0;  // g0's start-cell draw happens below, after the map is staged
+    } else {
+      midx = p.map_idx[n];
     }
-    mi = __shfl_sync(gmask, mi, (tid & 31) - li);
-    midx = (int)mi;
-    const unsigned* gm = p.bank + (size_t)midx * mw;
-    for (int q = li; q < mw; q += p.G) smap[q] = gm[q];
-    __syncwarp(gmask);
-    int col = 0, row = 0;
-    if (li == 0) {
+    s_midx[lane] = midx;
+    s_reset[lane] = do_reset ? 1 : 0;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 2: stage the maps
+  for (int q = tid; q < nE * mw; q += kThreads) {
+    const int e = q / mw;
+    smem_maps[q] = p.bank[(size_t)s_midx[e] * mw + (q - e * mw)];
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 3: lane = environment
+  if (act) {
+    MapView mv{smem_maps + (size_t)lane * mw, p.W, p.H, p.words};
+    const int midx = s_midx[lane];
+    float posx, posy, initx, inity;
+    int elapsed;
+    bool aliased;
+    unsigned err = 0;
+    unsigned char term = 0;
+    if (do_reset) {
       apg::Pcg64 g0 = p.g0[n];
-      const unsigned n_free = count_free(smap, p.W, p.H, p.words);
+      const unsigned n_free = count_free(mv.bits, p.W, p.H, p.words);
       const unsigned k = (unsigned)apg::rng_integers_below(g0, (uint64_t)n_free);
-      kth_free_cell(smap, p.W, p.H, p.words, k, col, row);
+      int col, row;
+      kth_free_cell(mv.bits, p.W, p.H, p.words, k, col, row);
       p.g0[n] = g0;
-    }
-    col = __shfl_sync(gmask, col, (tid & 31) - li);
-    row = __shfl_sync(gmask, row, (tid & 31) - li);
-    posx = __fadd_rn((float)col, 0.5f);
-    posy = __fadd_rn((float)row, 0.5f);
-    initx = posx; inity = posy;
-    aliased = true;
-    elapsed = 0;
-    if (p.map_obs) {  // map.astype(f32)[..., None] / 255  -> {0, 1/255}
-      float* mo = p.map_obs + (size_t)n * p.H * p.W;
-      const float one = __fdiv_rn(1.0f, 255.0f);
-      for (int q = li; q < p.H * p.W; q += p.G) {
-        const int y = q / p.W, x = q - y * p.W;
-        mo[q] = ((smap[y * p.words + (x >> 5)] >> (x & 31)) & 1u) ? one : 0.0f;
-      }
-    }
-    if (li == 0) {
+      posx = __fadd_rn((float)col, 0.5f);
+      posy = __fadd_rn((float)row, 0.5f);
+      initx = posx; inity = posy;
+      aliased = true;
+      elapsed = 0;
       p.reward[n] = 0.0f;
       p.base_reward[n] = 0.0f;
       p.loss[n] = 0.0f;
       p.target[2 * n] = 0.0f; p.target[2 * n + 1] = 0.0f;
       p.stepped[n] = 0;
       p.map_idx[n] = midx;
-      p.map_idx_out[n] = (long long)midx;
       if (p.reward2) p.reward2[n] = 0.0f;
-    }
-  } else {
-    // ---------------- real step: every lane of the group computes the (uniform) move
-    midx = p.map_idx[n];
-    const unsigned* gm = p.bank + (size_t)midx * mw;
-    for (int q = li; q < mw; q += p.G) smap[q] = gm[q];
-    posx = p.pos[2 * n]; posy = p.pos[2 * n + 1];
-    initx = p.init[2 * n]; inity = p.init[2 * n + 1];
-    aliased = p.aliased[n] != 0;
-    elapsed = p.elapsed[n];
-    float a0 = p.action[2 * n], a1 = p.action[2 * n + 1];
-    const float q0 = p.pred[2 * n], q1 = p.pred[2 * n + 1];
-    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
-    if (isnan(q0) || isnan(q1)) err |= APG_FLAG_NAN_PRED;
-    __syncwarp(gmask);
-    const float lastx = posx, lasty = posy;
-    const float base = __fsub_rn(0.1f, __fmul_rn(1e-3f, __fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1))));
-    const float mag = norm2f(a0, a1);
-    if (mag > 1.0f) { a0 = __fdiv_rn(a0, mag); a1 = __fdiv_rn(a1, mag); }
-    const float tx = __fadd_rn(posx, a0), ty = __fadd_rn(posy, a1);
-    float dirx = __fsub_rn(tx, posx), diry = __fsub_rn(ty, posy);
-    const float total = norm2f(dirx, diry);
-    if (total > 0.0f) {
-      dirx = __fdiv_rn(dirx, total); diry = __fdiv_rn(diry, total);
-      int c0, c1;
-      const float d = scan_one(mv, posx, posy, tx, ty, c0, c1);
-      posx = __fadd_rn(posx, __fmul_rn(dirx, d));
-      posy = __fadd_rn(posy, __fmul_rn(diry, d));
-      const float rem = __fsub_rn(total, d);
-      if (rem > 1e-5f) {
-        const float rvx = __fmul_rn(dirx, rem), rvy = __fmul_rn(diry, rem);
-        const bool kx = rvx > 1e-5f, ky = rvy > 1e-5f;
-        if (kx || ky) {
-          const float v0 = (kx && ky) ? rvx : (kx ? rvx : rvy);
-          const float v1 = (kx && ky) ? rvy : (kx ? rvx : rvy);
-          const float d0 = scan_one(mv, posx, posy, __fadd_rn(posx, v0), __fadd_rn(posy, 0.0f), c0, c1);
-          const float d1 = scan_one(mv, posx, posy, __fadd_rn(posx, 0.0f), __fadd_rn(posy, v1), c0, c1);
-          if (d0 > 0.0f) {
-            const float nv = norm2f(v0, 0.0f);
-            posx = __fadd_rn(posx, __fmul_rn(__fdiv_rn(v0, nv), d0));
-            posy = __fadd_rn(posy, __fmul_rn(__fdiv_rn(0.0f, nv), d0));
-          } else {
-            const float nv = norm2f(0.0f, v1);
-            posx = __fadd_rn(posx, __fmul_rn(__fdiv_rn(0.0f, nv), d1));
-            posy = __fadd_rn(posy, __fmul_rn(__fdiv_rn(v1, nv), d1));
+    } else {
+      posx = p.pos[2 * n]; posy = p.pos[2 * n + 1];
+      initx = p.init[2 * n]; inity = p.init[2 * n + 1];
+      aliased = p.aliased[n] != 0;
+      elapsed = p.elapsed[n];
+      float a0 = p.action[2 * n], a1 = p.action[2 * n + 1];
+      const float q0 = p.pred[2 * n], q1 = p.pred[2 * n + 1];
+      if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
+      if (isnan(q0) || isnan(q1)) err |= APG_FLAG_NAN_PRED;
+      const float lastx = posx, lasty = posy;
+      const float base = __fsub_rn(0.1f, __fmul_rn(1e-3f, __fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1))));
+      const float mag = norm2f(a0, a1);
+      if (mag > 1.0f) { a0 = __fdiv_rn(a0, mag); a1 = __fdiv_rn(a1, mag); }
+      const float tx = __fadd_rn(posx, a0), ty = __fadd_rn(posy, a1);
+      float dirx = __fsub_rn(tx, posx), diry = __fsub_rn(ty, posy);
+      const float total = norm2f(dirx, diry);
+      if (total > 0.0f) {
+        dirx = __fdiv_rn(dirx, total); diry = __fdiv_rn(diry, total);
+        int c0, c1;
+        const float d = scan_one(mv, posx, posy, tx, ty, c0, c1);
+        posx = __fadd_rn(posx, __fmul_rn(dirx, d));
+        posy = __fadd_rn(posy, __fmul_rn(diry, d));
+        const float rem = __fsub_rn(total, d);
+        if (rem > 1e-5f) {
+          const float rvx = __fmul_rn(dirx, rem), rvy = __fmul_rn(diry, rem);
+          const bool kx = rvx > 1e-5f, ky = rvy > 1e-5f;
+          if (kx || ky) {
+            const float v0 = (kx && ky) ? rvx : (kx ? rvx : rvy);
+            const float v1 = (kx && ky) ? rvy : (kx ? rvx : rvy);
+            const float d0 = scan_one(mv, posx, posy, __fadd_rn(posx, v0), __fadd_rn(posy, 0.0f), c0, c1);
+            const float d1 = scan_one(mv, posx, posy, __fadd_rn(posx, 0.0f), __fadd_rn(posy, v1), c0, c1);
+            if (d0 > 0.0f) {
+              const float nv = norm2f(v0, 0.0f);
+              posx = __fadd_rn(posx, __fmul_rn(__fdiv_rn(v0, nv), d0));
+              posy = __fadd_rn(posy, __fmul_rn(__fdiv_rn(0.0f, nv), d0));
+            } else {
+              const float nv = norm2f(0.0f, v1);
+              posx = __fadd_rn(posx, __fmul_rn(__fdiv_rn(0.0f, nv), d1));
+              posy = __fadd_rn(posy, __fmul_rn(__fdiv_rn(v1, nv), d1));
+            }
           }
         }
       }
-    }
-    if (aliased) { initx = posx; inity = posy; }
-    const bool oob = (posx < 0.0f) || (posy < 0.0f) || (posx >= Wf) || (posy >= Hf);
-    posx = fminf(fmaxf(posx, 0.0f), Wf);
-    posy = fminf(fmaxf(posy, 0.0f), Hf);
-    aliased = false;
-    const float t0 = __fsub_rn(__fmul_rn(__fdiv_rn(lastx, Wf), 2.0f), 1.0f);
-    const float t1 = __fsub_rn(__fmul_rn(__fdiv_rn(lasty, Hf), 2.0f), 1.0f);
-    const float e0 = __fsub_rn(q0, t0), e1 = __fsub_rn(q1, t1);
-    const float mse = __fdiv_rn(__fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)), 2.0f);
-    const float loss = __fadd_rn(__fmul_rn(mse, 3.0f), 0.0f);
-    elapsed += 1;
-    term = (oob || elapsed >= p.T) ? 1 : 0;
-    if (li == 0) {
+      if (aliased) { initx = posx; inity = posy; }
+      const bool oob = (posx < 0.0f) || (posy < 0.0f) || (posx >= Wf) || (posy >= Hf);
+      posx = fminf(fmaxf(posx, 0.0f), Wf);
+      posy = fminf(fmaxf(posy, 0.0f), Hf);
+      aliased = false;
+      const float t0 = __fsub_rn(__fmul_rn(__fdiv_rn(lastx, Wf), 2.0f), 1.0f);
+      const float t1 = __fsub_rn(__fmul_rn(__fdiv_rn(lasty, Hf), 2.0f), 1.0f);
+      const float e0 = __fsub_rn(q0, t0), e1 = __fsub_rn(q1, t1);
+      const float mse = __fdiv_rn(__fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)), 2.0f);
+      const float loss = __fadd_rn(__fmul_rn(mse, 3.0f), 0.0f);
+      elapsed += 1;
+      term = (oob || elapsed >= p.T) ? 1 : 0;
       const float rew = __fsub_rn(base, loss);
       // euclidean_distance = ||target - prediction|| (float32, no axis), mse = mean((target - prediction)^2)
       const float m1 = norm2f(e0, e1), m2 = mse;
@@ -376,13 +382,10 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
       p.loss[n] = loss;
       p.target[2 * n] = t0; p.target[2 * n + 1] = t1;
       p.stepped[n] = 1;
-      p.map_idx_out[n] = (long long)midx;
       if (p.reward2) p.reward2[n] = rew;
     }
-  }
-
-  // ---------------- state write-back + scalar observations
-  if (li == 0) {
+    // ---- state write-back + scalar observations
+    p.map_idx_out[n] = (long long)midx;
     p.pos[2 * n] = posx; p.pos[2 * n + 1] = posy;
     p.init[2 * n] = initx; p.init[2 * n + 1] = inity;
     p.aliased[n] = aliased ? 1 : 0;
@@ -396,19 +399,45 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
     // odometry normalisation (:263-270)
     p.odometry[2 * n] = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(posx, initx), -Wf), __fsub_rn(Wf, -Wf)), 2.0f), 1.0f);
     p.odometry[2 * n + 1] = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fsub_rn(posy, inity), -Hf), __fsub_rn(Hf, -Hf)), 2.0f), 1.0f);
+    s_posx[lane] = posx;
+    s_posy[lane] = posy;
     if (err) atomicOr(p.err, err);
   }
+  __syncthreads();
 
-  // ---------------- observation scan: lane -> beams li, li+G, ...
-  for (int b = li; b < p.B; b += p.G) {
-    const float ddx = p.dirs[2 * b], ddy = p.dirs[2 * b + 1];
-    int c0, c1;
-    const float d = scan_one(mv, posx, posy, __fadd_rn(posx, ddx), __fadd_rn(posy, ddy), c0, c1);
-    p.lidar[(size_t)n * p.B + b] = fminf(fmaxf(__fdiv_rn(d, p.range), -1.0f), 1.0f);
-    if (p.cells) {
-      p.cells[((size_t)n * p.B + b) * 2] = c0;
-      p.cells[((size_t)n * p.B + b) * 2 + 1] = c1;
-      p.dists[(size_t)n * p.B + b] = d;
+  // ---------------------------------------------------------------- phase 4: map observation of reset environments
+  if (p.map_obs) {
+    const float one = __fdiv_rn(1.0f, 255.0f);  // map.astype(f32)[..., None] / 255 -> {0, 1/255}
+    const int hw = p.H * p.W;
+    for (int e = 0; e < nE; ++e) {
+      if (!s_reset[e]) continue;
+      float* mo = p.map_obs + (size_t)(env0 + e) * hw;
+      const unsigned* bits = smem_maps + (size_t)e * mw;
+      for (int q = tid; q < hw; q += kThreads) {
+        const int y = q / p.W, x = q - y * p.W;
+        mo[q] = ((bits[y * p.words + (x >> 5)] >> (x & 31)) & 1u) ? one : 0.0f;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- phase 5: beams
+  const int envs_per_warp = 32 / p.G;
+  const int gi = lane / p.G;            // group inside the warp
+  const int li = lane - gi * p.G;
+  for (int e = warp * envs_per_warp + gi; e < nE; e += kWarpsPerBlock * envs_per_warp) {
+    MapView mv{smem_maps + (size_t)e * mw, p.W, p.H, p.words};
+    const float posx = s_posx[e], posy = s_posy[e];
+    const size_t row = (size_t)(env0 + e) * p.B;
+    for (int b = li; b < p.B; b += p.G) {
+      const float ddx = p.dirs[2 * b], ddy = p.dirs[2 * b + 1];
+      int c0, c1;
+      const float d = scan_one(mv, posx, posy, __fadd_rn(posx, ddx), __fadd_rn(posy, ddy), c0, c1);
+      p.lidar[row + b] = fminf(fmaxf(__fdiv_rn(d, p.range), -1.0f), 1.0f);
+      if (p.cells) {
+        p.cells[(row + b) * 2] = c0;
+        p.cells[(row + b) * 2 + 1] = c1;
+        p.dists[row + b] = d;
+      }
     }
   }
 }
@@ -461,8 +490,7 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   p.reward2 = reward2; p.done2 = done2; p.err = e->d_err;
   p.acc1 = e->d_acc1; p.acc2 = e->d_acc2; p.acc_ret = e->d_acc_ret; p.ep_avg1 = e->b.d_ep_avg1; p.ep_final1 = e->b.d_ep_final1;
   p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return; p.stats = e->d_stats;
-  const int groups_per_block = kThreads / e->G;
-  const int grid = apg::ceil_div(c.num_envs, groups_per_block);
+  const int grid = apg::ceil_div(c.num_envs, kEnvsPerBlock);
   lidar_step_kernel<<<grid, kThreads, e->smem, e->stream>>>(p);
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
@@ -495,7 +523,7 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
   while (G < cfg->beam_count && G < 32) G <<= 1;
   if (G < 4) G = 4;
   e->G = G;
-  e->smem = (size_t)(kThreads / G) * cfg->height * e->words * sizeof(unsigned);
+  e->smem = (size_t)kEnvsPerBlock * cfg->height * e->words * sizeof(unsigned);
   const size_t N = cfg->num_envs, B = cfg->beam_count;
   cudaError_t err = cudaSuccess;
   auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
