@@ -80,6 +80,7 @@ SYMBOLS = {
     "apg_image_step": (C.c_int, [_P, _P, _P]),
     "apg_image_rollout": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "apg_image_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "apg_image_unique_topk": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, C.c_int32, _P]),
     "apg_image_get_buffers": (C.c_int, [_P, C.POINTER(ImageBuffers)]),
     "apg_image_get_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "apg_image_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),

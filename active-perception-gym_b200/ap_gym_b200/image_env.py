@@ -430,35 +430,58 @@ class ImageClassificationVectorEnv(_ImageVectorEnvBase):
 class ImageLocalizationVectorEnv(_ImageVectorEnvBase):
     """ap_gym.envs.image_localization.ImageLocalizationVectorEnv on the B200 engine.
 
-    Explicit `reset()` targets: the reference runs `sample_unique_glimpse_positions` (O(N * 729^2 * S^2 C),
-    9.9 s for N=8 on the CPU).  Pass `options={"prediction_target": (N,2) float32}` to supply them, or leave
-    the default `target_sampling="uniform"` which draws U(-1,1) like the reference's own autoreset does
-    (documented deviation); the module Generator is advanced exactly as the reference would."""
+    Explicit `reset()` targets follow the reference (`sample_unique_glimpse_positions`,
+    image_perception_module.py:253-292): the uniqueness search -- O(729^2 * 300) per 64x64x3 image, 1.2 s on a CPU
+    core -- runs on the GPU (`apg_image_unique_topk`) and is cached per bank image; the random pick and jitter come
+    from the module Generator exactly like in the reference.  `options={"prediction_target": (N,2) float32}` overrides
+    the targets; `target_sampling="uniform"` skips the search and draws U(-1,1) (the Generator is still advanced
+    exactly as the reference would, so later episodes stay in lock-step)."""
 
     _TASK = _capi.TASK_LOCALIZATION
     _TARGET_VIEW = "target_xy"
     _METRICS = ("euclidean_distance", "mse")
 
-    def __init__(self, *args, target_sampling: Literal["uniform"] = "uniform", **kwargs):
+    def __init__(self, *args, target_sampling: Literal["unique", "uniform"] = "unique", **kwargs):
         super().__init__(*args, **kwargs)
-        if target_sampling != "uniform":
-            raise ValueError("target_sampling must be 'uniform' (or pass options['prediction_target'])")
-
-    def _explicit_targets(self, options, idx, pos):
+        if target_sampling not in ("unique", "uniform"):
+            raise ValueError("target_sampling must be 'unique' or 'uniform'")
+        self._target_sampling = target_sampling
         cfg = self._config
         eff = np.array(cfg.sensor_size) * cfg.sensor_scale
         lim = (np.array([self._W, self._H]) - 1) / 2 - (eff - 1) / 2
-        max_cell = eff / lim * cfg.unique_sampling_max_grid_cell_size_rel
-        sel, jitter = self._stream.draw_unique_selection(cfg.unique_sampling_top_k, max_cell)
+        self._max_cell = eff / lim * cfg.unique_sampling_max_grid_cell_size_rel
+        cnt = np.ceil(2 / self._max_cell)
+        self._grid = np.ascontiguousarray(np.stack(
+            np.meshgrid(np.linspace(-1, 1, int(cnt[0])), np.linspace(-1, 1, int(cnt[1])), indexing="ij"),
+            axis=-1).reshape(-1, 2))
+        self._topk_cache: dict[int, np.ndarray] = {}
+
+    def unique_topk(self, bank_indices: np.ndarray) -> np.ndarray:
+        """(n, top_k) grid indices of the most unique glimpse positions of the given bank images (cached)."""
+        k = int(self._config.unique_sampling_top_k)
+        bank_indices = np.asarray(bank_indices, dtype=np.int64)
+        missing = np.array(sorted({int(i) for i in bank_indices} - self._topk_cache.keys()), dtype=np.int64)
+        if len(missing):
+            out = np.empty((len(missing), k), dtype=np.int32)
+            _capi.check(self._lib.apg_image_unique_topk(self._h, _void(missing), len(missing), _void(self._grid),
+                                                        len(self._grid), k, _void(out)))
+            for i, row in zip(missing, out):
+                self._topk_cache[int(i)] = row
+        return np.stack([self._topk_cache[int(i)] for i in bank_indices])
+
+    def _explicit_targets(self, options, idx, pos):
+        cfg = self._config
+        sel, jitter = self._stream.draw_unique_selection(cfg.unique_sampling_top_k, self._max_cell)
         if options and options.get("prediction_target") is not None:
             t = np.ascontiguousarray(options["prediction_target"], dtype=np.float32)
             if t.shape != (self.num_envs, 2):
                 raise ValueError("options['prediction_target'] must have shape (num_envs, 2)")
             return t
-        # uniform stand-in built from the same two draws: grid cell (sel/top_k spreads over [-1,1]) is not
-        # available without the uniqueness search, so use the jitter draw rescaled to the full range
-        u = jitter / max_cell  # U(-1, 1)
-        return np.ascontiguousarray(np.clip(u, -1, 1).astype(np.float32))
+        if self._target_sampling == "uniform":
+            return np.ascontiguousarray(np.clip(jitter / self._max_cell, -1, 1).astype(np.float32))
+        top = self.unique_topk(idx)
+        base = self._grid[top[np.arange(self.num_envs), sel]]
+        return np.ascontiguousarray(np.clip(base + jitter, -1, 1).astype(np.float32))
 
     def _autoreset_targets(self):
         return self._stream.draw_autoreset_targets()

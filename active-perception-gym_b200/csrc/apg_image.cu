@@ -1026,6 +1026,14 @@ int apg_image_poll_error(apg_image_env* e, uint32_t* flags, int clear) {
   return APG_OK;
 }
 
+// internal: lets csrc/apg_unique.cu read the bank of a handle (not part of the public header)
+int apg_image_bank_info(apg_image_env* e, const void** d_bank, int32_t* bank_pitch, int64_t* n_items, apg_image_cfg* cfg,
+                        void** stream) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  *d_bank = e->d_bank; *bank_pitch = e->bank_pitch; *n_items = e->n_items; *cfg = e->cfg; *stream = e->stream;
+  return APG_OK;
+}
+
 int apg_image_sync(apg_image_env* e) {
   APG_CHECK(e, APG_ERR_INVALID, "null env");
   APG_CUDA(cudaSetDevice(e->cfg.device));

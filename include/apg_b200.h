@@ -152,6 +152,14 @@ int apg_image_rollout(apg_image_env* env, const float* d_actions, const float* d
 int apg_image_step_host(apg_image_env* env, const float* h_action, const float* h_pred, float* h_reward,
                         uint8_t* h_terminated, uint8_t* h_truncated, float* h_glimpse);
 
+/* Unique-glimpse search of ImageLocalizationVectorEnv.reset(): for each of the n_imgs bank images h_img_idx[i], the
+ * top_k grid positions (indices into h_grid, (n_positions, 2) float64 normalised (x, y)) whose glimpse differs most
+ * from every other grid glimpse, in descending order of uniqueness -- h_topk (n_imgs, top_k) int32.
+ * Replaces ImagePerceptionModule.sample_unique_glimpse_positions up to the random pick
+ * (ap_gym/envs/image/image_perception_module.py:253-277).  Synchronous. */
+int apg_image_unique_topk(apg_image_env* env, const int64_t* h_img_idx, int64_t n_imgs, const double* h_grid,
+                          int32_t n_positions, int32_t top_k, int32_t* h_topk);
+
 int apg_image_get_buffers(apg_image_env* env, apg_image_buffers* out);
 /* Episode statistics accumulated on the device since creation / the last clear, summed over this shard's envs
  * (the payload of the final NCCL reduce): h_stats[0] = finished episodes, [1] = sum of per-episode avg metric 1,

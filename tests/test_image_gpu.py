@@ -150,6 +150,27 @@ def test_engine_matches_oracle_odd_geometries(geom, task):
     env.close()
 
 
+@pytest.mark.parametrize("name", ["tinyloc_n4", "mnistloc_n6"])
+def test_unique_glimpse_targets_match_reference(name):
+    """Explicit reset() of the localisation env: the GPU uniqueness search + the module Generator's pick reproduce
+    the reference's sample_unique_glimpse_positions targets (image_perception_module.py:253-292) bit-exactly."""
+    import ap_gym_b200 as apg
+
+    case = IMAGE_CASES[name]
+    g = load_golden("image", name)
+    imgs, labels = make_bank(case["bank"])
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, case["K"]), **case["cfg"])
+    env = apg.ImageLocalizationVectorEnv(case["N"], cfg, output="numpy")
+    obs, info = env.reset(seed=case["seed"])
+    assert np.array_equal(_np(env.state()["cur_target_xy"]), g["reset_target"]), "unique-glimpse targets"
+    assert np.array_equal(obs["target_glimpse"], g["reset_target_glimpse"])
+    for s in range(20):  # crosses an autoreset: later episodes stay in lock-step with the reference
+        o, r, te, tr, inf = env.step({"action": g["actions"][s], "prediction": g["preds"][s]})
+        assert np.array_equal(o["target_glimpse"], g["obs_target_glimpse"][s])
+        assert np.array_equal(inf["prediction"]["target"], g["target"][s])
+    env.close()
+
+
 def test_error_conventions():
     import ap_gym_b200 as apg
     from oracle.datasets import synthetic_u8_bank
