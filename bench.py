@@ -275,7 +275,10 @@ def main():
         preds = torch.rand((tot, n, 2), generator=gen, device=dev) * 2 - 1
     else:
         preds = torch.randn((tot, n, pw), generator=gen, device=dev)
+    t_reset0 = time.perf_counter()
     env.reset(seed=0)
+    env.sync()
+    reset_s = time.perf_counter() - t_reset0
 
     def run(s0, s1):
         s = s0
@@ -380,7 +383,7 @@ def main():
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}",
+            "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}", "explicit_reset_s": round(reset_s, 3),
                        "l2": "per-step inputs are distinct and streamed from HBM (%.0f MB total > 126 MB L2); engine-owned obs buffers are rewritten every step" % (acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
