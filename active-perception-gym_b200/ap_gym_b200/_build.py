@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",  # reference-exact arithmetic: numpy never fuses mul+add (numerics)
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden" if False else "-fno-strict-aliasing",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "-Xcompiler", "-ffp-contract=off",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
 ]
 

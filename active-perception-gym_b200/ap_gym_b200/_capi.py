@@ -48,6 +48,25 @@ class ImageBuffers(C.Structure):
     ]
 
 
+class Pcg64State(C.Structure):
+    _fields_ = [("state_hi", C.c_uint64), ("state_lo", C.c_uint64), ("inc_hi", C.c_uint64), ("inc_lo", C.c_uint64),
+                ("has_uint32", C.c_uint32), ("uinteger", C.c_uint32)]
+
+    @classmethod
+    def from_numpy(cls, gen):
+        st = gen.bit_generator.state
+        s, inc = int(st["state"]["state"]), int(st["state"]["inc"])
+        m = (1 << 64) - 1
+        return cls(s >> 64, s & m, inc >> 64, inc & m, int(st["has_uint32"]), int(st["uinteger"]))
+
+    def to_numpy(self, gen):
+        st = gen.bit_generator.state
+        st["state"]["state"] = (int(self.state_hi) << 64) | int(self.state_lo)
+        st["state"]["inc"] = (int(self.inc_hi) << 64) | int(self.inc_lo)
+        st["has_uint32"], st["uinteger"] = int(self.has_uint32), int(self.uinteger)
+        gen.bit_generator.state = st
+
+
 class LidarCfg(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("num_envs", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
@@ -77,6 +96,10 @@ SYMBOLS = {
     "apg_image_reset": (C.c_int, [_P, _P, _P, _P, _P]),
     "apg_image_queue_reset_payload": (C.c_int, [_P, _P, _P, _P, _P]),
     "apg_image_pending_payloads": (C.c_int, [_P]),
+    "apg_image_set_streams": (C.c_int, [_P, C.POINTER(Pcg64State), C.POINTER(Pcg64State), C.POINTER(Pcg64State),
+                                        C.c_int64, C.c_int64]),
+    "apg_image_get_streams": (C.c_int, [_P, C.POINTER(Pcg64State), C.POINTER(Pcg64State), C.POINTER(Pcg64State)]),
+    "apg_image_prefetch_payloads": (C.c_int, [_P, C.c_int32]),
     "apg_image_step": (C.c_int, [_P, _P, _P]),
     "apg_image_rollout": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "apg_image_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

@@ -204,10 +204,28 @@ class _ImageVectorEnvBase:
     def np_random(self):
         if self._stream is None:
             self._seed(None)
+        self._pull_streams()
         return self._stream.g0
 
     def _seed(self, seed):
         self._stream = ImageResetStream(seed, self._global_n, len(self._bank), self._slice)
+        self._engine_has_streams = False
+
+    def _push_streams(self):
+        """Hand the three numpy Generators to the engine: from here on it draws every autoreset payload itself
+        (bit-identical to numpy, csrc/apg_rng.h) so no python runs on the autoreset path."""
+        st = [_capi.Pcg64State.from_numpy(g) for g in (self._stream.g0, self._stream.g1, self._stream.g2)]
+        _capi.check(self._lib.apg_image_set_streams(self._h, C.byref(st[0]), C.byref(st[1]), C.byref(st[2]),
+                                                    self._global_n, self._slice.start))
+        self._engine_has_streams = True
+
+    def _pull_streams(self):
+        """Bring the numpy Generators up to date with the draws the engine made since _push_streams."""
+        if getattr(self, "_engine_has_streams", False):
+            st = [_capi.Pcg64State() for _ in range(3)]
+            _capi.check(self._lib.apg_image_get_streams(self._h, C.byref(st[0]), C.byref(st[1]), C.byref(st[2])))
+            for s_, g in zip(st, (self._stream.g0, self._stream.g1, self._stream.g2)):
+                s_.to_numpy(g)
 
     # ------------------------------------------------------------------------------------------ errors
     def _poll(self):
@@ -239,20 +257,19 @@ class _ImageVectorEnvBase:
     def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
         if seed is not None or self._stream is None:
             self._seed(seed)
+        else:
+            self._pull_streams()
         idx, inv, pos = self._stream.draw_episode(bool(self._config.randomly_invert_labels))
         target = self._explicit_targets(options, idx, pos)
         _capi.check(self._lib.apg_image_reset(self._h, _void(idx), _void(pos), _void(target), _void(inv)))
+        self._push_streams()
         as_numpy = bool(options and options.get("numpy", False)) or self._numpy_mode
         return self._obs(as_numpy), {"index": self._out("index", as_numpy)}
 
     def queue_autoreset_payloads(self, count: int = 1):
-        """Draw and upload the payloads of the next `count` autoresets ahead of time (rollouts / graphs).
-        The draws follow the reference's stream order, assuming no explicit reset() happens in between."""
-        for _ in range(count):
-            target = self._autoreset_targets()  # env-level Generator first (image_localization.py:153-156)
-            idx, inv, pos = self._stream.draw_episode(bool(self._config.randomly_invert_labels))
-            _capi.check(self._lib.apg_image_queue_reset_payload(self._h, _void(idx), _void(pos), _void(target),
-                                                               _void(inv)))
+        """Draw and upload the payloads of the next `count` autoresets ahead of time (bounded by the payload ring);
+        without it the engine draws each payload when its autoreset step is queued."""
+        _capi.check(self._lib.apg_image_prefetch_payloads(self._h, int(count)))
 
     # ------------------------------------------------------------------------------------------ step
     def _out(self, name: str, as_numpy: bool):
@@ -269,9 +286,6 @@ class _ImageVectorEnvBase:
 
     def step(self, action):
         a, p = action["action"], action["prediction"]
-        b = self._buffers()
-        if b.needs_reset and self._lib.apg_image_pending_payloads(self._h) == 0:
-            self.queue_autoreset_payloads(1)
         host_mode = not _is_torch(a)
         if host_mode:
             a = np.ascontiguousarray(a, dtype=np.float32)
@@ -341,20 +355,6 @@ class _ImageVectorEnvBase:
         """`n_steps` consecutive steps from stacked CUDA tensors (n_steps, N, 2) / (n_steps, N, K|2); per-step
         rewards (f32) / dones (bool) land in the optional (n_steps, N) tensors.  Asynchronous."""
         n_steps = int(actions.shape[0])
-        T = int(self._config.step_limit)
-        b = self._buffers()
-        t, need, resets = b.elapsed, bool(b.needs_reset), 0
-        for _ in range(n_steps):
-            if need:
-                resets, t, need = resets + 1, 0, False
-            else:
-                t += 1
-                need = t >= T
-        missing = resets - self._lib.apg_image_pending_payloads(self._h)
-        if resets > self._ring:
-            raise ValueError(f"a rollout may span at most payload_ring={self._ring} autoresets")
-        if missing > 0:
-            self.queue_autoreset_payloads(missing)
         _capi.check(self._lib.apg_image_rollout(
             self._h, actions.data_ptr(), predictions.data_ptr(), n_steps,
             None if rewards is None else rewards.data_ptr(), None if dones is None else dones.data_ptr()))

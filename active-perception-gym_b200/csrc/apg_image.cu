@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "apg_common.h"
+#include "apg_rng.h"
 
 namespace {
 
@@ -591,6 +592,14 @@ struct apg_image_env {
   // staging for *_host
   float* d_in_action = nullptr;
   float* d_in_pred = nullptr;
+  // numpy-compatible reset streams (optional): autoreset payloads are drawn by the engine when the ring is empty
+  apg::Pcg64 g0{}, g1{}, g2{};
+  bool have_streams = false;
+  int64_t global_n = 0, env_offset = 0;
+  std::vector<int64_t> h_idx;
+  std::vector<double> h_pos;
+  std::vector<float> h_target;
+  std::vector<uint8_t> h_inv;
   // episode clock (all-or-nothing, shared by every env of the vector env)
   int t = 0;
   bool has_reset = false;
@@ -701,7 +710,48 @@ if (c.bank_dtype == APG_BANK_U8)
   return APG_OK;
 }
 
+// One autoreset payload from the reference's streams, in the reference's draw order, for the global batch; this
+// shard keeps its slice.  (image_localization.py:153-156 -> dataset_iterator.py:57 -> image_perception_module.py:131-133
+// -> :159-161)
+int generate_payload(apg_image_env* e) {
+  APG_CHECK(e->have_streams, APG_ERR_NEED_PAYLOAD, "no reset payload queued and no reset streams set");
+  APG_CHECK(e->ring_count < (int)e->ring.size(), APG_ERR_STATE, "reset payload ring is full");
+  const int64_t N = e->cfg.num_envs, Ng = e->global_n, off = e->env_offset;
+  const bool loc = e->cfg.task == APG_TASK_LOCALIZATION, inv = e->cfg.randomly_invert_labels != 0;
+  e->h_idx.resize(N); e->h_pos.resize(2 * N);
+  if (loc) e->h_target.resize(2 * N);
+  if (inv) e->h_inv.resize(N);
+  if (loc) {  // g0.uniform(-1, 1, (Ng, 2)).astype(float32)
+    apg::pcg64_advance(e->g0, (uint64_t)(2 * off));
+    for (int64_t i = 0; i < 2 * N; ++i) e->h_target[i] = (float)apg::rng_uniform(e->g0, -1.0, 2.0);
+    apg::pcg64_advance(e->g0, (uint64_t)(2 * (Ng - off - N)));
+  }
+  for (int64_t j = 0; j < Ng; ++j) {  // g2.integers(0, len(dataset), Ng): rejections shift the stream, draw them all
+    const uint64_t v = apg::rng_integers_below(e->g2, (uint64_t)e->n_items);
+    if (j >= off && j < off + N) e->h_idx[j - off] = (int64_t)v;
+  }
+  if (inv) {  // g1.integers(0, 2, size=Ng) == 1
+    for (int64_t j = 0; j < Ng; ++j) {
+      const uint64_t v = apg::rng_integers_below(e->g1, 2);
+      if (j >= off && j < off + N) e->h_inv[j - off] = (uint8_t)(v == 1);
+    }
+  }
+  apg::pcg64_advance(e->g1, (uint64_t)(2 * off));  // g1.uniform(-1, 1, (Ng, 2))
+  for (int64_t i = 0; i < 2 * N; ++i) e->h_pos[i] = apg::rng_uniform(e->g1, -1.0, 2.0);
+  apg::pcg64_advance(e->g1, (uint64_t)(2 * (Ng - off - N)));
+  apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
+  int rc = stage_payload(e, s, e->h_idx.data(), e->h_pos.data(), loc ? e->h_target.data() : nullptr,
+                         inv ? e->h_inv.data() : nullptr);
+  if (rc != APG_OK) return rc;
+  e->ring_count += 1;
+  return APG_OK;
+}
+
 int step_once(apg_image_env* e, const float* d_action, const float* d_pred, float* reward2, uint8_t* done2) {
+  if (e->needs_reset && e->ring_count == 0 && e->have_streams) {
+    int rc = generate_payload(e);
+    if (rc != APG_OK) return rc;
+  }
   if (e->needs_reset) {
     APG_CHECK(e->ring_count > 0, APG_ERR_NEED_PAYLOAD,
               "autoreset step is due but no reset payload is queued (apg_image_queue_reset_payload)");
@@ -949,6 +999,48 @@ int apg_image_queue_reset_payload(apg_image_env* e, const int64_t* h_idx, const 
 
 int apg_image_pending_payloads(apg_image_env* e) { return e ? e->ring_count : APG_ERR_INVALID; }
 
+static void to_internal(const apg_pcg64_state* s, apg::Pcg64& g) {
+  g.state_hi = s->state_hi; g.state_lo = s->state_lo; g.inc_hi = s->inc_hi; g.inc_lo = s->inc_lo;
+  g.has_uint32 = s->has_uint32; g.uinteger = s->uinteger;
+}
+static void from_internal(const apg::Pcg64& g, apg_pcg64_state* s) {
+  s->state_hi = g.state_hi; s->state_lo = g.state_lo; s->inc_hi = g.inc_hi; s->inc_lo = g.inc_lo;
+  s->has_uint32 = g.has_uint32; s->uinteger = g.uinteger;
+}
+
+int apg_image_set_streams(apg_image_env* e, const apg_pcg64_state* g0, const apg_pcg64_state* g1,
+                          const apg_pcg64_state* g2, int64_t global_num_envs, int64_t env_offset) {
+  APG_CHECK(e && g0 && g1 && g2, APG_ERR_INVALID, "apg_image_set_streams: null argument");
+  APG_CHECK(env_offset >= 0 && env_offset + e->cfg.num_envs <= global_num_envs, APG_ERR_INVALID,
+            "shard [%lld, %lld) exceeds the global batch of %lld envs", (long long)env_offset,
+            (long long)(env_offset + e->cfg.num_envs), (long long)global_num_envs);
+  APG_CHECK(e->ring_count == 0, APG_ERR_STATE, "cannot replace the reset streams while %d payloads drawn from the old ones are queued",
+            e->ring_count);
+  to_internal(g0, e->g0); to_internal(g1, e->g1); to_internal(g2, e->g2);
+  e->global_n = global_num_envs; e->env_offset = env_offset;
+  e->have_streams = true;
+  return APG_OK;
+}
+
+int apg_image_get_streams(apg_image_env* e, apg_pcg64_state* g0, apg_pcg64_state* g1, apg_pcg64_state* g2) {
+  APG_CHECK(e && g0 && g1 && g2, APG_ERR_INVALID, "apg_image_get_streams: null argument");
+  APG_CHECK(e->have_streams, APG_ERR_STATE, "no reset streams set");
+  APG_CHECK(e->ring_count == 0, APG_ERR_STATE, "%d prefetched payloads have already advanced the streams", e->ring_count);
+  from_internal(e->g0, g0); from_internal(e->g1, g1); from_internal(e->g2, g2);
+  return APG_OK;
+}
+
+int apg_image_prefetch_payloads(apg_image_env* e, int32_t count) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  APG_CHECK(e->d_bank, APG_ERR_STATE, "payload prefetch before apg_image_set_bank");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < count && e->ring_count < (int)e->ring.size(); ++i) {
+    int rc = generate_payload(e);
+    if (rc != APG_OK) return rc;
+  }
+  return APG_OK;
+}
+
 int apg_image_step(apg_image_env* e, const float* d_action, const float* d_pred) {
   APG_CHECK(e && d_action && d_pred, APG_ERR_INVALID, "apg_image_step: null argument");
   APG_CHECK(e->has_reset, APG_ERR_STATE, "step before reset");
@@ -969,8 +1061,8 @@ int apg_image_rollout(apg_image_env* e, const float* d_actions, const float* d_p
       if (need) { resets++; t = 0; need = false; }
       else { t++; need = t >= e->cfg.step_limit; }
     }
-    APG_CHECK(resets <= e->ring_count, APG_ERR_NEED_PAYLOAD, "rollout of %d steps needs %d reset payloads, %d queued",
-              n_steps, resets, e->ring_count);
+    APG_CHECK(e->have_streams || resets <= e->ring_count, APG_ERR_NEED_PAYLOAD,
+              "rollout of %d steps needs %d reset payloads, %d queued", n_steps, resets, e->ring_count);
   }
   const size_t N = e->cfg.num_envs;
   for (int k = 0; k < n_steps; ++k) {

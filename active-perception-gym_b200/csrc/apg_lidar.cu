@@ -707,7 +707,8 @@ int apg_lidar_sync(apg_lidar_env* e) {
 }
 
 // ---- host-side test hook for the numpy-compatible random streams (apg_rng.h) -----------------------------
-// op: 0 next64, 1 next32, 2 integers(0, arg), 3 integers(0, 2**32, endpoint=True), 4 re-seed with SeedSequence(arg)
+// op: 0 next64, 1 next32, 2 integers(0, arg), 3 integers(0, 2**32, endpoint=True), 4 re-seed with SeedSequence(arg),
+//     5 uniform(-1, 1) (result = the float64 bit pattern), 6 advance by arg raw draws
 int apg_rng_host_stream(uint64_t seed, int32_t n_ops, const int32_t* op, const uint64_t* arg, uint64_t* out) {
   APG_CHECK(n_ops >= 0 && (n_ops == 0 || (op && arg && out)), APG_ERR_INVALID, "apg_rng_host_stream: bad argument");
   apg::Pcg64 g;
@@ -719,6 +720,8 @@ int apg_rng_host_stream(uint64_t seed, int32_t n_ops, const int32_t* op, const u
       case 2: out[i] = apg::rng_integers_below(g, arg[i]); break;
       case 3: out[i] = apg::rng_integers_0_to_2p32_inclusive(g); break;
       case 4: apg::pcg64_seed(g, arg[i]); out[i] = 0; break;
+      case 5: { const double u = apg::rng_uniform(g, -1.0, 2.0); memcpy(&out[i], &u, 8); break; }
+      case 6: apg::pcg64_advance(g, arg[i]); out[i] = 0; break;
       default: return apg::fail(APG_ERR_INVALID, "bad op %d", op[i]);
     }
   }

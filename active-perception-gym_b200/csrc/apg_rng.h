@@ -110,6 +110,32 @@ APG_HD uint64_t pcg64_next64(Pcg64& g) {
   return (x >> rot) | (x << ((64u - rot) & 63u));
 }
 
+// jump the 128-bit LCG ahead by `delta` raw draws (the 32-bit half-word buffer is left untouched)
+APG_HD void pcg64_advance(Pcg64& g, uint64_t delta) {
+  const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | (u128)0x4385DF649FCCF645ull;
+  u128 cur_mult = mult, cur_plus = ((u128)g.inc_hi << 64) | g.inc_lo;
+  u128 acc_mult = 1, acc_plus = 0;
+  while (delta > 0) {
+    if (delta & 1) {
+      acc_mult *= cur_mult;
+      acc_plus = acc_plus * cur_mult + cur_plus;
+    }
+    cur_plus = (cur_mult + 1) * cur_plus;
+    cur_mult *= cur_mult;
+    delta >>= 1;
+  }
+  u128 s = ((u128)g.state_hi << 64) | g.state_lo;
+  s = acc_mult * s + acc_plus;
+  g.state_hi = (uint64_t)(s >> 64);
+  g.state_lo = (uint64_t)s;
+}
+
+// Generator.uniform(low, low + range): low + range * ((raw >> 11) * 2^-53)   (one raw draw per double)
+APG_HD double rng_uniform(Pcg64& g, double low, double range) {
+  const double u = (double)(pcg64_next64(g) >> 11) * (1.0 / 9007199254740992.0);
+  return low + range * u;
+}
+
 APG_HD uint32_t pcg64_next32(Pcg64& g) {
   if (g.has_uint32) {
     g.has_uint32 = 0;

@@ -295,20 +295,10 @@ def main():
     # pre-draw the autoreset payloads of warm-up + timed region so the timed region is device-only
     run(0, W)
     barrier()
-    # queue as many payloads as the timed region needs (ring depth 64 >= K/17 + 1 for the default K);
-    # the LIDAR engine draws its resets on the device, nothing to stage
+    # the engine draws autoreset payloads itself (numpy-compatible streams); prefetch a ring-full so the timed region
+    # starts with payloads resident.  The LIDAR engine draws its resets on the device, nothing to stage.
     if not is_lidar:
-        b = env._buffers()
-        t_, need, resets = b.elapsed, bool(b.needs_reset), 0
-        for _ in range(K):
-            if need:
-                resets, t_, need = resets + 1, 0, False
-            else:
-                t_ += 1
-                need = t_ >= T
-        pre = min(resets, 64) - env._lib.apg_image_pending_payloads(env._h)
-        if pre > 0:
-            env.queue_autoreset_payloads(pre)
+        env.queue_autoreset_payloads(64)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -345,8 +335,6 @@ def main():
             _capi.check(lib.apg_lidar_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
                                                 h_tr.data_ptr(), None))
             return
-        if env._buffers().needs_reset and lib.apg_image_pending_payloads(env._h) == 0:
-            env.queue_autoreset_payloads(1)
         _capi.check(lib.apg_image_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
                                             h_tr.data_ptr(), None))
 

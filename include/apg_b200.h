@@ -138,6 +138,23 @@ int apg_image_queue_reset_payload(apg_image_env* env, const int64_t* h_idx, cons
                                   const float* h_target, const uint8_t* h_invert);
 int apg_image_pending_payloads(apg_image_env* env);
 
+/* The reference's three reset-path Generators (g0 env-level, g1 module-level, g2 dataset iterator) as
+ * numpy PCG64 states.  Once set, the engine draws the payload of every autoreset itself (host side, bit-identical to
+ * numpy: image_perception_module.py:129-133,159-161, dataset_iterator.py:57, image_localization.py:153-156) whenever
+ * no payload is queued -- for the GLOBAL batch of global_num_envs envs, of which this shard is
+ * [env_offset, env_offset + num_envs).  apg_image_get_streams returns the advanced states (e.g. to continue them in
+ * numpy for the next explicit reset). */
+typedef struct {
+  uint64_t state_hi, state_lo; /* numpy bit_generator.state["state"]["state"] (128 bit) */
+  uint64_t inc_hi, inc_lo;     /* ...["state"]["inc"] */
+  uint32_t has_uint32, uinteger;
+} apg_pcg64_state;
+int apg_image_set_streams(apg_image_env* env, const apg_pcg64_state* g0, const apg_pcg64_state* g1,
+                          const apg_pcg64_state* g2, int64_t global_num_envs, int64_t env_offset);
+int apg_image_get_streams(apg_image_env* env, apg_pcg64_state* g0, apg_pcg64_state* g1, apg_pcg64_state* g2);
+/* Draw and queue up to `count` autoreset payloads ahead of time from the streams (bounded by the ring). */
+int apg_image_prefetch_payloads(apg_image_env* env, int32_t count);
+
 /* One vector step with DEVICE inputs: d_action (N,2) f32, d_pred (N,K) f32 logits or (N,2) f32 coordinates.
  * One fused kernel launch; asynchronous.  Replaces ActivePerceptionVectorEnv.step end to end. */
 int apg_image_step(apg_image_env* env, const float* d_action, const float* d_pred);
@@ -245,7 +262,8 @@ int apg_lidar_sync(apg_lidar_env* env);
 /* Host-side test hook for the numpy-compatible random streams used on the device reset path (csrc/apg_rng.h):
  * a Generator(PCG64(SeedSequence(seed))) driven by n_ops operations --
  * op 0 next raw uint64, 1 next buffered uint32, 2 integers(0, arg), 3 integers(0, 2**32, endpoint=True),
- * 4 re-seed with SeedSequence(arg).  out[i] receives the result of operation i. */
+ * 4 re-seed with SeedSequence(arg), 5 uniform(-1, 1) (float64 bit pattern), 6 advance by arg raw draws.
+ * out[i] receives the result of operation i. */
 int apg_rng_host_stream(uint64_t seed, int32_t n_ops, const int32_t* op, const uint64_t* arg, uint64_t* out);
 
 /* ------------------------------------------------------------------------------------------------------

@@ -59,3 +59,26 @@ def test_bounded_draws_special_ranges():
     hi = 2**31 + 12345
     want = g.integers(0, hi, 500).tolist()
     assert _stream(11, [(2, hi)] * 500).tolist() == want
+
+
+def test_uniform_and_advance_match_numpy():
+    """image_perception_module.py:159-161 / image_localization.py:153-156: uniform(-1, 1) doubles, interleaved with
+    buffered 32-bit draws, and the LCG jump used to skip other shards' draws."""
+    seed = 21
+    g = np.random.default_rng(seed)
+    ops, want = [], []
+    for rep in range(3):
+        for _ in range(5):
+            ops.append((2, 2))
+            want.append(int(g.integers(0, 2)))
+        for _ in range(7):
+            ops.append((5, 0))
+            want.append(np.float64(g.uniform(-1, 1)).view(np.uint64).item())
+    got = _stream(seed, ops)
+    assert got.tolist() == want
+    # advance(k) == k discarded raw draws
+    for k in (1, 2, 17, 1000, 2**20 + 3):
+        g = np.random.default_rng(seed)
+        g.bit_generator.advance(k)
+        want = g.uniform(-1, 1, 3).view(np.uint64).tolist()
+        assert _stream(seed, [(6, k), (5, 0), (5, 0), (5, 0)])[1:].tolist() == want
