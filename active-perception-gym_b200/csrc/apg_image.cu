@@ -122,11 +122,12 @@ struct __align__(16) Tap {
   int pad;
 };
 
-struct __align__(16) EnvHdr {
-  int lead;     // byte offset of the tile's first needed column inside the staged (aligned-down) row
-  int cmin;     // first tap column of the tile
-  int rmin;     // first tap row of the tile
-  int nrows;    // staged rows
+struct __align__(16) EnvHdr {  // 16 bytes: the per-environment shared-memory footprint decides blocks per SM
+  unsigned short lead;   // byte offset of the tile's first needed column inside the staged (aligned-down) row
+  unsigned short nrows;  // staged rows
+  unsigned short cmin;   // first tap column of the tile
+  unsigned short rmin;   // first tap row of the tile
+  unsigned colbits[2];   // visited-mask column bits of this glimpse, words 0 and 1 (columns {j0, j0+1} of every tap)
 };
 
 // One lane's column of the sensor window (warp-per-environment path): walks the sensor rows i_first, i_first +
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
       Tap* rows = s_taps + el;                 // tap k of this env: rows[k * E]
       Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
       int rmin = 0, rmax = 0, cmin = 0, cmax = 0;
+      unsigned cb0 = 0u, cb1 = 0u;
       for (int i = 0; i < p.S0; ++i) {
         const double y = ccy + ((double)i - p.half0) * p.scale;
         if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
@@ -373,6 +375,8 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         cmax = k + 1;
         cols[j * p.E].w = w;
         cols[j * p.E].k = k;
+        if (k < 32) cb0 |= 1u << k; else if (k < 64) cb1 |= 1u << (k - 32);
+        if (k + 1 < 32) cb0 |= 1u << (k + 1); else if (k + 1 < 64) cb1 |= 1u << (k - 31);
       }
       const int nrows = min(rmax - rmin + 1, p.tile_rows);
       const int first_byte = cmin * p.C * ES;
@@ -381,7 +385,9 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
       int span = (cmax + 1) * p.C * ES - start;                          // bytes needed from `start`
       span = min((span + 15) & ~15, min(row_bytes - start, p.pitch));
       EnvHdr h;
-      h.lead = lead; h.cmin = cmin; h.rmin = rmin; h.nrows = nrows;
+      h.lead = (unsigned short)lead; h.cmin = (unsigned short)cmin; h.rmin = (unsigned short)rmin;
+      h.nrows = (unsigned short)nrows;
+      h.colbits[0] = cb0; h.colbits[1] = cb1;
       s_hdr[el] = h;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bank) + (long long)idx * p.H * row_bytes +
                                  (long long)rmin * row_bytes + start;
@@ -449,10 +455,14 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
             for (int q = 0; q < p.H * p.words; ++q) vm[q] = 0u;
           for (int w = 0; w < p.words; ++w) {
             unsigned bits = 0u;
-            for (int jj = 0; jj < p.S1; ++jj) {
-              const int j0 = cols[jj * p.E].k;
-              if ((j0 >> 5) == w) bits |= 1u << (j0 & 31);
-              if (((j0 + 1) >> 5) == w) bits |= 1u << ((j0 + 1) & 31);
+            if (w < 2) {
+              bits = h.colbits[w];
+            } else {
+              for (int jj = 0; jj < p.S1; ++jj) {
+                const int j0 = cols[jj * p.E].k;
+                if ((j0 >> 5) == w) bits |= 1u << (j0 & 31);
+                if (((j0 + 1) >> 5) == w) bits |= 1u << ((j0 + 1) & 31);
+              }
             }
             if (!bits) continue;
             int last = -1;  // tap rows are non-decreasing
@@ -486,13 +496,16 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
     const int r_sub = lane / cpp;
     const int jc0 = lane - r_sub * cpp;
     float* out_set = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
+    const int pitch_e = p.pitch / ES;
+    const int first = min(r_sub, p.S0 - 1);
+    const int n_rows = (p.S0 - first + R - 1) / R;
+    const int kind = (R == 1) ? ((p.C == 3) ? 3 : ((p.C == 1) ? 1 : 0)) : -1;
     for (int el = warp; el < nE; el += blockDim.x >> 5) {
       const EnvHdr h = s_hdr[el];
       const Tap* rows = s_taps + el;
-      const Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
-      const unsigned char* tile = s_tile + (size_t)el * p.tile_bytes;
-      float* out = out_set + (size_t)el * p.P;
-      unsigned colbits0 = 0u, colbits1 = 0u;
+      const Tap* cols = s_taps + p.S0 * p.E + el;
+      const unsigned char* tile = s_tile + el * p.tile_bytes;
+      float* out = out_set + el * p.P;
       for (int chunk = 0; chunk < n_chunks; ++chunk) {
         const int jc = (chunk << 5) + jc0;
         const bool col_ok = (jc < G) && (r_sub < R);
@@ -500,25 +513,15 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         const int c = jc - j * p.C;
         const Tap ct = cols[min(j, p.S1 - 1) * p.E];
         const double wx = ct.w, omx = 1.0 - ct.w;
-        if (set == 0 && col_ok && r_sub == 0) {
-          const int j0 = ct.k;
-          if ((j0 >> 5) == 0) colbits0 |= 1u << (j0 & 31);
-          else if ((j0 >> 5) == 1) colbits1 |= 1u << (j0 & 31);
-          if (((j0 + 1) >> 5) == 0) colbits0 |= 1u << ((j0 + 1) & 31);
-          else if (((j0 + 1) >> 5) == 1) colbits1 |= 1u << ((j0 + 1) & 31);
-        }
-        const BankT* colp = reinterpret_cast<const BankT*>(tile + h.lead) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
-        const int pitch_e = p.pitch / ES;
-        float* outp = out + min(r_sub, p.S0 - 1) * G + (col_ok ? jc : 0);
         // lanes without a column (or a row) run the same loads on valid addresses and skip the store
-        const int first = min(r_sub, p.S0 - 1);
-        const int n_rows = (p.S0 - first + R - 1) / R;
+        const BankT* colp = reinterpret_cast<const BankT*>(tile + h.lead) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
+        float* outp = out + first * G + (col_ok ? jc : 0);
         const Tap* tp = rows + first * p.E;
-        if (R == 1 && p.C == 3)
+        if (kind == 3)
           blend_column<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wx, omx, outp, G, col_ok);
-        else if (R == 1 && p.C == 1)
+        else if (kind == 1)
           blend_column<BankT, 1, true>(colp, tp, p.E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
-        else if (R == 1)
+        else if (kind == 0)
           blend_column<BankT, 0, true>(colp, tp, p.E, pitch_e, p.C, n_rows, wx, omx, outp, G, col_ok);
         else
           blend_column<BankT, 0, false>(colp, tp, R * p.E, pitch_e, p.C, n_rows, wx, omx, outp, R * G,
@@ -532,15 +535,18 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
           __syncwarp();
         }
         for (int w = 0; w < p.words; ++w) {
-          unsigned my = (w == 0) ? colbits0 : ((w == 1) ? colbits1 : 0u);
-          if (w >= 2) {  // images wider than 64 px
+          unsigned bits;
+          if (w < 2) {
+            bits = h.colbits[w];
+          } else {  // images wider than 64 px
+            unsigned my = 0u;
             for (int jj = lane; jj < p.S1; jj += 32) {
               const int j0 = cols[jj * p.E].k;
               if ((j0 >> 5) == w) my |= 1u << (j0 & 31);
               if (((j0 + 1) >> 5) == w) my |= 1u << ((j0 + 1) & 31);
             }
+            bits = __reduce_or_sync(0xffffffffu, my);
           }
-          const unsigned bits = __reduce_or_sync(0xffffffffu, my);
           if (bits) {
             for (int rr = lane; rr < 2 * p.S0; rr += 32) {
               const int row = h.rmin + ((rr < p.S0) ? rows[rr * p.E].k : rows[(rr - p.S0) * p.E].k + 1);
@@ -781,7 +787,8 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
                 (double)cfg->width >= cfg->sensor_w * cfg->sensor_scale,
             APG_ERR_INVALID, "Image size (%d, %d) cannot be smaller than effective sensor size (%g, %g).",
             cfg->height, cfg->width, cfg->sensor_h * cfg->sensor_scale, cfg->sensor_w * cfg->sensor_scale);
-  APG_CHECK(cfg->height >= 2 && cfg->width >= 2, APG_ERR_INVALID, "image must be at least 2x2");
+  APG_CHECK(cfg->height >= 2 && cfg->width >= 2 && cfg->height <= 32768 && cfg->width <= 32768, APG_ERR_INVALID,
+            "image must be between 2x2 and 32768x32768");
   APG_CHECK(cfg->step_limit > 0, APG_ERR_INVALID, "step_limit must be positive");
   APG_CHECK(cfg->bank_dtype == APG_BANK_U8 || cfg->bank_dtype == APG_BANK_F32, APG_ERR_INVALID, "bad bank dtype");
   if (cfg->task == APG_TASK_CLASSIFICATION)
@@ -828,6 +835,10 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       E = E > 64 ? 64 : E;
       if (per_env > 768 && E > 32) E = 32;
       e->threads = kThreads;
+      if (const char* ov = getenv("APG_IMG_THREADS")) {
+        const int v = atoi(ov);
+        if (v >= 32 && v <= kThreads && v % 32 == 0) e->threads = v;
+      }
     }
     if (const char* ov = getenv("APG_IMG_ENVS_PER_BLOCK")) {
       const int v = atoi(ov);
