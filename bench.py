@@ -364,6 +364,13 @@ def main():
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:  # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if args.workload in tj and n == w["n_envs"]:
+                traffic = tj[args.workload]["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         bytes_per_launch = w["bytes_per_step"] * n
         avg_launch_s = (ms_max * 1e-3) / K
         achieved = bytes_per_launch / avg_launch_s / 1e9
@@ -378,7 +385,7 @@ def main():
                     "steps": Ke, "api": ("apg_lidar_step_host" if is_lidar else "apg_image_step_host") + " (pinned host action/prediction in, reward/terminated/truncated out)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel": "lidar_step_kernel" if is_lidar else "image_step_kernel", "bytes_per_env_step": w["bytes_per_step"],
                          "avg_launch_us": avg_launch_s * 1e6},
             "episode_stats_allreduce": stats,
