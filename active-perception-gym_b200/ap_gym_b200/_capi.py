@@ -114,6 +114,7 @@ SYMBOLS = {
     "apg_lidar_set_map_bank": (C.c_int, [_P, _P, C.c_int64]),
     "apg_lidar_set_beams": (C.c_int, [_P, _P]),
     "apg_lidar_reset": (C.c_int, [_P, C.c_uint64]),
+    "apg_lidar_reset_all": (C.c_int, [_P]),
     "apg_lidar_step": (C.c_int, [_P, _P, _P]),
     "apg_lidar_rollout": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "apg_lidar_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

@@ -150,13 +150,13 @@ class LIDARLocalization2DVectorEnv:
             self._poll()
 
     def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
-        if seed is None:
-            if self._has_reset:
-                raise NotImplementedError(
-                    "reset() without a seed after the first reset is not supported: every env autoresets on its own")
-            # like gymnasium's lazily seeded np_random: entropy from the OS
-            seed = int(np.random.SeedSequence().entropy % (2**63))
-        _capi.check(self._lib.apg_lidar_reset(self._h, C.c_uint64(int(seed))))
+        if seed is None and self._has_reset:
+            # every env resets, its own Generators continue (what SyncVectorEnv.reset() without a seed does)
+            _capi.check(self._lib.apg_lidar_reset_all(self._h))
+        else:
+            if seed is None:  # like gymnasium's lazily seeded np_random: entropy from the OS
+                seed = int(np.random.SeedSequence().entropy % (2**63))
+            _capi.check(self._lib.apg_lidar_reset(self._h, C.c_uint64(int(seed))))
         self._has_reset = True
         as_numpy = self._numpy_mode or bool(options and options.get("numpy", False))
         return self._obs(as_numpy), {"map_idx": self._out("map_idx", as_numpy)}

@@ -41,6 +41,7 @@ struct ImgParams {
   int tile_rows;     // staged rows per environment
   int tile_bytes;    // pitch * tile_rows
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
+  int tb;            // thread-blend path: threads that share one environment's sensor columns
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
   int t_stamp;       // overlay stamp slot of this step (pre-move time index), mode 0 only
   float time_obs;    // obs["time_step"] value after this step
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 
   for (int set = 0; set < n_sets; ++set) {
     // ------------------------------------------------------------------ phase A: thread = environment
-    for (int el = tid; el < nE; el += blockDim.x) {
+    for (int el = tid; el < nE; el += blockDim.x) {  // one iteration: E <= blockDim
       const int n = env0 + el;
       unsigned err = 0;
       if (set == 0) {
@@ -411,14 +412,17 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
       // (conflict-free) and the block then streams them out as one contiguous, fully coalesced run.
       float* s_out = reinterpret_cast<float*>(s_tile + (size_t)p.E * p.tile_bytes);
       const int Pp = p.P | 1;  // odd stride in floats
-      for (int el = tid; el < nE; el += blockDim.x) {
+      // `tb` threads share an environment: thread tid serves env (tid % E) and the sensor columns tid / E, + tb, ...
+      const int tb = p.tb;
+      const int sub = tid / p.E;
+      for (int el = tid - sub * p.E; el < nE && sub < tb; el += p.E * tb) {
         const EnvHdr h = s_hdr[el];
         const Tap* rows = s_taps + el;
         const Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
         const BankT* tile = reinterpret_cast<const BankT*>(s_tile + (size_t)el * p.tile_bytes + h.lead);
         const int pitch_e = p.pitch / ES;
         float* o = s_out + (size_t)el * Pp;
-        for (int j = 0; j < p.S1; ++j) {
+        for (int j = sub; j < p.S1; j += tb) {
           const Tap ct = cols[j * p.E];
           const double wx = ct.w, omx = 1.0 - ct.w;
           const BankT* colp = tile + (ct.k - h.cmin) * p.C;
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
             }
           }
         }
-        if (p.track && set == 0) {
+        if (p.track && set == 0 && sub == 0) {
           unsigned* vm = p.visited + (size_t)(env0 + el) * p.H * p.words;
           if (p.mode != 0)
             for (int q = 0; q < p.H * p.words; ++q) vm[q] = 0u;
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 struct apg_image_env {
   apg_image_cfg cfg{};
   cudaStream_t stream = nullptr;
-  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0;
+  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -652,7 +656,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.tb = e->tb; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -827,7 +831,9 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       per_env += (size_t)(e->P | 1) * 4;  // parked output floats
       E = (int)((64 * 1024) / per_env);
       E = E >= 64 ? 64 : 32;  // swept on B200: 64 beats 32 and 128 for the 5x5x1 MNIST glimpse
-      e->threads = E;
+      e->tb = cfg->sensor_w >= 2 ? 2 : 1;
+      if (const char* ov = getenv("APG_IMG_TB")) { const int v = atoi(ov); if (v >= 1 && v <= 4) e->tb = v; }
+      e->threads = E * e->tb;
     } else {
       // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
       // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
@@ -843,7 +849,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     if (const char* ov = getenv("APG_IMG_ENVS_PER_BLOCK")) {
       const int v = atoi(ov);
       if (v >= 1 && v <= kThreads && (size_t)v * per_env <= 200 * 1024) E = v;
-      if (e->thread_blend) e->threads = ((E + 31) / 32) * 32;
+      if (e->thread_blend) e->threads = (((E + 31) / 32) * 32) * e->tb;
     }
     E = E >= 8 ? (E & ~7) : (E >= 4 ? 4 : (E >= 2 ? 2 : 1));
     e->E = E;

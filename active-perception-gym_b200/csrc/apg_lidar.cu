@@ -32,7 +32,7 @@ constexpr int kEnvsPerBlock = 32;
 struct LidarParams {
   int N, W, H, words, B, G, T, M;
   int static_map, static_idx, emit_cells;
-  int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams)
+  int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams), 3 = explicit reset (keep streams)
   float range;
   unsigned long long seed;  // mode 2: env i is seeded with seed + env_offset + i
   long long env_offset;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   const int n = env0 + lane;          // warp 0's environment
   const bool act = (warp == 0) && (lane < nE);
   if (act) {
-    do_reset = (p.mode == 2) || (p.prev_done[n] != 0);
+    do_reset = (p.mode != 0) || (p.prev_done[n] != 0);
     int midx;
     if (do_reset) {
       apg::Pcg64 g0, g2;
@@ -633,6 +633,13 @@ int apg_lidar_reset(apg_lidar_env* e, uint64_t seed) {
   if (rc != APG_OK) return rc;
   e->has_reset = true;
   return APG_OK;
+}
+
+int apg_lidar_reset_all(apg_lidar_env* e) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  APG_CHECK(e->has_reset, APG_ERR_STATE, "the first reset must be seeded (the reference has no data loader before that either)");
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  return lidar_launch(e, 3, 0, nullptr, nullptr, nullptr, nullptr);
 }
 
 int apg_lidar_step(apg_lidar_env* e, const float* d_action, const float* d_pred) {

@@ -247,6 +247,8 @@ int apg_lidar_set_map_bank(apg_lidar_env* env, const uint32_t* h_bits, int64_t n
 int apg_lidar_set_beams(apg_lidar_env* env, const float* h_dirs);
 /* reset(seed=seed): seeds env i with seed + env_offset + i and resets every env.  Asynchronous. */
 int apg_lidar_reset(apg_lidar_env* env, uint64_t seed);
+/* reset() without a seed: every env resets now, its random streams continue where they are.  Asynchronous. */
+int apg_lidar_reset_all(apg_lidar_env* env);
 /* One vector step, DEVICE inputs d_action (N,2), d_pred (N,2) float32.  One kernel launch, asynchronous. */
 int apg_lidar_step(apg_lidar_env* env, const float* d_action, const float* d_pred);
 int apg_lidar_rollout(apg_lidar_env* env, const float* d_actions, const float* d_preds, int32_t n_steps,

@@ -96,6 +96,33 @@ def test_engine_matches_oracle_seeded(bank, B, N, steps):
     env.close()
 
 
+def test_unseeded_reset_continues_the_streams():
+    import ap_gym_b200 as apg
+    from oracle.lidar_oracle import LidarVecOracle
+
+    maps = load_bank("rooms32", 32)
+    N, B = 64, 8
+    oracle = LidarVecOracle(maps, N, beam_count=B)
+    env = apg.LIDARLocalization2DVectorEnv(N, apg.FloorMapBank.from_maps(maps), lidar_beam_count=B, output="numpy")
+    oracle.reset(seed=5)
+    env.reset(seed=5)
+    rng = np.random.default_rng(0)
+    for s in range(7):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        oracle.step(a, a)
+        env.step({"action": a, "prediction": a})
+    # SyncVectorEnv.reset() without a seed: every sub-env resets, Generators continue
+    for i in range(N):
+        oracle._reset_env(i)
+    oracle.autoreset[:] = False
+    oracle._scan_obs(np.ones(N, bool))
+    eo, einfo = env.reset()
+    assert np.array_equal(einfo["map_idx"], oracle.map_idx)
+    assert np.array_equal(_np(env.state()["pos"]), oracle.pos)
+    assert np.array_equal(eo["lidar"], oracle.lidar)
+    env.close()
+
+
 def test_adversarial_rays_through_the_engine():
     """The degenerate single rays of tests/golden/lidar_scan_adversarial.npz, cast as *beams*: an env is placed
     by choosing a one-free-cell... not possible for arbitrary positions, so instead the move ray is used:
