@@ -108,6 +108,7 @@ SYMBOLS = {
     "apg_image_get_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "apg_image_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),
     "apg_image_sync": (C.c_int, [_P]),
+    "apg_image_variant": (C.c_int, [_P]),
     "apg_lidar_create": (C.c_int, [C.POINTER(LidarCfg), C.POINTER(_P)]),
     "apg_lidar_destroy": (None, [_P]),
     "apg_lidar_set_stream": (C.c_int, [_P, _P]),

@@ -386,7 +386,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "kernel": "lidar_step_kernel" if is_lidar else "image_step_kernel", "bytes_per_env_step": w["bytes_per_step"],
+                         "kernel": "lidar_step_kernel" if is_lidar else
+                         ["image_step_kernel (warp blend)", "image_step_kernel (thread blend)",
+                          "image_step_pipelined_kernel"][lib.apg_image_variant(env._h)], "bytes_per_env_step": w["bytes_per_step"],
                          "avg_launch_us": avg_launch_s * 1e6},
             "episode_stats_allreduce": stats,
         }

@@ -187,6 +187,9 @@ int apg_image_get_stats(apg_image_env* env, double* h_stats, int clear);
 /* Reads (and with clear!=0 resets) the sticky device error flags; synchronises the stream. */
 int apg_image_poll_error(apg_image_env* env, uint32_t* flags, int clear);
 int apg_image_sync(apg_image_env* env);
+/* Which step-kernel variant the handle selected for its sensor geometry: 0 = block-staged / warp-per-env blend,
+ * 1 = block-staged / thread-per-env blend (small glimpses), 2 = persistent producer/consumer pipeline. */
+int apg_image_variant(apg_image_env* env);
 
 /* ------------------------------------------------------------------------------------------------------
  * LIDAR localisation environments.  One handle = one shard of the vector env that

@@ -171,6 +171,38 @@ def test_unique_glimpse_targets_match_reference(name):
     env.close()
 
 
+def test_pipelined_variant_matches_default(monkeypatch):
+    """The opt-in persistent producer/consumer kernel (APG_IMG_PIPELINE=1) against the default kernel: bit-identical
+    observations, rewards and state over two episodes of the localisation env (target glimpse = second set)."""
+    import ap_gym_b200 as apg
+    from oracle.datasets import synthetic_u8_bank
+
+    imgs, labels = synthetic_u8_bank(seed=9, M=64, H=64, W=64, C=3, K=5)
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, 5), sensor_size=(10, 10), step_limit=6)
+    N = 1000
+    rng = np.random.default_rng(1)
+    tgt = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+    envs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("APG_IMG_PIPELINE", flag)
+        envs.append(apg.ImageLocalizationVectorEnv(N, cfg, output="numpy"))
+    assert envs[0]._lib.apg_image_variant(envs[0]._h) == 0 and envs[1]._lib.apg_image_variant(envs[1]._h) == 2
+    obs = [e.reset(seed=4, options={"prediction_target": tgt})[0] for e in envs]
+    for k in obs[0]:
+        assert np.array_equal(obs[0][k], obs[1][k]), k
+    for s in range(15):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        p = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        out = [e.step({"action": a, "prediction": p}) for e in envs]
+        for k in out[0][0]:
+            assert np.array_equal(out[0][0][k], out[1][0][k]), f"step {s} obs {k}"
+        assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+        assert np.array_equal(_np(envs[0].state()["visited"]), _np(envs[1].state()["visited"]))
+    assert envs[0].episode_stats(reduce=False) == envs[1].episode_stats(reduce=False)
+    for e in envs:
+        e.close()
+
+
 def test_error_conventions():
     import ap_gym_b200 as apg
     from oracle.datasets import synthetic_u8_bank
