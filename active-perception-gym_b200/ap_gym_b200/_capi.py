@@ -30,7 +30,7 @@ class ImageCfg(C.Structure):
         ("sensor_h", C.c_int32), ("sensor_w", C.c_int32),
         ("sensor_scale", C.c_double), ("max_step_length", C.c_double * 2),
         ("step_limit", C.c_int32), ("num_classes", C.c_int32), ("bank_dtype", C.c_int32),
-        ("randomly_invert_labels", C.c_int32), ("track_visited", C.c_int32), ("payload_ring", C.c_int32),
+        ("randomly_invert_labels", C.c_int32), ("track_visited", C.c_int32), ("payload_ring", C.c_int32), ("blend_f32", C.c_int32),
     ]
 
 

@@ -62,9 +62,13 @@ class _ImageVectorEnvBase:
                  render_mode: Literal["rgb_array"] = "rgb_array", *, device: int = 0,
                  env_offset: int = 0, global_num_envs: int | None = None, track_visited: bool = True,
                  check_errors: Literal["step", "lazy", "never"] = "lazy",
-                 output: Literal["torch", "numpy"] = "torch", payload_ring: int = 4):
+                 output: Literal["torch", "numpy"] = "torch", payload_ring: int = 4,
+                 blend: Literal["float64", "float32"] = "float64"):
         if render_mode not in self.metadata["render_modes"]:
             raise ValueError(f"Unsupported render mode: {render_mode}")
+        if blend not in ("float64", "float32"):
+            raise ValueError("blend must be 'float64' (the reference's arithmetic, bit-exact) or 'float32'")
+        self.blend = blend
         cfg = image_perception_config
         self._config = cfg
         self._render_mode = render_mode
@@ -100,7 +104,7 @@ class _ImageVectorEnvBase:
             max_step_length=(C.c_double * 2)(float(msl[0]), float(msl[1])), step_limit=int(cfg.step_limit),
             num_classes=self._K, bank_dtype=_capi.BANK_U8 if bank.is_u8 else _capi.BANK_F32,
             randomly_invert_labels=int(cfg.randomly_invert_labels), track_visited=int(track_visited),
-            payload_ring=int(payload_ring))
+            payload_ring=int(payload_ring), blend_f32=int(blend == "float32"))
         self._ring = max(1, min(int(payload_ring) if payload_ring > 0 else _capi.PAYLOAD_RING_DEFAULT,
                                 _capi.PAYLOAD_RING_MAX))
         h = C.c_void_p()

@@ -41,6 +41,8 @@ struct ImgParams {
   int tile_rows;     // staged rows per environment
   int tile_bytes;    // pitch * tile_rows
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
+  int split;         // warp path: phase A split into per-env scalars (one thread) + taps / staging (all threads)
+  int fast;          // 1: float32 blend (within the 1e-5 bar), 0: the reference's float64 blend (bit-exact)
   int tb;            // thread-blend path: threads that share one environment's sensor columns
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
   int t_stamp;       // overlay stamp slot of this step (pre-move time index), mode 0 only
@@ -133,8 +135,13 @@ __device__ __forceinline__ double px_to_f64(unsigned char u) {
 __device__ __forceinline__ double px_to_f64(float v) { return (double)v; }
 
 struct __align__(16) Tap {
-  double w;  // normalised distance to the lower grid point
-  int k;     // tap index relative to the staged tile (row) / absolute column
+  union {
+    double w;  // exact blend: normalised distance to the lower grid point (float64, like scipy)
+    struct {
+      float wf, omwf;  // float32 blend: w and 1 - w, each rounded once from the float64 values
+    };
+  };
+  int k;  // tap index relative to the staged tile (row) / absolute column
   int pad;
 };
 
@@ -145,6 +152,40 @@ struct __align__(16) EnvHdr {  // 16 bytes: the per-environment shared-memory fo
   unsigned short rmin;   // first tap row of the tile
   unsigned colbits[2];   // visited-mask column bits of this glimpse, words 0 and 1 (columns {j0, j0+1} of every tap)
 };
+
+// float32 blend (opt-in): pixel -> float32 without the exact-division emulation; the result differs from the reference's
+// float64 blend by a few float32 ulps of the (non-negative) sum, far inside the 1e-5 relative bar.
+__device__ __forceinline__ float px_to_f32(unsigned char u) { return __fmul_rn((float)u, 0.003921568859368563f); }
+__device__ __forceinline__ float px_to_f32(float v) { return v; }
+
+template <typename BankT, int CT, bool VREUSE>
+__device__ __forceinline__ void blend_column_f32(const BankT* __restrict__ colp, const Tap* __restrict__ tp, int tap_step,
+                                                 int pitch_e, int c_rt, int n_rows, float wx, float omx,
+                                                 float* __restrict__ outp, int out_step, bool store_ok) {
+  const int C = CT ? CT : c_rt;
+  int prev_k = -4;
+  float b0 = 0.0f, b1 = 0.0f;
+  for (int i = 0; i < n_rows; ++i, tp += tap_step, outp += out_step) {
+    const Tap rt = *tp;
+    const BankT* rp = colp + rt.k * pitch_e;
+    float p00 = b0, p01 = b1;
+    if (!VREUSE || rt.k != prev_k + 1) {
+      p00 = px_to_f32(rp[0]);
+      p01 = px_to_f32(rp[C]);
+    }
+    rp += pitch_e;
+    const float p10 = px_to_f32(rp[0]), p11 = px_to_f32(rp[C]);
+    b0 = p10;
+    b1 = p11;
+    prev_k = rt.k;
+    const float wy = rt.wf, omy = rt.omwf;
+    float acc = __fmul_rn(p00, __fmul_rn(omy, omx));
+    acc = __fmaf_rn(p01, __fmul_rn(omy, wx), acc);
+    acc = __fmaf_rn(p10, __fmul_rn(wy, omx), acc);
+    acc = __fmaf_rn(p11, __fmul_rn(wy, wx), acc);
+    if (store_ok) *outp = __saturatef(acc);
+  }
+}
 
 // One lane's column of the sensor window (warp-per-environment path): walks the sensor rows i_first, i_first +
 // i_step, ... of one (column, channel), blending from the staged tile.  With one sensor row per pass (VREUSE) the
@@ -356,7 +397,8 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
     tap(y, p.offy, p.H, k, w);
     if (i == 0) rmin = k;
     rmax = k + 1;
-    rows[i * p.E].w = w;
+    if (p.fast) { rows[i * p.E].wf = (float)w; rows[i * p.E].omwf = (float)(1.0 - w); }
+    else rows[i * p.E].w = w;
     rows[i * p.E].k = k - rmin;
   }
   for (int j = 0; j < p.S1; ++j) {
@@ -367,7 +409,8 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
     tap(x, p.offx, p.W, k, w);
     if (j == 0) cmin = k;
     cmax = k + 1;
-    cols[j * p.E].w = w;
+    if (p.fast) { cols[j * p.E].wf = (float)w; cols[j * p.E].omwf = (float)(1.0 - w); }
+    else cols[j * p.E].w = w;
     cols[j * p.E].k = k;
     if (k < 32) cb0 |= 1u << k; else if (k < 64) cb1 |= 1u << (k - 32);
     if (k + 1 < 32) cb0 |= 1u << (k + 1); else if (k + 1 < 64) cb1 |= 1u << (k - 31);
@@ -390,6 +433,99 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
     for (int b = 0; b < span; b += 16) __pipeline_memcpy_async(dst + b, src + b, 16);
     src += row_bytes;
     dst += p.pitch;
+  }
+}
+
+// ---- split phase A (warp-per-environment path) ------------------------------------------------------------------------
+// The serial per-environment part of phase A (40 taps + ~35 copies for a 10x10x3 glimpse) kept one warp busy for ~40 % of
+// a block's lifetime while the other warps waited at the barrier (profiles/r01_final_tinyloc.txt: 35 % of all stall
+// samples).  Split: the environment's thread only does the scalars and the tile header (first / last tap per axis);
+// after a barrier ALL threads compute the taps (one tap per work item) and issue the copies (one 16-byte chunk per item,
+// consecutive threads -> consecutive chunks of a row).
+struct __align__(16) EnvCtr {  // sensor centre (pixels), bank image and copy span of one environment
+  double ccx, ccy;
+  int idx, span;
+  int pad[2];
+};
+
+template <typename BankT>
+__device__ __forceinline__ void stage_head(const ImgParams& p, int el, EnvHdr* s_hdr, EnvCtr* s_ctr, double ccx, double ccy,
+                                           int idx, unsigned& err) {
+  constexpr int ES = (int)sizeof(BankT);
+  // the tap coordinates are monotone in the tap number: the first and the last one decide the footprint and the
+  // out-of-grid flag
+  const double y0 = ccy + (0.0 - p.half0) * p.scale, y1 = ccy + ((double)(p.S0 - 1) - p.half0) * p.scale;
+  const double x0 = ccx + (0.0 - p.half1) * p.scale, x1 = ccx + ((double)(p.S1 - 1) - p.half1) * p.scale;
+  if (y0 < -p.offy || y0 > p.offy || y1 < -p.offy || y1 > p.offy || x0 < -p.offx || x0 > p.offx || x1 < -p.offx ||
+      x1 > p.offx)
+    err |= APG_FLAG_OUT_OF_GRID;
+  int rmin, rlast, cmin, clast;
+  double w;
+  tap(y0, p.offy, p.H, rmin, w);
+  tap(y1, p.offy, p.H, rlast, w);
+  tap(x0, p.offx, p.W, cmin, w);
+  tap(x1, p.offx, p.W, clast, w);
+  const int nrows = min(rlast + 1 - rmin + 1, p.tile_rows);
+  const int first_byte = cmin * p.C * ES;
+  const int lead = first_byte & 15;
+  const int start = first_byte - lead;
+  int span = (clast + 2) * p.C * ES - start;
+  span = min((span + 15) & ~15, min(p.bank_pitch - start, p.pitch));
+  EnvHdr h;
+  h.lead = (unsigned short)lead; h.cmin = (unsigned short)cmin; h.rmin = (unsigned short)rmin;
+  h.nrows = (unsigned short)nrows;
+  h.colbits[0] = 0u; h.colbits[1] = 0u;  // OR-ed together by the column-tap work items
+  s_hdr[el] = h;
+  EnvCtr c;
+  c.ccx = ccx; c.ccy = ccy; c.idx = idx; c.span = span; c.pad[0] = c.pad[1] = 0;
+  s_ctr[el] = c;
+}
+
+template <typename BankT>
+__device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid, int nthreads, EnvHdr* s_hdr,
+                                            const EnvCtr* s_ctr, Tap* s_taps, unsigned char* s_tile) {
+  constexpr int ES = (int)sizeof(BankT);
+  // copies first (longest latency): item = (environment, tile row, 16-byte chunk)
+  const int nch = p.pitch >> 4;
+  const int per_env = p.tile_rows * nch;
+  for (int q = tid; q < nE * per_env; q += nthreads) {
+    const int el = q / per_env;
+    const int rem = q - el * per_env;
+    const int r = rem / nch;
+    const int b = (rem - r * nch) << 4;
+    const EnvHdr h = s_hdr[el];
+    const EnvCtr c = s_ctr[el];
+    if (r < (int)h.nrows && b < c.span) {
+      const int start = (int)h.cmin * p.C * ES - (int)h.lead;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bank) + (long long)c.idx * p.H * p.bank_pitch +
+                                 (long long)((int)h.rmin + r) * p.bank_pitch + start + b;
+      __pipeline_memcpy_async(s_tile + (size_t)el * p.tile_bytes + r * p.pitch + b, src, 16);
+    }
+  }
+  // taps: item = (tap, environment), environment fastest (conflict-free shared-memory stores)
+  const int n_taps = p.S0 + p.S1;
+  for (int q = tid; q < n_taps * p.E; q += nthreads) {
+    const int t = q / p.E;
+    const int el = q - t * p.E;
+    if (el >= nE) continue;
+    const EnvCtr c = s_ctr[el];
+    int k;
+    double w;
+    if (t < p.S0) {
+      tap(c.ccy + ((double)t - p.half0) * p.scale, p.offy, p.H, k, w);
+      k -= (int)s_hdr[el].rmin;
+    } else {
+      tap(c.ccx + ((double)(t - p.S0) - p.half1) * p.scale, p.offx, p.W, k, w);
+      unsigned b0 = 0u, b1 = 0u;
+      if (k < 32) b0 |= 1u << k; else if (k < 64) b1 |= 1u << (k - 32);
+      if (k + 1 < 32) b0 |= 1u << (k + 1); else if (k + 1 < 64) b1 |= 1u << (k - 31);
+      if (b0) atomicOr(&s_hdr[el].colbits[0], b0);
+      if (b1) atomicOr(&s_hdr[el].colbits[1], b1);
+    }
+    Tap* tp = s_taps + (size_t)t * p.E + el;
+    if (p.fast) { tp->wf = (float)w; tp->omwf = (float)(1.0 - w); }
+    else tp->w = w;
+    tp->k = k;
   }
 }
 
@@ -435,7 +571,18 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
     const BankT* colp = reinterpret_cast<const BankT*>(tile + h.lead) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
     float* outp = out + first * G + (col_ok ? jc : 0);
     const Tap* tp = rows + first * p.E;
-    if (kind == 3)
+    if (p.fast) {
+      const float wxf = ct.wf, omxf = ct.omwf;
+      if (kind == 3)
+        blend_column_f32<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wxf, omxf, outp, G, col_ok);
+      else if (kind == 1)
+        blend_column_f32<BankT, 1, true>(colp, tp, p.E, pitch_e, 1, n_rows, wxf, omxf, outp, G, col_ok);
+      else if (kind == 0)
+        blend_column_f32<BankT, 0, true>(colp, tp, p.E, pitch_e, p.C, n_rows, wxf, omxf, outp, G, col_ok);
+      else
+        blend_column_f32<BankT, 0, false>(colp, tp, R * p.E, pitch_e, p.C, n_rows, wxf, omxf, outp, R * G,
+                                          col_ok && r_sub < p.S0);
+    } else if (kind == 3)
       blend_column<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wx, omx, outp, G, col_ok);
     else if (kind == 1)
       blend_column<BankT, 1, true>(colp, tp, p.E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
@@ -502,11 +649,24 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
 
   for (int set = 0; set < n_sets; ++set) {
     // ------------------------------------------------------------------ phase A: thread = environment
-    for (int el = tid; el < nE; el += blockDim.x) {  // one iteration: E <= blockDim
-      unsigned err = 0;
-      if (set == 0) env_scalars(p, env0 + el, s_stats, ep_end, px, py, tcx, tcy, idx, err);
-      stage_env<BankT>(p, el, s_hdr, s_taps, s_tile, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx, err);
-      if (err) atomicOr(p.err, err);
+    if (p.split) {
+      EnvCtr* s_ctr = reinterpret_cast<EnvCtr*>(s_tile + (size_t)p.E * p.tile_bytes);
+      for (int el = tid; el < nE; el += blockDim.x) {
+        unsigned err = 0;
+        if (set == 0) env_scalars(p, env0 + el, s_stats, ep_end, px, py, tcx, tcy, idx, err);
+        stage_head<BankT>(p, el, s_hdr, s_ctr, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx, err);
+        if (err) atomicOr(p.err, err);
+      }
+      __syncthreads();
+      stage_block<BankT>(p, nE, tid, blockDim.x, s_hdr, s_ctr, s_taps, s_tile);
+    } else {
+      for (int el = tid; el < nE; el += blockDim.x) {  // one iteration: E <= blockDim
+        unsigned err = 0;
+        if (set == 0) env_scalars(p, env0 + el, s_stats, ep_end, px, py, tcx, tcy, idx, err);
+        stage_env<BankT>(p, el, s_hdr, s_taps, s_tile, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx,
+                         err);
+        if (err) atomicOr(p.err, err);
+      }
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -532,33 +692,14 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         float* o = s_out + (size_t)el * Pp;
         for (int j = sub; j < p.S1; j += tb) {
           const Tap ct = cols[j * p.E];
-          const double wx = ct.w, omx = 1.0 - ct.w;
           const BankT* colp = tile + (ct.k - h.cmin) * p.C;
           for (int c = 0; c < p.C; ++c) {
-            int prev_k = -4;
-            double b0 = 0.0, b1 = 0.0;
-            for (int i = 0; i < p.S0; ++i) {
-              const Tap rt = rows[i * p.E];
-              const BankT* rp = colp + rt.k * pitch_e + c;
-              double p00, p01;
-              if (rt.k == prev_k + 1) {
-                p00 = b0;
-                p01 = b1;
-              } else {
-                p00 = px_to_f64(rp[0]);
-                p01 = px_to_f64(rp[p.C]);
-              }
-              const double p10 = px_to_f64(rp[pitch_e]), p11 = px_to_f64(rp[pitch_e + p.C]);
-              b0 = p10;
-              b1 = p11;
-              prev_k = rt.k;
-              const double wy = rt.w, omy = 1.0 - rt.w;
-              double acc = 0.0 + p00 * (omy * omx);
-              acc = acc + p01 * (omy * wx);
-              acc = acc + p10 * (wy * omx);
-              acc = acc + p11 * (wy * wx);
-              o[(i * p.S1 + j) * p.C + c] = (ES == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
-            }
+            if (p.fast)
+              blend_column_f32<BankT, 0, true>(colp + c, rows, p.E, pitch_e, p.C, p.S0, ct.wf, ct.omwf, o + j * p.C + c,
+                                               p.S1 * p.C, true);
+            else
+              blend_column<BankT, 0, true>(colp + c, rows, p.E, pitch_e, p.C, p.S0, ct.w, 1.0 - ct.w, o + j * p.C + c,
+                                           p.S1 * p.C, true);
           }
         }
         if (p.track && set == 0 && sub == 0) {
@@ -692,6 +833,7 @@ struct apg_image_env {
   cudaStream_t stream = nullptr;
   int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
+  int split = 0;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -774,7 +916,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.tb = e->tb; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -966,6 +1108,9 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       E = E > 64 ? 64 : E;
       if (per_env > 768 && E > 32) E = 32;
       e->threads = kThreads;
+      e->split = 1;
+      if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) ? 1 : 0;
+      if (e->split) per_env += sizeof(EnvCtr);
       if (const char* ov = getenv("APG_IMG_THREADS")) {
         const int v = atoi(ov);
         if (v >= 32 && v <= kThreads && v % 32 == 0) e->threads = v;

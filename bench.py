@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--bank", type=int, default=0, help="override bank length")
     ap.add_argument("--e2e-steps", type=int, default=68)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blend", default="float64", choices=["float64", "float32"],
+                    help="image workloads: float64 = the reference's blend arithmetic (bit-exact pixels, default); "
+                         "float32 = opt-in blend within the 1e-5 relative bar")
     return ap.parse_args()
 
 
@@ -225,7 +228,7 @@ def build_env(args, rank, world, device):
         ds = apg.SyntheticImageDataset("mnist", length=args.bank or None, seed=0)
         cfg = apg.ImagePerceptionConfig(dataset=ds)
         env = apg.ImageClassificationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
-                                               check_errors="never", payload_ring=64)
+                                               check_errors="never", payload_ring=64, blend=args.blend)
         pw = 10
     elif args.workload in LIDAR:
         fname, beams = LIDAR[args.workload]
@@ -237,7 +240,7 @@ def build_env(args, rank, world, device):
         ds = apg.SyntheticImageDataset("tinyimagenet", length=args.bank or None, seed=0)
         cfg = apg.ImagePerceptionConfig(dataset=ds, sensor_size=(10, 10))
         env = apg.ImageLocalizationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
-                                             check_errors="never", payload_ring=64)
+                                             check_errors="never", payload_ring=64, blend=args.blend)
         pw = 2
     return env, n, pw
 
@@ -378,7 +381,7 @@ def main():
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}", "explicit_reset_s": round(reset_s, 3),
+            "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}", "blend": None if is_lidar else args.blend, "explicit_reset_s": round(reset_s, 3),
                        "l2": "per-step inputs are distinct and streamed from HBM (%.0f MB total > 126 MB L2); engine-owned obs buffers are rewritten every step" % (acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -74,6 +74,9 @@ typedef struct {
   int32_t randomly_invert_labels; /* ImagePerceptionConfig.randomly_invert_labels */
   int32_t track_visited;          /* keep the visited bitmask + overlay stamp log (reference: always on) */
   int32_t payload_ring;           /* how many future autoreset payloads may be queued (0 -> 4, max 64) */
+  int32_t blend_f32;              /* 0: the reference's float64 blend (bit-exact pixels); 1: float32 blend with weights
+                                     rounded once from float64 (pixels within a few float32 ulps, i.e. inside the
+                                     1e-5 relative bar; about twice the throughput on large glimpses) */
 } apg_image_cfg;
 
 /* Engine-owned persistent device buffers.  Views stay valid until apg_image_destroy; contents are

@@ -28,19 +28,35 @@ def _np(x):
     return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
 
 
+BLENDS = ["float64", "float32"]
+
+
+def _assert_obs(got, want, key, blend, msg):
+    """blend="float64" (default engine mode): everything bit-exact.  blend="float32" (opt-in fast mode): the resampled
+    pixels must meet the north-star bar for float pixels -- 1e-5 RELATIVE, no absolute slack -- everything else
+    (glimpse position, time step, labels) stays bit-exact."""
+    got, want = _np(got), np.asarray(want)
+    if blend == "float32" and key in ("glimpse", "target_glimpse"):
+        assert got.dtype == want.dtype and got.shape == want.shape, msg
+        assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-5 * np.abs(want)), msg
+    else:
+        assert np.array_equal(got, want), msg
+
+
+@pytest.mark.parametrize("blend", BLENDS)
 @pytest.mark.parametrize("mode", ["numpy", "torch"])
 @pytest.mark.parametrize("name", list(IMAGE_CASES))
-def test_engine_matches_reference_golden(name, mode):
+def test_engine_matches_reference_golden(name, mode, blend):
     import torch
 
     case = IMAGE_CASES[name]
     g = load_golden("image", name)
     imgs, labels = make_bank(case["bank"])
-    env = _engine_for(case, imgs, labels, check_errors="step")
+    env = _engine_for(case, imgs, labels, check_errors="step", blend=blend)
     opts = {"prediction_target": g["reset_target"]} if case["task"] == "loc" else None
     obs, info = env.reset(seed=case["seed"], options=opts)
     for k in obs:
-        assert np.array_equal(_np(obs[k]), g["reset_" + k]), f"reset obs {k}"
+        _assert_obs(obs[k], g["reset_" + k], k, blend, f"reset obs {k}")
     assert np.array_equal(_np(info["index"]), g["reset_index"])
     for s in range(case["steps"]):
         a, p = g["actions"][s], g["preds"][s]
@@ -48,7 +64,7 @@ def test_engine_matches_reference_golden(name, mode):
             a, p = torch.from_numpy(a).cuda(), torch.from_numpy(p).cuda()
         o, r, te, tr, inf = env.step({"action": a, "prediction": p})
         for k in o:
-            assert np.array_equal(_np(o[k]), g["obs_" + k][s]), f"step {s} obs {k}"
+            _assert_obs(o[k], g["obs_" + k][s], k, blend, f"step {s} obs {k}")
         assert np.array_equal(_np(env.state()["pos"]), g["pos64"][s]), f"step {s} float64 position"
         assert np.array_equal(_np(te), g["terminated"][s]) and np.array_equal(_np(tr), g["truncated"][s])
         assert np.array_equal(_np(inf["index"]), g["index"][s])
@@ -116,8 +132,9 @@ def test_engine_matches_oracle_seeded_mnist_2048():
     dict(H=28, W=28, C=3, sensor_size=(5, 5), sensor_scale=1.0),     # unrolled 5x5x3 path
     dict(H=40, W=40, C=1, sensor_size=(10, 10), sensor_scale=1.0),   # unrolled 10x10x1 path
 ])
+@pytest.mark.parametrize("blend", BLENDS)
 @pytest.mark.parametrize("task", ["cls", "loc"])
-def test_engine_matches_oracle_odd_geometries(geom, task):
+def test_engine_matches_oracle_odd_geometries(geom, task, blend):
     """Sensor / image geometries that exercise every code path of the kernel (generic row loop, column chunks,
     wide visited masks, clamped and scaled taps) against the oracle: bit-exact pixels, masks, positions."""
     from oracle.datasets import synthetic_u8_bank
@@ -129,20 +146,21 @@ def test_engine_matches_oracle_odd_geometries(geom, task):
     kw = dict(sensor_size=geom["sensor_size"], sensor_scale=geom["sensor_scale"], step_limit=6, max_step_length=0.5)
     oracle = ImageEnvOracle(imgs, labels, N, task=task, num_classes=K, track_overlay=False, **kw)
     cls = apg.ImageClassificationVectorEnv if task == "cls" else apg.ImageLocalizationVectorEnv
-    env = cls(N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K), **kw), output="numpy")
+    env = cls(N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K), **kw), output="numpy",
+              blend=blend)
     rng = np.random.default_rng(4)
     tgt = rng.uniform(-1, 1, (N, 2)).astype(np.float32) if task == "loc" else None
     oo, _ = oracle.reset(seed=2, explicit_targets=tgt)
     eo, _ = env.reset(seed=2, options={"prediction_target": tgt} if task == "loc" else None)
     for k in oo:
-        assert np.array_equal(eo[k], oo[k]), f"reset obs {k}"
+        _assert_obs(eo[k], oo[k], k, blend, f"reset obs {k}")
     for s in range(16):
         a = (rng.uniform(-1, 1, (N, 2)) * 1.5).astype(np.float32)
         p = rng.standard_normal((N, K if task == "cls" else 2)).astype(np.float32)
         oo, orw, ote, _, oinf = oracle.step(a, p)
         eo, erw, ete, _, einf = env.step({"action": a, "prediction": p})
         for k in oo:
-            assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+            _assert_obs(eo[k], oo[k], k, blend, f"step {s} obs {k}")
         assert np.array_equal(_np(env.state()["pos"]), oracle.pos)
         assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited), f"step {s} visited"
         assert np.array_equal(ete, ote)
