@@ -146,12 +146,16 @@ struct __align__(16) Tap {
 };
 
 struct __align__(16) EnvHdr {  // 16 bytes: the per-environment shared-memory footprint decides blocks per SM
-  unsigned short lead;   // byte offset of the tile's first needed column inside the staged (aligned-down) row
+  unsigned short lead;   // bits 0-3: byte offset of the tile's first needed column inside the staged (aligned-down)
+                         // row; bit 15 (kNonConsec): the row taps are NOT k0, k0+1, ..., k0+S0-1
   unsigned short nrows;  // staged rows
   unsigned short cmin;   // first tap column of the tile
   unsigned short rmin;   // first tap row of the tile
   unsigned colbits[2];   // visited-mask column bits of this glimpse, words 0 and 1 (columns {j0, j0+1} of every tap)
 };
+
+constexpr unsigned kNonConsec = 0x8000u;
+constexpr unsigned kLeadMask = 15u;
 
 // float32 blend (opt-in): pixel -> float32 without the exact-division emulation; the result differs from the reference's
 // float64 blend by a few float32 ulps of the (non-negative) sum, far inside the 1e-5 relative bar.
@@ -240,6 +244,27 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
   float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
   float m1 = 0.0f, m2 = 0.0f;  // LogWrapper metrics of this step
   double neg_loss_d = 0.0;
+  // Everything an ordinary step reads is requested here, back to back, before the first store: the loads below used to
+  // sit behind stores they might alias and cost one memory round trip each (five in a row on the localization path).
+  float2 in_action = make_float2(0.f, 0.f), in_pred2 = make_float2(0.f, 0.f), in_target = make_float2(0.f, 0.f);
+  float in_acc1 = 0.0f, in_acc2 = 0.0f, in_accr = 0.0f;
+  int in_fc = -1, in_lic = -1;
+  if (p.mode == 0) {
+    in_action = reinterpret_cast<const float2*>(p.action)[n];
+    if (p.t_stamp != 0) {
+      in_acc1 = p.acc1[n];
+      in_acc2 = p.acc2[n];
+      in_accr = p.acc_ret[n];
+      if (p.task == APG_TASK_CLASSIFICATION) {
+        in_fc = p.first_correct[n];
+        in_lic = p.last_incorrect[n];
+      }
+    }
+  }
+  if (p.task != APG_TASK_CLASSIFICATION && p.mode != 2) {
+    in_target = reinterpret_cast<const float2*>(p.st_target)[n];
+    in_pred2 = reinterpret_cast<const float2*>(p.pred)[n];
+  }
   if (p.mode == 0) {
     const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
     px = pp.x;
@@ -295,10 +320,9 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
   } else {
     float t0 = 0.f, t1 = 0.f;
     if (p.mode != 2) {
-      const float2 tt = reinterpret_cast<const float2*>(p.st_target)[n];
-      t0 = tt.x;
-      t1 = tt.y;
-      const float2 qq = reinterpret_cast<const float2*>(p.pred)[n];
+      t0 = in_target.x;
+      t1 = in_target.y;
+      const float2 qq = in_pred2;
       if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
       const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
       const float ss = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
@@ -319,8 +343,7 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
   }
   // ---- move (mode 0): overlay stamp of the PRE-move position, then the float64 position update
   if (p.mode == 0) {
-    const float2 aa = reinterpret_cast<const float2*>(p.action)[n];
-    const float a0 = aa.x, a1 = aa.y;
+    const float a0 = in_action.x, a1 = in_action.y;
     if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
     if (p.track) {
       p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
@@ -352,12 +375,11 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
     if (p.done2) p.done2[n] = p.terminated;
     // ---- episode statistics (the *VectorLogWrapper loops): real steps only, cleared by the reset step
     if (p.mode == 0) {
-      const float a1 = __fadd_rn(p.t_stamp == 0 ? 0.0f : p.acc1[n], m1);
-      const float a2 = __fadd_rn(p.t_stamp == 0 ? 0.0f : p.acc2[n], m2);
-      const float ar = __fadd_rn(p.t_stamp == 0 ? 0.0f : p.acc_ret[n], reward_f);
+      const float a1 = __fadd_rn(in_acc1, m1);
+      const float a2 = __fadd_rn(in_acc2, m2);
+      const float ar = __fadd_rn(in_accr, reward_f);
       if (p.task == APG_TASK_CLASSIFICATION) {
-        int fc = p.t_stamp == 0 ? -1 : p.first_correct[n];
-        int lic = p.t_stamp == 0 ? -1 : p.last_incorrect[n];
+        int fc = in_fc, lic = in_lic;
         if (m2 > 0.5f) { if (fc < 0) fc = p.t_stamp; } else lic = p.t_stamp;
         p.first_correct[n] = fc;
         p.last_incorrect[n] = lic;
@@ -388,7 +410,7 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
   Tap* rows = s_taps + el;                 // tap k of this env: rows[k * E]
   Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
   int rmin = 0, rmax = 0, cmin = 0, cmax = 0;
-  unsigned cb0 = 0u, cb1 = 0u;
+  unsigned cb0 = 0u, cb1 = 0u, nonconsec = 0u;
   for (int i = 0; i < p.S0; ++i) {
     const double y = ccy + ((double)i - p.half0) * p.scale;
     if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
@@ -396,6 +418,7 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
     double w;
     tap(y, p.offy, p.H, k, w);
     if (i == 0) rmin = k;
+    if (k - rmin != i) nonconsec = kNonConsec;
     rmax = k + 1;
     if (p.fast) { rows[i * p.E].wf = (float)w; rows[i * p.E].omwf = (float)(1.0 - w); }
     else rows[i * p.E].w = w;
@@ -422,7 +445,7 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
   int span = (cmax + 1) * p.C * ES - start;                          // bytes needed from `start`
   span = min((span + 15) & ~15, min(row_bytes - start, p.pitch));
   EnvHdr h;
-  h.lead = (unsigned short)lead; h.cmin = (unsigned short)cmin; h.rmin = (unsigned short)rmin;
+  h.lead = (unsigned short)(lead | nonconsec); h.cmin = (unsigned short)cmin; h.rmin = (unsigned short)rmin;
   h.nrows = (unsigned short)nrows;
   h.colbits[0] = cb0; h.colbits[1] = cb1;
   s_hdr[el] = h;
@@ -433,6 +456,55 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
     for (int b = 0; b < span; b += 16) __pipeline_memcpy_async(dst + b, src + b, 16);
     src += row_bytes;
     dst += p.pitch;
+  }
+}
+
+// ---- consecutive tap rows (the common case: sensor_scale == 1 away from rounding accidents) ---------------------------
+// Row tap i reads tile rows i and i+1, so the bottom pixels of one sensor row are the top pixels of the next and each
+// tile row is loaded and converted exactly once, with no tap-index compare in the loop.  `colp` points at tile row 0.
+template <typename BankT, int CT>
+__device__ __forceinline__ void blend_column_consec(const BankT* __restrict__ colp, const Tap* __restrict__ tp,
+                                                    int tap_step, int pitch_e, int c_rt, int n_rows, double wx, double omx,
+                                                    float* __restrict__ out, int out_step, bool store_ok) {
+  const int C = CT ? CT : c_rt;
+  double p00 = px_to_f64(colp[0]), p01 = px_to_f64(colp[C]);
+  int o = 0;
+  for (int i = 0; i < n_rows; ++i, tp += tap_step, o += out_step) {
+    colp += pitch_e;
+    const double p10 = px_to_f64(colp[0]), p11 = px_to_f64(colp[C]);
+    const double wy = tp->w, omy = 1.0 - wy;
+    double acc = p00 * (omy * omx);  // same four terms, same order as blend_column
+    acc = acc + p01 * (omy * wx);
+    acc = acc + p10 * (wy * omx);
+    acc = acc + p11 * (wy * wx);
+    const float v = (sizeof(BankT) == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
+    if (store_ok) out[o] = v;
+    p00 = p10;
+    p01 = p11;
+  }
+}
+
+// float32 blend, consecutive rows: separable form -- one horizontal blend per tile row, one vertical blend per sensor
+// row; the uint8 scale 1/255 is folded into the column weights.  Error: a few float32 ulps of a non-negative sum.
+__device__ __forceinline__ float px_raw_f32(unsigned char u) { return (float)u; }
+__device__ __forceinline__ float px_raw_f32(float v) { return v; }
+
+template <typename BankT, int CT>
+__device__ __forceinline__ void blend_column_consec_f32(const BankT* __restrict__ colp, const Tap* __restrict__ tp,
+                                                        int tap_step, int pitch_e, int c_rt, int n_rows, float wx,
+                                                        float omx, float* __restrict__ out, int out_step, bool store_ok) {
+  const int C = CT ? CT : c_rt;
+  const float unit = (sizeof(BankT) == 1) ? 0.003921568859368563f : 1.0f;
+  const float sx0 = __fmul_rn(omx, unit), sx1 = __fmul_rn(wx, unit);
+  float hp = __fmaf_rn(px_raw_f32(colp[C]), sx1, __fmul_rn(px_raw_f32(colp[0]), sx0));
+  int o = 0;
+  for (int i = 0; i < n_rows; ++i, tp += tap_step, o += out_step) {
+    colp += pitch_e;
+    const float h = __fmaf_rn(px_raw_f32(colp[C]), sx1, __fmul_rn(px_raw_f32(colp[0]), sx0));
+    const float2 wq = *reinterpret_cast<const float2*>(tp);  // (w, 1 - w)
+    const float v = __saturatef(__fmaf_rn(h, wq.x, __fmul_rn(hp, wq.y)));
+    if (store_ok) out[o] = v;
+    hp = h;
   }
 }
 
@@ -486,17 +558,19 @@ __device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid,
                                             const EnvCtr* s_ctr, Tap* s_taps, unsigned char* s_tile) {
   constexpr int ES = (int)sizeof(BankT);
   // copies first (longest latency): item = (environment, tile row, 16-byte chunk)
+  // (integer divisions by block-uniform divisors: (q + 0.5) * (1 / d) truncates to q / d exactly for q < 2^16)
   const int nch = p.pitch >> 4;
   const int per_env = p.tile_rows * nch;
+  const float inv_per_env = __frcp_rn((float)per_env), inv_nch = __frcp_rn((float)nch), inv_E = __frcp_rn((float)p.E);
   for (int q = tid; q < nE * per_env; q += nthreads) {
-    const int el = q / per_env;
+    const int el = (int)(((float)q + 0.5f) * inv_per_env);
     const int rem = q - el * per_env;
-    const int r = rem / nch;
+    const int r = (int)(((float)rem + 0.5f) * inv_nch);
     const int b = (rem - r * nch) << 4;
     const EnvHdr h = s_hdr[el];
     const EnvCtr c = s_ctr[el];
     if (r < (int)h.nrows && b < c.span) {
-      const int start = (int)h.cmin * p.C * ES - (int)h.lead;
+      const int start = (int)h.cmin * p.C * ES - (int)(h.lead & kLeadMask);
       const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bank) + (long long)c.idx * p.H * p.bank_pitch +
                                  (long long)((int)h.rmin + r) * p.bank_pitch + start + b;
       __pipeline_memcpy_async(s_tile + (size_t)el * p.tile_bytes + r * p.pitch + b, src, 16);
@@ -505,7 +579,7 @@ __device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid,
   // taps: item = (tap, environment), environment fastest (conflict-free shared-memory stores)
   const int n_taps = p.S0 + p.S1;
   for (int q = tid; q < n_taps * p.E; q += nthreads) {
-    const int t = q / p.E;
+    const int t = (int)(((float)q + 0.5f) * inv_E);
     const int el = q - t * p.E;
     if (el >= nE) continue;
     const EnvCtr c = s_ctr[el];
@@ -514,6 +588,7 @@ __device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid,
     if (t < p.S0) {
       tap(c.ccy + ((double)t - p.half0) * p.scale, p.offy, p.H, k, w);
       k -= (int)s_hdr[el].rmin;
+      if (k != t) atomicOr(reinterpret_cast<unsigned*>(&s_hdr[el]), kNonConsec);  // `lead` is the low half of word 0
     } else {
       tap(c.ccx + ((double)(t - p.S0) - p.half1) * p.scale, p.offx, p.W, k, w);
       unsigned b0 = 0u, b1 = 0u;
@@ -568,10 +643,26 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
     const Tap ct = cols[min(j, p.S1 - 1) * p.E];
     const double wx = ct.w, omx = 1.0 - ct.w;
     // lanes without a column (or a row) run the same loads on valid addresses and skip the store
-    const BankT* colp = reinterpret_cast<const BankT*>(tile + h.lead) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
+    const BankT* colp =
+        reinterpret_cast<const BankT*>(tile + (h.lead & kLeadMask)) + ((ct.k - h.cmin) * p.C + (col_ok ? c : 0));
     float* outp = out + first * G + (col_ok ? jc : 0);
     const Tap* tp = rows + first * p.E;
-    if (p.fast) {
+    if (kind >= 0 && !(h.lead & kNonConsec)) {  // warp-uniform: consecutive tap rows, one sensor row per pass
+      if (p.fast) {
+        const float wxf = ct.wf, omxf = ct.omwf;
+        if (kind == 3)
+          blend_column_consec_f32<BankT, 3>(colp, tp, p.E, pitch_e, 3, n_rows, wxf, omxf, outp, G, col_ok);
+        else if (kind == 1)
+          blend_column_consec_f32<BankT, 1>(colp, tp, p.E, pitch_e, 1, n_rows, wxf, omxf, outp, G, col_ok);
+        else
+          blend_column_consec_f32<BankT, 0>(colp, tp, p.E, pitch_e, p.C, n_rows, wxf, omxf, outp, G, col_ok);
+      } else if (kind == 3)
+        blend_column_consec<BankT, 3>(colp, tp, p.E, pitch_e, 3, n_rows, wx, omx, outp, G, col_ok);
+      else if (kind == 1)
+        blend_column_consec<BankT, 1>(colp, tp, p.E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
+      else
+        blend_column_consec<BankT, 0>(colp, tp, p.E, pitch_e, p.C, n_rows, wx, omx, outp, G, col_ok);
+    } else if (p.fast) {
       const float wxf = ct.wf, omxf = ct.omwf;
       if (kind == 3)
         blend_column_f32<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wxf, omxf, outp, G, col_ok);
@@ -602,7 +693,7 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
     for (int w = 0; w < p.words; ++w) {
       unsigned bits;
       if (w < 2) {
-        bits = h.colbits[w];
+        bits = w == 0 ? h.colbits[0] : h.colbits[1];
       } else {  // images wider than 64 px
         unsigned my = 0u;
         for (int jj = lane; jj < p.S1; jj += 32) {
@@ -624,7 +715,7 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
 }
 
 template <typename BankT>
-__global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p) {
+__global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvHdr* s_hdr = reinterpret_cast<EnvHdr*>(smem_raw);
   Tap* s_taps = reinterpret_cast<Tap*>(smem_raw + (size_t)p.E * sizeof(EnvHdr));
@@ -687,13 +778,15 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
         const EnvHdr h = s_hdr[el];
         const Tap* rows = s_taps + el;
         const Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
-        const BankT* tile = reinterpret_cast<const BankT*>(s_tile + (size_t)el * p.tile_bytes + h.lead);
+        const BankT* tile = reinterpret_cast<const BankT*>(s_tile + (size_t)el * p.tile_bytes + (h.lead & kLeadMask));
         const int pitch_e = p.pitch / ES;
         float* o = s_out + (size_t)el * Pp;
         for (int j = sub; j < p.S1; j += tb) {
           const Tap ct = cols[j * p.E];
           const BankT* colp = tile + (ct.k - h.cmin) * p.C;
           for (int c = 0; c < p.C; ++c) {
+            // (no consecutive-row variant here: the flag differs between the threads of a warp, e.g. at the image
+            //  border, and both variants would run one after the other)
             if (p.fast)
               blend_column_f32<BankT, 0, true>(colp + c, rows, p.E, pitch_e, p.C, p.S0, ct.wf, ct.omwf, o + j * p.C + c,
                                                p.S1 * p.C, true);
@@ -709,7 +802,7 @@ __global__ void __launch_bounds__(kThreads) image_step_kernel(const ImgParams p)
           for (int w = 0; w < p.words; ++w) {
             unsigned bits = 0u;
             if (w < 2) {
-              bits = h.colbits[w];
+              bits = w == 0 ? h.colbits[0] : h.colbits[1];
             } else {
               for (int jj = 0; jj < p.S1; ++jj) {
                 const int j0 = cols[jj * p.E].k;
