@@ -41,7 +41,8 @@ struct ImgParams {
   int tile_rows;     // staged rows per environment
   int tile_bytes;    // pitch * tile_rows
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
-  int split;         // warp path: phase A split into per-env scalars (one thread) + taps / staging (all threads)
+  int ctr_off;       // byte offset of the EnvCtr array in dynamic shared memory (split phase A)
+  int split;         //  phase A split into per-env scalars (one thread) + taps / staging (all threads)
   int fast;          // 1: float32 blend (within the 1e-5 bar), 0: the reference's float64 blend (bit-exact)
   int tb;            // thread-blend path: threads that share one environment's sensor columns
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
@@ -236,57 +237,90 @@ __device__ __forceinline__ void blend_column(const BankT* __restrict__ colp, con
 //      from the tile (LDS.U8), with one sensor row per pass the bottom taps of row i are the top taps of row i+1;
 //      the blend is the reference's 4-term float64 sum in the same order (bit-exact pixels); each output row is one
 //      contiguous run of stores.  The visited bitmask rows of the environment are updated by the warp.
-// Per-environment scalar work of one step (thread = environment): move, loss, reward, flags, overlay stamp, episode
-// statistics.  Leaves the float64 glimpse position (px, py), the target centre (tcx, tcy; localization reset steps)
-// and the bank index behind.
-__device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s_stats, bool ep_end, double& px, double& py,
-                                            double& tcx, double& tcy, int& idx, unsigned& err) {
+// The per-environment scalar work of one step is two INDEPENDENT chains with disjoint state, so that two threads can run
+// them side by side (and neither waits for the other's memory round trips):
+//   env_move   position state: pre-move overlay stamp, float64 position update, bank index; leaves the glimpse position
+//              (px, py), the target centre (tcx, tcy; localization reset steps) and the bank index behind -- everything
+//              the taps / staging need;
+//   env_loss   labels / targets, loss, reward, flags, overlay colour, episode statistics.
+// Both read the (read-only) action; env_move alone touches pos / st_idx, env_loss alone st_label / st_target / acc*.
+__device__ __forceinline__ void env_move(const ImgParams& p, int n, double& px, double& py, double& tcx, double& tcy,
+                                         int& idx, unsigned& err) {
+  if (p.mode == 0) {
+    const float2 aa = reinterpret_cast<const float2*>(p.action)[n];
+    const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
+    idx = p.st_idx[n];
+    px = pp.x;
+    py = pp.y;
+    const float a0 = aa.x, a1 = aa.y;
+    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
+    if (p.track) {  // overlay stamp of the PRE-move position
+      p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
+      p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
+    }
+    const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
+    float q0 = a0, q1 = a1;
+    if (m > 1.0f) {
+      const float den = fmaxf(m, 1.0f);
+      q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
+      q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
+    }
+    px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
+    py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
+  } else {
+    const long long ni = p.new_idx[n];
+    const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[n];
+    idx = (int)ni;
+    px = pp.x;
+    py = pp.y;
+    p.st_idx[n] = idx;
+    p.index[n] = ni;
+    if (p.task != APG_TASK_CLASSIFICATION) {
+      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
+      tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
+      tcy = (double)nt.y * p.lim_y;
+    }
+  }
+  reinterpret_cast<double2*>(p.pos)[n] = make_double2(px, py);
+  reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
+}
+
+__device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_stats, bool ep_end, unsigned& err) {
   float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
   float m1 = 0.0f, m2 = 0.0f;  // LogWrapper metrics of this step
   double neg_loss_d = 0.0;
-  // Everything an ordinary step reads is requested here, back to back, before the first store: the loads below used to
-  // sit behind stores they might alias and cost one memory round trip each (five in a row on the localization path).
+  const bool cls = p.task == APG_TASK_CLASSIFICATION;
+  // Everything an ordinary step reads is requested here, back to back, before the first store: loads that sit behind
+  // stores they might alias cost one memory round trip each.
   float2 in_action = make_float2(0.f, 0.f), in_pred2 = make_float2(0.f, 0.f), in_target = make_float2(0.f, 0.f);
-  float in_acc1 = 0.0f, in_acc2 = 0.0f, in_accr = 0.0f;
-  int in_fc = -1, in_lic = -1;
+  float in_acc1 = 0.0f, in_acc2 = 0.0f, in_accr = 0.0f, x_first = 0.0f, x_last = 0.0f;
+  int in_fc = -1, in_lic = -1, label = 0;
   if (p.mode == 0) {
     in_action = reinterpret_cast<const float2*>(p.action)[n];
     if (p.t_stamp != 0) {
       in_acc1 = p.acc1[n];
       in_acc2 = p.acc2[n];
       in_accr = p.acc_ret[n];
-      if (p.task == APG_TASK_CLASSIFICATION) {
+      if (cls) {
         in_fc = p.first_correct[n];
         in_lic = p.last_incorrect[n];
       }
     }
+    if (cls) label = p.st_label[n];
   }
-  if (p.task != APG_TASK_CLASSIFICATION && p.mode != 2) {
+  if (cls && p.mode != 2) {  // pulls the environment's logits into L1 with the other inputs
+    x_first = p.pred[(size_t)n * p.K];
+    x_last = p.pred[(size_t)n * p.K + p.K - 1];
+  }
+  if (!cls && p.mode != 2) {
     in_target = reinterpret_cast<const float2*>(p.st_target)[n];
     in_pred2 = reinterpret_cast<const float2*>(p.pred)[n];
   }
-  if (p.mode == 0) {
-    const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
-    px = pp.x;
-    py = pp.y;
-    idx = p.st_idx[n];
-  } else {
-    const long long ni = p.new_idx[n];
-    idx = (int)ni;
-    const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[n];
-    px = pp.x;
-    py = pp.y;
-    p.st_idx[n] = idx;
-    p.index[n] = ni;
-  }
   // ---- labels / targets and the loss (the reset step still charges a loss)
-  if (p.task == APG_TASK_CLASSIFICATION) {
-    int label;
+  if (cls) {
     unsigned char inv = 0;
-    if (p.mode == 0) {
-      label = p.st_label[n];
-    } else {
-      label = p.bank_labels[idx];
+    if (p.mode != 0) {
+      label = p.bank_labels[(int)p.new_idx[n]];
       if (p.invert) {
         inv = p.new_inv[n];
         if (inv) label = p.K - label - 1;
@@ -297,9 +331,9 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
     p.target_label[n] = label;
     if (p.mode != 2) {
       const float* x = p.pred + (size_t)n * p.K;
-      float mx = -INFINITY;
-      bool has_nan = false;
-      for (int k = 0; k < p.K; ++k) {
+      float mx = fmaxf(x_first, x_last);
+      bool has_nan = isnan(x_first) || isnan(x_last);
+      for (int k = 1; k < p.K - 1; ++k) {
         const float v = x[k];
         has_nan |= isnan(v);
         mx = fmaxf(mx, v);
@@ -318,10 +352,8 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
       m2 = (pq > p.inv_k) ? 1.0f : 0.0f;  // accuracy (:166-168)
     }
   } else {
-    float t0 = 0.f, t1 = 0.f;
     if (p.mode != 2) {
-      t0 = in_target.x;
-      t1 = in_target.y;
+      const float t0 = in_target.x, t1 = in_target.y;
       const float2 qq = in_pred2;
       if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
       const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
@@ -337,36 +369,19 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
       const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
       reinterpret_cast<float2*>(p.st_target)[n] = nt;
       if (p.mode == 2) reinterpret_cast<float2*>(p.target_xy)[n] = nt;
-      tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
-      tcy = (double)nt.y * p.lim_y;
     }
   }
-  // ---- move (mode 0): overlay stamp of the PRE-move position, then the float64 position update
   if (p.mode == 0) {
     const float a0 = in_action.x, a1 = in_action.y;
-    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
-    if (p.track) {
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
-      p.stamp_q[(size_t)p.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
-    }
+    if (p.track) p.stamp_q[(size_t)p.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
     const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
-    float q0 = a0, q1 = a1;
-    if (m > 1.0f) {
-      const float den = fmaxf(m, 1.0f);
-      q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
-      q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
-    }
-    px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
-    py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
     base = __fmul_rn(-m, 1e-3f);
   }
-  reinterpret_cast<double2*>(p.pos)[n] = make_double2(px, py);
   if (p.mode != 2) {
     float reward_f;
     // classification: float32 base - float64 loss -> float64; localization stays float32 except on the reset
     // step, whose base reward is np.zeros(N) (float64)
-    if (p.task == APG_TASK_CLASSIFICATION) reward_f = (float)((double)base + neg_loss_d);
+    if (cls) reward_f = (float)((double)base + neg_loss_d);
     else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
     p.reward[n] = reward_f;
     p.base_reward[n] = base;
@@ -378,7 +393,7 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
       const float a1 = __fadd_rn(in_acc1, m1);
       const float a2 = __fadd_rn(in_acc2, m2);
       const float ar = __fadd_rn(in_accr, reward_f);
-      if (p.task == APG_TASK_CLASSIFICATION) {
+      if (cls) {
         int fc = in_fc, lic = in_lic;
         if (m2 > 0.5f) { if (fc < 0) fc = p.t_stamp; } else lic = p.t_stamp;
         p.first_correct[n] = fc;
@@ -397,7 +412,6 @@ __device__ __forceinline__ void env_scalars(const ImgParams& p, int n, double* s
   }
   p.terminated_out[n] = p.terminated;
   p.truncated_out[n] = 0;
-  reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
   p.time_step[n] = p.time_obs;
 }
 
@@ -741,25 +755,41 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
   for (int set = 0; set < n_sets; ++set) {
     // ------------------------------------------------------------------ phase A: thread = environment
     if (p.split) {
-      EnvCtr* s_ctr = reinterpret_cast<EnvCtr*>(s_tile + (size_t)p.E * p.tile_bytes);
-      for (int el = tid; el < nE; el += blockDim.x) {
+      EnvCtr* s_ctr = reinterpret_cast<EnvCtr*>(smem_raw + p.ctr_off);
+      if (tid < nE) {  // E <= blockDim
         unsigned err = 0;
-        if (set == 0) env_scalars(p, env0 + el, s_stats, ep_end, px, py, tcx, tcy, idx, err);
-        stage_head<BankT>(p, el, s_hdr, s_ctr, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx, err);
+        if (set == 0) env_move(p, env0 + tid, px, py, tcx, tcy, idx, err);
+        stage_head<BankT>(p, tid, s_hdr, s_ctr, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx, err);
         if (err) atomicOr(p.err, err);
       }
       __syncthreads();
       stage_block<BankT>(p, nE, tid, blockDim.x, s_hdr, s_ctr, s_taps, s_tile);
-    } else {
-      for (int el = tid; el < nE; el += blockDim.x) {  // one iteration: E <= blockDim
+      __pipeline_commit();
+      // loss / reward / statistics by the block's LAST threads while the copies are in flight: nothing in the block
+      // depends on them before the final barrier
+      const int el = tid - ((int)blockDim.x - p.E);
+      if (set == 0 && el >= 0 && el < nE) {
         unsigned err = 0;
-        if (set == 0) env_scalars(p, env0 + el, s_stats, ep_end, px, py, tcx, tcy, idx, err);
-        stage_env<BankT>(p, el, s_hdr, s_taps, s_tile, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx,
-                         err);
+        env_loss(p, env0 + el, s_stats, ep_end, err);
         if (err) atomicOr(p.err, err);
       }
+    } else {
+      // threads [0, E): position + taps + staging; threads [E, 2E) (when the block has them): loss / reward /
+      // statistics, side by side with the first group
+      const int role = tid / p.E, el = tid - role * p.E;
+      const int loss_role = ((int)blockDim.x >= 2 * p.E) ? 1 : 0;
+      if (el < nE && role <= loss_role) {
+        unsigned err = 0;
+        if (role == 0) {
+          if (set == 0) env_move(p, env0 + el, px, py, tcx, tcy, idx, err);
+          stage_env<BankT>(p, el, s_hdr, s_taps, s_tile, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy,
+                           idx, err);
+        }
+        if (role == loss_role && set == 0) env_loss(p, env0 + el, s_stats, ep_end, err);
+        if (err) atomicOr(p.err, err);
+      }
+      __pipeline_commit();
     }
-    __pipeline_commit();
     __pipeline_wait_prior(0);
     __syncthreads();
     if (ep_end && set == 0 && tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
@@ -824,11 +854,10 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
       __syncthreads();
       float* out_blk = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
       const int total = nE * p.P;
-      int el_c = tid / p.P, off_c = tid - el_c * p.P;  // (environment, float) of flat index q, advanced incrementally
+      const float inv_P = __frcp_rn((float)p.P);  // q / P == trunc((q + 0.5) * (1 / P)) for q < 2^16
       for (int q = tid; q < total; q += blockDim.x) {
-        out_blk[q] = s_out[el_c * Pp + off_c];
-        off_c += blockDim.x;
-        while (off_c >= p.P) { off_c -= p.P; ++el_c; }
+        const int el_c = (int)(((float)q + 0.5f) * inv_P);
+        out_blk[q] = s_out[el_c * Pp + (q - el_c * p.P)];
       }
       if (set + 1 < n_sets) __syncthreads();
       continue;
@@ -887,7 +916,10 @@ __global__ void __launch_bounds__(kPipeThreads) image_step_pipelined_kernel(cons
         const int nE = min(p.E, p.N - env0);
         if (lane < nE) {
           unsigned err = 0;
-          if (prod_set == 0) env_scalars(p, env0 + lane, s_stats, ep_end, px, py, tcx, tcy, idx, err);
+          if (prod_set == 0) {
+            env_move(p, env0 + lane, px, py, tcx, tcy, idx, err);
+            env_loss(p, env0 + lane, s_stats, ep_end, err);
+          }
           stage_env<BankT>(p, lane, reinterpret_cast<EnvHdr*>(st_p), reinterpret_cast<Tap*>(st_p + hdr_bytes),
                            st_p + hdr_bytes + taps_bytes, prod_set == 0 ? px * p.lim_x : tcx,
                            prod_set == 0 ? py * p.lim_y : tcy, idx, err);
@@ -926,7 +958,7 @@ struct apg_image_env {
   cudaStream_t stream = nullptr;
   int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
-  int split = 0;
+  int split = 0, ctr_off = 0;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -1009,7 +1041,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.ctr_off = e->ctr_off; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -1194,6 +1226,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       e->tb = cfg->sensor_w >= 2 ? 2 : 1;
       if (const char* ov = getenv("APG_IMG_TB")) { const int v = atoi(ov); if (v >= 1 && v <= 4) e->tb = v; }
       e->threads = E * e->tb;
+      if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) ? 1 : 0;
     } else {
       // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
       // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
@@ -1203,7 +1236,6 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       e->threads = kThreads;
       e->split = 1;
       if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) ? 1 : 0;
-      if (e->split) per_env += sizeof(EnvCtr);
       if (const char* ov = getenv("APG_IMG_THREADS")) {
         const int v = atoi(ov);
         if (v >= 32 && v <= kThreads && v % 32 == 0) e->threads = v;
@@ -1216,6 +1248,8 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     }
     E = E >= 8 ? (E & ~7) : (E >= 4 ? 4 : (E >= 2 ? 2 : 1));
     e->E = E;
+    e->ctr_off = (int)(per_env * E);
+    if (e->split) per_env += sizeof(EnvCtr);
     e->smem = per_env * E;
     if (e->smem > 200 * 1024) {
       delete e;
