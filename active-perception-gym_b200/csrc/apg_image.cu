@@ -31,6 +31,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kThreadBlendMaxP = 96;  // glimpses up to this many floats are blended by one or two threads per env
 constexpr int kMaxK = 4096;
 
 struct ImgParams {
@@ -638,6 +639,34 @@ __device__ __forceinline__ WarpLane warp_lane(const ImgParams& p, int lane) {
   return L;
 }
 
+// Rare path of the warp-per-environment blend (non-consecutive tap rows, or several sensor rows per pass): kept out of
+// line so that the geometry-specialised kernels do not unroll it.
+template <typename BankT>
+__device__ __noinline__ void blend_column_any(int fast, int kind, const BankT* colp, const Tap* tp, int E, int pitch_e, int C,
+                                              int R, int G, int S0, int r_sub, int n_rows, Tap ct, float* outp, bool col_ok) {
+  if (fast) {
+    const float wxf = ct.wf, omxf = ct.omwf;
+    if (kind == 3)
+      blend_column_f32<BankT, 3, true>(colp, tp, E, pitch_e, 3, n_rows, wxf, omxf, outp, G, col_ok);
+    else if (kind == 1)
+      blend_column_f32<BankT, 1, true>(colp, tp, E, pitch_e, 1, n_rows, wxf, omxf, outp, G, col_ok);
+    else if (kind == 0)
+      blend_column_f32<BankT, 0, true>(colp, tp, E, pitch_e, C, n_rows, wxf, omxf, outp, G, col_ok);
+    else
+      blend_column_f32<BankT, 0, false>(colp, tp, R * E, pitch_e, C, n_rows, wxf, omxf, outp, R * G, col_ok && r_sub < S0);
+  } else {
+    const double wx = ct.w, omx = 1.0 - ct.w;
+    if (kind == 3)
+      blend_column<BankT, 3, true>(colp, tp, E, pitch_e, 3, n_rows, wx, omx, outp, G, col_ok);
+    else if (kind == 1)
+      blend_column<BankT, 1, true>(colp, tp, E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
+    else if (kind == 0)
+      blend_column<BankT, 0, true>(colp, tp, E, pitch_e, C, n_rows, wx, omx, outp, G, col_ok);
+    else
+      blend_column<BankT, 0, false>(colp, tp, R * E, pitch_e, C, n_rows, wx, omx, outp, R * G, col_ok && r_sub < S0);
+  }
+}
+
 // Blend of one environment's glimpse by one warp from its staged tile, plus its visited-mask update (set 0).
 template <typename BankT>
 __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLane& L, int lane, int el, int n, int set,
@@ -676,26 +705,9 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
         blend_column_consec<BankT, 1>(colp, tp, p.E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
       else
         blend_column_consec<BankT, 0>(colp, tp, p.E, pitch_e, p.C, n_rows, wx, omx, outp, G, col_ok);
-    } else if (p.fast) {
-      const float wxf = ct.wf, omxf = ct.omwf;
-      if (kind == 3)
-        blend_column_f32<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wxf, omxf, outp, G, col_ok);
-      else if (kind == 1)
-        blend_column_f32<BankT, 1, true>(colp, tp, p.E, pitch_e, 1, n_rows, wxf, omxf, outp, G, col_ok);
-      else if (kind == 0)
-        blend_column_f32<BankT, 0, true>(colp, tp, p.E, pitch_e, p.C, n_rows, wxf, omxf, outp, G, col_ok);
-      else
-        blend_column_f32<BankT, 0, false>(colp, tp, R * p.E, pitch_e, p.C, n_rows, wxf, omxf, outp, R * G,
-                                          col_ok && r_sub < p.S0);
-    } else if (kind == 3)
-      blend_column<BankT, 3, true>(colp, tp, p.E, pitch_e, 3, n_rows, wx, omx, outp, G, col_ok);
-    else if (kind == 1)
-      blend_column<BankT, 1, true>(colp, tp, p.E, pitch_e, 1, n_rows, wx, omx, outp, G, col_ok);
-    else if (kind == 0)
-      blend_column<BankT, 0, true>(colp, tp, p.E, pitch_e, p.C, n_rows, wx, omx, outp, G, col_ok);
-    else
-      blend_column<BankT, 0, false>(colp, tp, R * p.E, pitch_e, p.C, n_rows, wx, omx, outp, R * G,
-                                    col_ok && r_sub < p.S0);
+    } else {
+      blend_column_any<BankT>(p.fast, kind, colp, tp, p.E, pitch_e, p.C, R, G, p.S0, r_sub, n_rows, ct, outp, col_ok);
+    }
   }
   // ---- visited bitmask of the observation glimpse: rows {i0, i0+1} x columns {j0, j0+1}
   if (p.track && set == 0) {
@@ -728,8 +740,14 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
   }
 }
 
-template <typename BankT>
-__global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams p) {
+// S0T/S1T/CT > 0 fix the sensor geometry at compile time (the benchmark shapes 10x10x3 and 5x5x1): row loops unroll, the
+// lane decomposition and every output offset become constants.  <BankT, 0, 0, 0> is the generic kernel.
+template <typename BankT, int S0T, int S1T, int CT>
+__global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams p_in) {
+  ImgParams p = p_in;
+  if (S0T > 0) {
+    p.S0 = S0T; p.S1 = S1T; p.C = CT; p.P = S0T * S1T * CT;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvHdr* s_hdr = reinterpret_cast<EnvHdr*>(smem_raw);
   Tap* s_taps = reinterpret_cast<Tap*>(smem_raw + (size_t)p.E * sizeof(EnvHdr));
@@ -794,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
     __syncthreads();
     if (ep_end && set == 0 && tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
 
-    if (p.thread_blend) {
+    if ((S0T > 0) ? (S0T * S1T * CT <= kThreadBlendMaxP) : (p.thread_blend != 0)) {
       // -------------------------------------------------------------- phase B (small glimpses): thread = environment
       // A 5x5 glimpse is too small to occupy a warp; every thread blends its own environment's window from its tile
       // (no redundant work, no per-environment warp overhead), parks the floats in shared memory with an odd stride
@@ -958,7 +976,7 @@ struct apg_image_env {
   cudaStream_t stream = nullptr;
   int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
-  int split = 0, ctr_off = 0;
+  int split = 0, ctr_off = 0, spec = 0;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -1101,9 +1119,11 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
     else
       image_step_pipelined_kernel<float><<<pgrid, kPipeThreads, e->pipe_smem, e->stream>>>(p);
   } else if (c.bank_dtype == APG_BANK_U8) {
-    image_step_kernel<unsigned char><<<grid, e->threads, e->smem, e->stream>>>(p);
+    if (e->spec == 1) image_step_kernel<unsigned char, 10, 10, 3><<<grid, e->threads, e->smem, e->stream>>>(p);
+    else if (e->spec == 2) image_step_kernel<unsigned char, 5, 5, 1><<<grid, e->threads, e->smem, e->stream>>>(p);
+    else image_step_kernel<unsigned char, 0, 0, 0><<<grid, e->threads, e->smem, e->stream>>>(p);
   } else {
-    image_step_kernel<float><<<grid, e->threads, e->smem, e->stream>>>(p);
+    image_step_kernel<float, 0, 0, 0><<<grid, e->threads, e->smem, e->stream>>>(p);
   }
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
@@ -1216,7 +1236,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     e->tile_rows = span_rows < cfg->height ? span_rows : cfg->height;
     size_t per_env = sizeof(EnvHdr) + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->pitch * e->tile_rows;
     // small glimpses (<= 96 floats, e.g. 5x5x1 / 5x5x3): one thread blends a whole environment
-    e->thread_blend = e->P <= 96 ? 1 : 0;
+    e->thread_blend = e->P <= kThreadBlendMaxP ? 1 : 0;
     if (const char* ov = getenv("APG_IMG_THREAD_BLEND")) e->thread_blend = atoi(ov) ? 1 : 0;
     int E;
     if (e->thread_blend) {
@@ -1325,9 +1345,16 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     }
   }
   if (err == cudaSuccess && e->smem > 48 * 1024) {
-    A(cudaFuncSetAttribute(image_step_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    A(cudaFuncSetAttribute(image_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    A(cudaFuncSetAttribute(image_step_kernel<unsigned char, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    A(cudaFuncSetAttribute(image_step_kernel<unsigned char, 10, 10, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    A(cudaFuncSetAttribute(image_step_kernel<unsigned char, 5, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    A(cudaFuncSetAttribute(image_step_kernel<float, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   }
+  // compile-time geometry for the benchmark shapes
+  if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 10 && cfg->sensor_w == 10 && cfg->channels == 3) e->spec = 1;
+  if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 5 && cfg->sensor_w == 5 && cfg->channels == 1) e->spec = 2;
+  if (const char* ov = getenv("APG_IMG_SPEC")) { if (!atoi(ov)) e->spec = 0; }
+  if (e->thread_blend != (e->P <= kThreadBlendMaxP ? 1 : 0)) e->spec = 0;  // path forced by APG_IMG_THREAD_BLEND
   if (err != cudaSuccess) {
     apg_image_destroy(e);
     return apg::fail(APG_ERR_CUDA, "apg_image_create: allocation failed: %s", cudaGetErrorString(err));
