@@ -529,10 +529,10 @@ __device__ __forceinline__ void blend_column_consec_f32(const BankT* __restrict_
 // samples).  Split: the environment's thread only does the scalars and the tile header (first / last tap per axis);
 // after a barrier ALL threads compute the taps (one tap per work item) and issue the copies (one 16-byte chunk per item,
 // consecutive threads -> consecutive chunks of a row).
-struct __align__(16) EnvCtr {  // sensor centre (pixels), bank image and copy span of one environment
-  double ccx, ccy;
-  int idx, span;
-  int pad[2];
+struct __align__(16) EnvCtr {  // two 16-byte halves: what the tap items read / what the copy items read
+  double ccx, ccy;   // sensor centre (pixels)
+  long long src0;    // byte offset of the tile's first copied byte inside the bank
+  int span, nrows;   // bytes per tile row to copy (multiple of 16), tile rows
 };
 
 template <typename BankT>
@@ -564,7 +564,8 @@ __device__ __forceinline__ void stage_head(const ImgParams& p, int el, EnvHdr* s
   h.colbits[0] = 0u; h.colbits[1] = 0u;  // OR-ed together by the column-tap work items
   s_hdr[el] = h;
   EnvCtr c;
-  c.ccx = ccx; c.ccy = ccy; c.idx = idx; c.span = span; c.pad[0] = c.pad[1] = 0;
+  c.ccx = ccx; c.ccy = ccy; c.span = span; c.nrows = nrows;
+  c.src0 = ((long long)idx * p.H + rmin) * p.bank_pitch + start;
   s_ctr[el] = c;
 }
 
@@ -582,13 +583,11 @@ __device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid,
     const int rem = q - el * per_env;
     const int r = (int)(((float)rem + 0.5f) * inv_nch);
     const int b = (rem - r * nch) << 4;
-    const EnvHdr h = s_hdr[el];
-    const EnvCtr c = s_ctr[el];
-    if (r < (int)h.nrows && b < c.span) {
-      const int start = (int)h.cmin * p.C * ES - (int)(h.lead & kLeadMask);
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bank) + (long long)c.idx * p.H * p.bank_pitch +
-                                 (long long)((int)h.rmin + r) * p.bank_pitch + start + b;
-      __pipeline_memcpy_async(s_tile + (size_t)el * p.tile_bytes + r * p.pitch + b, src, 16);
+    const longlong2 cp = reinterpret_cast<const longlong2*>(s_ctr + el)[1];  // (src0, span | nrows << 32)
+    const int span = (int)(cp.y & 0xffffffffll), nrows = (int)(cp.y >> 32);
+    if (r < nrows && b < span) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.bank) + cp.x + r * p.bank_pitch + b;
+      __pipeline_memcpy_async(s_tile + el * p.tile_bytes + r * p.pitch + b, src, 16);
     }
   }
   // taps: item = (tap, environment), environment fastest (conflict-free shared-memory stores)
@@ -597,15 +596,15 @@ __device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid,
     const int t = (int)(((float)q + 0.5f) * inv_E);
     const int el = q - t * p.E;
     if (el >= nE) continue;
-    const EnvCtr c = s_ctr[el];
+    const double2 c = reinterpret_cast<const double2*>(s_ctr + el)[0];  // (ccx, ccy)
     int k;
     double w;
     if (t < p.S0) {
-      tap(c.ccy + ((double)t - p.half0) * p.scale, p.offy, p.H, k, w);
+      tap(c.y + ((double)t - p.half0) * p.scale, p.offy, p.H, k, w);
       k -= (int)s_hdr[el].rmin;
       if (k != t) atomicOr(reinterpret_cast<unsigned*>(&s_hdr[el]), kNonConsec);  // `lead` is the low half of word 0
     } else {
-      tap(c.ccx + ((double)(t - p.S0) - p.half1) * p.scale, p.offx, p.W, k, w);
+      tap(c.x + ((double)(t - p.S0) - p.half1) * p.scale, p.offx, p.W, k, w);
       unsigned b0 = 0u, b1 = 0u;
       if (k < 32) b0 |= 1u << k; else if (k < 64) b1 |= 1u << (k - 32);
       if (k + 1 < 32) b0 |= 1u << (k + 1); else if (k + 1 < 64) b1 |= 1u << (k - 31);
@@ -716,6 +715,12 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
       for (int q = lane; q < p.H * p.words; q += 32) vm[q] = 0u;
       __syncwarp();
     }
+    if (!(h.lead & kNonConsec) && p.words <= 2 && (int)h.nrows * p.words <= 32) {
+      // consecutive tap rows: the touched rows are rmin .. rmin + nrows - 1; lane = (row, word), one RED per lane
+      const int r = (p.words == 2) ? (lane >> 1) : lane, w = (p.words == 2) ? (lane & 1) : 0;
+      const unsigned bits = w == 0 ? h.colbits[0] : h.colbits[1];
+      if (r < (int)h.nrows && bits) atomicOr(vm + ((int)h.rmin + r) * p.words + w, bits);
+    } else
     for (int w = 0; w < p.words; ++w) {
       unsigned bits;
       if (w < 2) {
