@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_lib", "libapg_b200.so")
+# APG_B200_LIB: developer override (A/B-testing a differently compiled build); the default is the in-tree library
+LIB_PATH = os.environ.get("APG_B200_LIB") or os.path.join(_PKG, "_lib", "libapg_b200.so")
 
 APG_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NEED_PAYLOAD, ERR_NAN_ACTION, ERR_NAN_PRED, ERR_OUT_OF_GRID = range(-1, -8, -1)

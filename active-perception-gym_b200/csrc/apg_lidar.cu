@@ -87,36 +87,20 @@ __device__ __forceinline__ float norm2f(float a, float b) {
   return __fsqrt_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)));
 }
 
-// oracle/lidar_oracle.c: apg_oracle_scan_one -- same arithmetic, written branch-light: the walk state is updated
-// with selects, the rare cases (rays along a grid line, lattice-corner ties, start on a grid line) take side paths.
-__device__ float scan_one(const MapView& m, float posx, float posy, float tx, float ty, int& cellx, int& celly) {
-  const double px = posx, py = posy;
-  const double dx = (double)tx - px, dy = (double)ty - py;
-  const int sx = dx > 0 ? 1 : (dx < 0 ? -1 : 0), sy = dy > 0 ? 1 : (dy < 0 ? -1 : 0);
-  // one IEEE reciprocal per ray and axis; every crossing parameter is (g - p) * inv (oracle/lidar_oracle.c)
-  const double inv_dx = sx != 0 ? __ddiv_rn(1.0, dx) : 0.0, inv_dy = sy != 0 ? __ddiv_rn(1.0, dy) : 0.0;
-  const double fpx = floor(px), fpy = floor(py);
-  const bool px_int = (px == fpx), py_int = (py == fpy);
-  int cx = (int)fpx, cy = (int)fpy;
-  if (px_int && sx < 0) cx -= 1;
-  if (py_int && sy < 0) cy -= 1;
-  const bool nbx = (sx == 0 && px_int), nby = (sy == 0 && py_int);
-  const bool nb_any = nbx || nby;  // the ray runs along a grid line: the cells on its other side touch it too
-#define WALL(X, Y) (is_wall(m, (X), (Y)) || (nb_any && ((nbx && is_wall(m, (X)-1, (Y))) || (nby && is_wall(m, (X), (Y)-1)))))
-  int n_pos = 0, n_zero = 0;
-  bool have_first = false;
-  bool in_iv = WALL(cx, cy);
-  double iv_t0 = 0.0, fex = px, fey = py;
-  if (in_iv) {
-    have_first = true;
-  } else if (px_int || py_int) {  // start point on a grid line: the cells behind it touch the segment at t = 0
-    bool touch = false;
-    const int bx = cx - sx, by = cy - sy;
-    if (px_int && sx != 0) touch |= is_wall(m, bx, cy) || (nby && is_wall(m, bx, cy - 1));
-    if (py_int && sy != 0) touch |= is_wall(m, cx, by) || (nbx && is_wall(m, cx - 1, by));
-    if (px_int && py_int && sx != 0 && sy != 0) touch |= (bool)is_wall(m, bx, by);
-    if (touch) { n_zero = 1; have_first = true; }
-  }
+struct WalkState {
+  int cx, cy, n_pos, n_zero;
+  bool have_first, in_iv;
+  double iv_t0, fex, fey;
+};
+
+// The grid walk of scan_one from the start cell to the end of the segment.  NB = the ray runs along a grid line, so the
+// cells on its other side touch it too (general, rare); NB = false drops those lookups from the loop.
+template <bool NB>
+__device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px, double py, double dx, double dy, int sx,
+                                     int sy, double inv_dx, double inv_dy, bool nbx, bool nby) {
+  int cx = ws.cx, cy = ws.cy, n_pos = ws.n_pos, n_zero = ws.n_zero;
+  bool have_first = ws.have_first, in_iv = ws.in_iv;
+  double iv_t0 = ws.iv_t0, fex = ws.fex, fey = ws.fey;
   const double sxd = (double)sx, syd = (double)sy;
   double gx = (double)(sx > 0 ? cx + 1 : cx), gy = (double)(sy > 0 ? cy + 1 : cy);  // next grid lines (exact integers)
   double tX = sx != 0 ? (gx - px) * inv_dx : INFINITY;
@@ -126,7 +110,8 @@ __device__ float scan_one(const MapView& m, float posx, float posy, float tx, fl
     const double tN = stepx ? tX : tY;
     if (!(tN <= 1.0)) break;  // the segment ends inside the current cell
     const int ncx = cx + (stepx ? sx : 0), ncy = cy + (stepy ? sy : 0);
-    const bool next_wall = WALL(ncx, ncy);
+    bool next_wall = is_wall(m, ncx, ncy);
+    if (NB) next_wall = next_wall || (nbx && is_wall(m, ncx - 1, ncy)) || (nby && is_wall(m, ncx, ncy - 1));
     bool side_wall = false;
     if (stepx && stepy) side_wall = is_wall(m, ncx, cy) || is_wall(m, cx, ncy);  // lattice corner
     const bool opens = !in_iv && next_wall;
@@ -145,11 +130,48 @@ __device__ float scan_one(const MapView& m, float posx, float posy, float tx, fl
     cx = ncx; cy = ncy;
     if (stepx) { gx += sxd; tX = (gx - px) * inv_dx; }
     if (stepy) { gy += syd; tY = (gy - py) * inv_dy; }
-    // positions lie inside the map, so a ray whose current cell is outside has left it for good
-    if (!in_iv && ((unsigned)cx >= (unsigned)m.W || (unsigned)cy >= (unsigned)m.H) && !nb_any) break;
+    // (no early exit for rays that leave the map: cells outside are free, the walk ends with the segment, and the
+    //  per-iteration bounds test cost more than the few iterations it saved -- measured on B200)
   }
   if (in_iv) { if (iv_t0 < 1.0) n_pos++; else n_zero++; }
-#undef WALL
+  ws.n_pos = n_pos; ws.n_zero = n_zero; ws.fex = fex; ws.fey = fey;
+}
+
+// oracle/lidar_oracle.c: apg_oracle_scan_one -- same arithmetic, written branch-light: the walk state is updated
+// with selects, the rare cases (rays along a grid line, lattice-corner ties, start on a grid line) take side paths.
+__device__ float scan_one(const MapView& m, float posx, float posy, float tx, float ty, int& cellx, int& celly) {
+  const double px = posx, py = posy;
+  const double dx = (double)tx - px, dy = (double)ty - py;
+  const int sx = dx > 0 ? 1 : (dx < 0 ? -1 : 0), sy = dy > 0 ? 1 : (dy < 0 ? -1 : 0);
+  // one IEEE reciprocal per ray and axis; every crossing parameter is (g - p) * inv (oracle/lidar_oracle.c)
+  const double inv_dx = sx != 0 ? __ddiv_rn(1.0, dx) : 0.0, inv_dy = sy != 0 ? __ddiv_rn(1.0, dy) : 0.0;
+  const double fpx = floor(px), fpy = floor(py);
+  const bool px_int = (px == fpx), py_int = (py == fpy);
+  int cx = (int)fpx, cy = (int)fpy;
+  if (px_int && sx < 0) cx -= 1;
+  if (py_int && sy < 0) cy -= 1;
+  const bool nbx = (sx == 0 && px_int), nby = (sy == 0 && py_int);
+  const bool nb_any = nbx || nby;  // the ray runs along a grid line: the cells on its other side touch it too
+  WalkState ws;
+  ws.n_pos = 0; ws.n_zero = 0; ws.have_first = false;
+  ws.in_iv = is_wall(m, cx, cy) || (nb_any && ((nbx && is_wall(m, cx - 1, cy)) || (nby && is_wall(m, cx, cy - 1))));
+  ws.iv_t0 = 0.0; ws.fex = px; ws.fey = py;
+  if (ws.in_iv) {
+    ws.have_first = true;
+  } else if (px_int || py_int) {  // start point on a grid line: the cells behind it touch the segment at t = 0
+    bool touch = false;
+    const int bx = cx - sx, by = cy - sy;
+    if (px_int && sx != 0) touch |= is_wall(m, bx, cy) || (nby && is_wall(m, bx, cy - 1));
+    if (py_int && sy != 0) touch |= is_wall(m, cx, by) || (nbx && is_wall(m, cx - 1, by));
+    if (px_int && py_int && sx != 0 && sy != 0) touch |= (bool)is_wall(m, bx, by);
+    if (touch) { ws.n_zero = 1; ws.have_first = true; }
+  }
+  ws.cx = cx; ws.cy = cy;
+  // rays along a grid line (rare) take the general walk; everything else the lean one
+  if (nb_any) walk<true>(m, ws, px, py, dx, dy, sx, sy, inv_dx, inv_dy, nbx, nby);
+  else walk<false>(m, ws, px, py, dx, dy, sx, sy, inv_dx, inv_dy, false, false);
+  const int n_pos = ws.n_pos, n_zero = ws.n_zero;
+  const double fex = ws.fex, fey = ws.fey;
   const float full = norm2f(__fsub_rn(tx, posx), __fsub_rn(ty, posy));
   float dist;
   int kind;
