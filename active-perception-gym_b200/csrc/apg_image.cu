@@ -42,6 +42,7 @@ struct ImgParams {
   int tile_rows;     // staged rows per environment
   int tile_bytes;    // pitch * tile_rows
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
+  int tb_consec;     // thread-blend path: use the consecutive-row variants
   int ctr_off;       // byte offset of the EnvCtr array in dynamic shared memory (split phase A)
   int split;         //  phase A split into per-env scalars (one thread) + taps / staging (all threads)
   int fast;          // 1: float32 blend (within the 1e-5 bar), 0: the reference's float64 blend (bit-exact)
@@ -105,6 +106,19 @@ __device__ __forceinline__ void tap(double coord, double off, int len, int& k_ou
   if ((double)k - off > coord) k -= 1;
   else if ((double)(k + 1) - off <= coord) k += 1;
   k = max(0, min(k, len - 2));
+  k_out = k;
+  w_out = coord - ((double)k - off);
+}
+
+// Row taps of uint8 banks keep the unclamped index len-1 when the coordinate sits exactly on the last grid point (the
+// sensor touches the bottom edge): scipy's clamped tap (len-2, w = 1) and this one (len-1, w = 0) blend the same row
+// with the same products, the other row gets weight +0 (finite uint8 pixels, exact), and the tap rows stay
+// CONSECUTIVE, which is what the fast blend variants need.  Readers of row k+1 must not leave the image.
+__device__ __forceinline__ void tap_row(double coord, double off, int len, bool keep_last, int& k_out, double& w_out) {
+  int k = (int)floor(coord + off);
+  if ((double)k - off > coord) k -= 1;
+  else if ((double)(k + 1) - off <= coord) k += 1;
+  k = max(0, min(k, keep_last ? len - 1 : len - 2));
   k_out = k;
   w_out = coord - ((double)k - off);
 }
@@ -431,10 +445,10 @@ __device__ __forceinline__ void stage_env(const ImgParams& p, int el, EnvHdr* s_
     if (y < -p.offy || y > p.offy) err |= APG_FLAG_OUT_OF_GRID;
     int k;
     double w;
-    tap(y, p.offy, p.H, k, w);
+    tap_row(y, p.offy, p.H, ES == 1, k, w);
     if (i == 0) rmin = k;
     if (k - rmin != i) nonconsec = kNonConsec;
-    rmax = k + 1;
+    rmax = min(k, p.H - 2) + 1;
     if (p.fast) { rows[i * p.E].wf = (float)w; rows[i * p.E].omwf = (float)(1.0 - w); }
     else rows[i * p.E].w = w;
     rows[i * p.E].k = k - rmin;
@@ -600,7 +614,7 @@ __device__ __forceinline__ void stage_block(const ImgParams& p, int nE, int tid,
     int k;
     double w;
     if (t < p.S0) {
-      tap(c.y + ((double)t - p.half0) * p.scale, p.offy, p.H, k, w);
+      tap_row(c.y + ((double)t - p.half0) * p.scale, p.offy, p.H, ES == 1, k, w);
       k -= (int)s_hdr[el].rmin;
       if (k != t) atomicOr(reinterpret_cast<unsigned*>(&s_hdr[el]), kNonConsec);  // `lead` is the low half of word 0
     } else {
@@ -737,7 +751,7 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
       if (bits) {
         for (int rr = lane; rr < 2 * p.S0; rr += 32) {
           const int row = h.rmin + ((rr < p.S0) ? rows[rr * p.E].k : rows[(rr - p.S0) * p.E].k + 1);
-          atomicOr(vm + row * p.words + w, bits);  // no return value -> RED: nothing waits for the old word
+          if (row < p.H) atomicOr(vm + row * p.words + w, bits);  // no return value -> RED: nothing waits for the old word
         }
       }
     }
@@ -832,15 +846,20 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
         const Tap* rows = s_taps + el;
         const Tap* cols = s_taps + (size_t)p.S0 * p.E + el;
         const BankT* tile = reinterpret_cast<const BankT*>(s_tile + (size_t)el * p.tile_bytes + (h.lead & kLeadMask));
+        const bool consec = p.tb_consec && !(h.lead & kNonConsec);  // (nearly) always: see tap_row
         const int pitch_e = p.pitch / ES;
         float* o = s_out + (size_t)el * Pp;
         for (int j = sub; j < p.S1; j += tb) {
           const Tap ct = cols[j * p.E];
           const BankT* colp = tile + (ct.k - h.cmin) * p.C;
           for (int c = 0; c < p.C; ++c) {
-            // (no consecutive-row variant here: the flag differs between the threads of a warp, e.g. at the image
-            //  border, and both variants would run one after the other)
-            if (p.fast)
+            if (consec && p.fast)
+              blend_column_consec_f32<BankT, CT>(colp + c, rows, p.E, pitch_e, p.C, p.S0, ct.wf, ct.omwf,
+                                                 o + j * p.C + c, p.S1 * p.C, true);
+            else if (consec)
+              blend_column_consec<BankT, CT>(colp + c, rows, p.E, pitch_e, p.C, p.S0, ct.w, 1.0 - ct.w, o + j * p.C + c,
+                                             p.S1 * p.C, true);
+            else if (p.fast)
               blend_column_f32<BankT, 0, true>(colp + c, rows, p.E, pitch_e, p.C, p.S0, ct.wf, ct.omwf, o + j * p.C + c,
                                                p.S1 * p.C, true);
             else
@@ -868,7 +887,7 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
             for (int i = 0; i < p.S0; ++i) {
               const int r0 = h.rmin + rows[i * p.E].k;
               if (r0 > last) atomicOr(vm + r0 * p.words + w, bits);
-              if (r0 + 1 > last) atomicOr(vm + (r0 + 1) * p.words + w, bits);
+              if (r0 + 1 > last && r0 + 1 < p.H) atomicOr(vm + (r0 + 1) * p.words + w, bits);
               last = r0 + 1;
             }
           }
@@ -981,7 +1000,7 @@ struct apg_image_env {
   cudaStream_t stream = nullptr;
   int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
-  int split = 0, ctr_off = 0, spec = 0;
+  int split = 0, ctr_off = 0, spec = 0, tile_bytes = 0, tb_consec = 1;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -1064,7 +1083,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->pitch * e->tile_rows; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.ctr_off = e->ctr_off; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.tb_consec = e->tb_consec; p.ctr_off = e->ctr_off; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -1239,7 +1258,10 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     if (pitch > row_bytes) pitch = row_bytes;
     e->pitch = pitch;
     e->tile_rows = span_rows < cfg->height ? span_rows : cfg->height;
-    size_t per_env = sizeof(EnvHdr) + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->pitch * e->tile_rows;
+    // (the row below an environment's last staged row may be read with weight 0, see tap_row: it is the next
+    //  environment's first row, or the `pitch` spare bytes added once behind the last tile)
+    e->tile_bytes = e->pitch * e->tile_rows;
+    size_t per_env = sizeof(EnvHdr) + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->tile_bytes;
     // small glimpses (<= 96 floats, e.g. 5x5x1 / 5x5x3): one thread blends a whole environment
     e->thread_blend = e->P <= kThreadBlendMaxP ? 1 : 0;
     if (const char* ov = getenv("APG_IMG_THREAD_BLEND")) e->thread_blend = atoi(ov) ? 1 : 0;
@@ -1275,7 +1297,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     e->E = E;
     e->ctr_off = (int)(per_env * E);
     if (e->split) per_env += sizeof(EnvCtr);
-    e->smem = per_env * E;
+    e->smem = per_env * E + (size_t)e->pitch;
     if (e->smem > 200 * 1024) {
       delete e;
       return apg::fail(APG_ERR_INVALID, "sensor window too large for the shared-memory tile (%zu bytes)", e->smem);
@@ -1359,6 +1381,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 10 && cfg->sensor_w == 10 && cfg->channels == 3) e->spec = 1;
   if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 5 && cfg->sensor_w == 5 && cfg->channels == 1) e->spec = 2;
   if (const char* ov = getenv("APG_IMG_SPEC")) { if (!atoi(ov)) e->spec = 0; }
+  if (const char* ov = getenv("APG_IMG_TB_CONSEC")) e->tb_consec = atoi(ov) ? 1 : 0;
   if (e->thread_blend != (e->P <= kThreadBlendMaxP ? 1 : 0)) e->spec = 0;  // path forced by APG_IMG_THREAD_BLEND
   if (err != cudaSuccess) {
     apg_image_destroy(e);
