@@ -34,6 +34,8 @@ constexpr int kThreads = 256;
 constexpr int kThreadBlendMaxP = 96;  // glimpses up to this many floats are blended by one or two threads per env
 constexpr int kMaxK = 4096;
 
+struct EnvHdr;
+struct EnvCtr;
 struct ImgParams {
   int N, H, W, C, S0, S1, P, K, task, invert, track, words, T;
   int E;             // environments per block
@@ -42,6 +44,8 @@ struct ImgParams {
   int tile_rows;     // staged rows per environment
   int tile_bytes;    // pitch * tile_rows
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
+  EnvHdr* g_hdr;     // split == 2: tile headers / centres written by image_head_kernel, (n_sets, N)
+  EnvCtr* g_ctr;
   int tb_consec;     // thread-blend path: use the consecutive-row variants
   int ctr_off;       // byte offset of the EnvCtr array in dynamic shared memory (split phase A)
   int split;         //  phase A split into per-env scalars (one thread) + taps / staging (all threads)
@@ -759,6 +763,34 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
   }
 }
 
+// Two-kernel variant of the warp-per-environment path (split == 2): the scalar chains and the tile headers of ALL
+// environments, one thread each.  Inside the blend kernel this work occupied one warp of eight for ~18 % of a block's
+// lifetime (memory round trip + serial float64 taps) with the other seven parked at a barrier; here 10^5 threads hide
+// each other's latency.  The headers travel through L2 (48 bytes per environment and glimpse set).
+template <typename BankT>
+__global__ void __launch_bounds__(256) image_head_kernel(const ImgParams p) {
+  __shared__ double s_stats[6];
+  const bool ep_end = (p.mode == 0) && p.terminated;
+  if (ep_end && threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
+  if (ep_end) __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < p.N) {
+    double px = 0.0, py = 0.0, tcx = 0.0, tcy = 0.0;
+    int idx = 0;
+    unsigned err = 0;
+    env_move(p, n, px, py, tcx, tcy, idx, err);
+    stage_head<BankT>(p, n, p.g_hdr, p.g_ctr, px * p.lim_x, py * p.lim_y, idx, err);
+    if ((p.task == APG_TASK_LOCALIZATION) && (p.mode != 0))
+      stage_head<BankT>(p, n, p.g_hdr + p.N, p.g_ctr + p.N, tcx, tcy, idx, err);
+    env_loss(p, n, s_stats, ep_end, err);
+    if (err) atomicOr(p.err, err);
+  }
+  if (ep_end) {
+    __syncthreads();
+    if (threadIdx.x < 6) atomicAdd(p.stats + threadIdx.x, s_stats[threadIdx.x]);
+  }
+}
+
 // S0T/S1T/CT > 0 fix the sensor geometry at compile time (the benchmark shapes 10x10x3 and 5x5x1): row loops unroll, the
 // lane decomposition and every output offset become constants.  <BankT, 0, 0, 0> is the generic kernel.
 template <typename BankT, int S0T, int S1T, int CT>
@@ -791,7 +823,18 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
 
   for (int set = 0; set < n_sets; ++set) {
     // ------------------------------------------------------------------ phase A: thread = environment
-    if (p.split) {
+    if (p.split == 2) {
+      // the per-environment scalars and the tile headers were computed by image_head_kernel (one thread per
+      // environment over the whole batch): fetch this block's headers, then taps / copies by all threads
+      EnvCtr* s_ctr = reinterpret_cast<EnvCtr*>(smem_raw + p.ctr_off);
+      if (tid < nE) {
+        s_hdr[tid] = p.g_hdr[(size_t)set * p.N + env0 + tid];
+        s_ctr[tid] = p.g_ctr[(size_t)set * p.N + env0 + tid];
+      }
+      __syncthreads();
+      stage_block<BankT>(p, nE, tid, blockDim.x, s_hdr, s_ctr, s_taps, s_tile);
+      __pipeline_commit();
+    } else if (p.split) {
       EnvCtr* s_ctr = reinterpret_cast<EnvCtr*>(smem_raw + p.ctr_off);
       if (tid < nE) {  // E <= blockDim
         unsigned err = 0;
@@ -829,7 +872,7 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
     }
     __pipeline_wait_prior(0);
     __syncthreads();
-    if (ep_end && set == 0 && tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
+    if (ep_end && set == 0 && tid < 6 && p.split != 2) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
 
     if ((S0T > 0) ? (S0T * S1T * CT <= kThreadBlendMaxP) : (p.thread_blend != 0)) {
       // -------------------------------------------------------------- phase B (small glimpses): thread = environment
@@ -1001,6 +1044,8 @@ struct apg_image_env {
   int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
   int split = 0, ctr_off = 0, spec = 0, tile_bytes = 0, tb_consec = 1;
+  void* d_ghdr = nullptr;
+  void* d_gctr = nullptr;
   size_t smem = 0;
   // bank
   void* d_bank = nullptr;
@@ -1083,7 +1128,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.tb_consec = e->tb_consec; p.ctr_off = e->ctr_off; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -1136,6 +1181,12 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   p.inv_k = (float)(1.0 / (double)(c.num_classes > 0 ? c.num_classes : 1));
 
   const int grid = apg::ceil_div(c.num_envs, e->E);
+  if (e->split == 2 && !e->pipelined) {
+    const int hgrid = apg::ceil_div(c.num_envs, 256);
+    if (c.bank_dtype == APG_BANK_U8) image_head_kernel<unsigned char><<<hgrid, 256, 0, e->stream>>>(p);
+    else image_head_kernel<float><<<hgrid, 256, 0, e->stream>>>(p);
+    apg::count_launch();
+  }
   if (e->pipelined) {
     const int pgrid = grid < e->pipe_grid ? grid : e->pipe_grid;
     if (c.bank_dtype == APG_BANK_U8)
@@ -1273,7 +1324,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       e->tb = cfg->sensor_w >= 2 ? 2 : 1;
       if (const char* ov = getenv("APG_IMG_TB")) { const int v = atoi(ov); if (v >= 1 && v <= 4) e->tb = v; }
       e->threads = E * e->tb;
-      if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) ? 1 : 0;
+      if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) == 1 ? 1 : 0;
     } else {
       // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
       // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
@@ -1281,8 +1332,8 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       E = E > 64 ? 64 : E;
       if (per_env > 768 && E > 32) E = 32;
       e->threads = kThreads;
-      e->split = 1;
-      if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) ? 1 : 0;
+      e->split = 2;  // 0: one thread per env does all of phase A; 1: taps / copies by all threads; 2: + head kernel
+      if (const char* ov = getenv("APG_IMG_SPLIT")) { const int v = atoi(ov); if (v >= 0 && v <= 2) e->split = v; }
       if (const char* ov = getenv("APG_IMG_THREADS")) {
         const int v = atoi(ov);
         if (v >= 32 && v <= kThreads && v % 32 == 0) e->threads = v;
@@ -1336,6 +1387,10 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   A(apg::dev_alloc(&e->d_st_label, N));
   A(apg::dev_alloc(&e->d_st_inv, N));
   A(apg::dev_alloc(&e->d_err, 1));
+  if (e->split == 2) {
+    A(cudaMalloc(&e->d_ghdr, 2 * N * sizeof(EnvHdr)));
+    A(cudaMalloc(&e->d_gctr, 2 * N * sizeof(EnvCtr)));
+  }
   A(apg::dev_alloc(&e->d_in_action, N * 2));
   A(apg::dev_alloc(&e->d_in_pred, N * e->pred_width));
   int depth = cfg->payload_ring <= 0 ? APG_PAYLOAD_RING_DEFAULT : cfg->payload_ring;
@@ -1395,6 +1450,8 @@ void apg_image_destroy(apg_image_env* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  if (e->d_ghdr) cudaFree(e->d_ghdr);
+  if (e->d_gctr) cudaFree(e->d_gctr);
   if (e->own_bank) cudaFree(e->d_bank);
   if (e->own_bank) cudaFree(e->d_bank_labels);
   apg::dev_free(e->b.d_glimpse); apg::dev_free(e->b.d_target_glimpse); apg::dev_free(e->b.d_glimpse_pos);
