@@ -419,7 +419,9 @@ def main():
                          "kernel": "lidar_step_kernel" if is_lidar else
                          ["image_step_kernel (warp blend)", "image_step_kernel (thread blend)",
                           "image_step_pipelined_kernel"][lib.apg_image_variant(env._h)], "bytes_per_env_step": w["bytes_per_step"],
-                         "avg_launch_us": avg_launch_s * 1e6},
+                         "avg_launch_us": avg_launch_s * 1e6, "launches_per_step": launches / K,
+                         "note": "achieved = algorithmic bytes of one step / device time of one step; with 2 launches per "
+                                 "step (image_head_kernel + image_step_kernel, warp path) the step time covers both"},
             "episode_stats_allreduce": stats,
         }
         if alt is not None:
