@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "apg_common.h"
+#include "apg_payload.h"
 #include "apg_rng.h"
 
 namespace {
@@ -1077,6 +1078,14 @@ struct apg_image_env {
   // numpy-compatible reset streams (optional): autoreset payloads are drawn by the engine when the ring is empty
   apg::Pcg64 g0{}, g1{}, g2{};
   bool have_streams = false;
+  // device-side payload generation (csrc/apg_payload.cu): the stream states live in d_streams while streams_on_device
+  apg::Pcg64* d_streams = nullptr;
+  apg::Pcg64 h_streams[3];
+  unsigned* d_words = nullptr;
+  unsigned* d_rej = nullptr;
+  size_t words_cap = 0;
+  bool streams_on_device = false;
+  bool host_rng = false;  // APG_IMG_HOST_RNG=1: always draw payloads on the host
   int64_t global_n = 0, env_offset = 0;
   std::vector<int64_t> h_idx;
   std::vector<double> h_pos;
@@ -1210,9 +1219,59 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
 // One autoreset payload from the reference's streams, in the reference's draw order, for the global batch; this
 // shard keeps its slice.  (image_localization.py:153-156 -> dataset_iterator.py:57 -> image_perception_module.py:131-133
 // -> :159-161)
+int streams_to_host(apg_image_env* e) {
+  if (!e->streams_on_device) return APG_OK;
+  APG_CUDA(cudaMemcpyAsync(e->h_streams, e->d_streams, sizeof(e->h_streams), cudaMemcpyDeviceToHost, e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  e->g0 = e->h_streams[0]; e->g1 = e->h_streams[1]; e->g2 = e->h_streams[2];
+  e->streams_on_device = false;
+  return APG_OK;
+}
+
+int streams_to_device(apg_image_env* e) {
+  if (e->streams_on_device) return APG_OK;
+  const size_t need = apg::payload_scratch_words(e->global_n);
+  if (!e->d_streams) {
+    APG_CUDA(cudaMalloc(&e->d_streams, sizeof(e->h_streams)));
+    APG_CUDA(apg::dev_alloc(&e->d_rej, (size_t)apg::kPayloadSlack + 1));
+  }
+  if (need > e->words_cap) {
+    if (e->d_words) cudaFree(e->d_words);
+    e->d_words = nullptr;
+    APG_CUDA(cudaMalloc(&e->d_words, need * sizeof(unsigned)));
+    e->words_cap = need;
+  }
+  APG_CUDA(cudaStreamSynchronize(e->stream));  // h_streams may still feed an earlier upload
+  e->h_streams[0] = e->g0; e->h_streams[1] = e->g1; e->h_streams[2] = e->g2;
+  APG_CUDA(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(e->h_streams), cudaMemcpyHostToDevice, e->stream));
+  e->streams_on_device = true;
+  return APG_OK;
+}
+
 int generate_payload(apg_image_env* e) {
   APG_CHECK(e->have_streams, APG_ERR_NEED_PAYLOAD, "no reset payload queued and no reset streams set");
   APG_CHECK(e->ring_count < (int)e->ring.size(), APG_ERR_STATE, "reset payload ring is full");
+  if (!e->host_rng && apg::payload_device_ok((unsigned long long)e->n_items, e->global_n)) {
+    // drawn on the device, in-stream, bit-identical to the numpy draws below (tests/test_rng_gpu.py)
+    int rc = streams_to_device(e);
+    if (rc != APG_OK) return rc;
+    apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
+    apg::PayloadArgs a{};
+    a.streams = e->d_streams; a.Ng = e->global_n; a.off = e->env_offset; a.N = e->cfg.num_envs;
+    a.M = (unsigned long long)e->n_items; a.loc = e->cfg.task == APG_TASK_LOCALIZATION ? 1 : 0;
+    a.inv = e->cfg.randomly_invert_labels ? 1 : 0;
+    a.d_idx = reinterpret_cast<long long*>(s.d_idx); a.d_pos = s.d_pos; a.d_target = s.d_target; a.d_inv = s.d_inv;
+    a.words = e->d_words; a.rej = e->d_rej;
+    const int n = apg::launch_device_payload(a, e->stream);
+    if (n < 0) return apg::fail(APG_ERR_CUDA, "payload kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
+    apg::count_launch(n);
+    e->ring_count += 1;
+    return APG_OK;
+  }
+  {
+    int rc = streams_to_host(e);
+    if (rc != APG_OK) return rc;
+  }
   const int64_t N = e->cfg.num_envs, Ng = e->global_n, off = e->env_offset;
   const bool loc = e->cfg.task == APG_TASK_LOCALIZATION, inv = e->cfg.randomly_invert_labels != 0;
   e->h_idx.resize(N); e->h_pos.resize(2 * N);
@@ -1437,6 +1496,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 5 && cfg->sensor_w == 5 && cfg->channels == 1) e->spec = 2;
   if (const char* ov = getenv("APG_IMG_SPEC")) { if (!atoi(ov)) e->spec = 0; }
   if (const char* ov = getenv("APG_IMG_TB_CONSEC")) e->tb_consec = atoi(ov) ? 1 : 0;
+  if (const char* ov = getenv("APG_IMG_HOST_RNG")) e->host_rng = atoi(ov) != 0;
   if (e->thread_blend != (e->P <= kThreadBlendMaxP ? 1 : 0)) e->spec = 0;  // path forced by APG_IMG_THREAD_BLEND
   if (err != cudaSuccess) {
     apg_image_destroy(e);
@@ -1450,6 +1510,9 @@ void apg_image_destroy(apg_image_env* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  if (e->d_streams) cudaFree(e->d_streams);
+  if (e->d_words) cudaFree(e->d_words);
+  if (e->d_rej) cudaFree(e->d_rej);
   if (e->d_ghdr) cudaFree(e->d_ghdr);
   if (e->d_gctr) cudaFree(e->d_gctr);
   if (e->own_bank) cudaFree(e->d_bank);
@@ -1567,6 +1630,7 @@ int apg_image_set_streams(apg_image_env* e, const apg_pcg64_state* g0, const apg
   to_internal(g0, e->g0); to_internal(g1, e->g1); to_internal(g2, e->g2);
   e->global_n = global_num_envs; e->env_offset = env_offset;
   e->have_streams = true;
+  e->streams_on_device = false;  // the host copies are the truth until the next device-drawn payload
   return APG_OK;
 }
 
@@ -1574,6 +1638,11 @@ int apg_image_get_streams(apg_image_env* e, apg_pcg64_state* g0, apg_pcg64_state
   APG_CHECK(e && g0 && g1 && g2, APG_ERR_INVALID, "apg_image_get_streams: null argument");
   APG_CHECK(e->have_streams, APG_ERR_STATE, "no reset streams set");
   APG_CHECK(e->ring_count == 0, APG_ERR_STATE, "%d prefetched payloads have already advanced the streams", e->ring_count);
+  {
+    APG_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = streams_to_host(e);
+    if (rc != APG_OK) return rc;
+  }
   from_internal(e->g0, g0); from_internal(e->g1, g1); from_internal(e->g2, g2);
   return APG_OK;
 }

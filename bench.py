@@ -296,13 +296,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # pre-draw the autoreset payloads of warm-up + timed region so the timed region is device-only
+    # warm-up.  Autoreset payloads are NOT staged ahead: the engine draws each one on the device, in-stream, right
+    # before the step that consumes it (numpy-identical streams, csrc/apg_payload.cu), inside the timed region.
     run(0, W)
-    barrier()
-    # the engine draws autoreset payloads itself (numpy-compatible streams); prefetch a ring-full so the timed region
-    # starts with payloads resident.  The LIDAR engine draws its resets on the device, nothing to stage.
-    if not is_lidar:
-        env.queue_autoreset_payloads(64)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -333,7 +329,6 @@ def main():
         env2, _, _ = build_env(a2, rank, world, local_rank)
         env2.reset(seed=0)
         run(0, W, env2)
-        env2.queue_autoreset_payloads(64)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

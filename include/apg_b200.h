@@ -274,6 +274,17 @@ int apg_lidar_sync(apg_lidar_env* env);
  * out[i] receives the result of operation i. */
 int apg_rng_host_stream(uint64_t seed, int32_t n_ops, const int32_t* op, const uint64_t* arg, uint64_t* out);
 
+/* Test hook for the DEVICE generator of the image environments' autoreset payloads (csrc/apg_payload.cu): draws one
+ * payload -- g0.uniform(-1,1,(Ng,2)).astype(f32) [localization], g2.integers(0, n_items, Ng),
+ * g1.integers(0,2,Ng)==1 [invert], g1.uniform(-1,1,(Ng,2)); reference: image_localization.py:153-156,
+ * dataset_iterator.py:57, image_perception_module.py:131-133,159-161 -- on `device`, copies this shard's slice
+ * [env_offset, env_offset + num_envs) to the host arrays and advances the three states exactly as numpy would.
+ * APG_ERR_INVALID when n_items rejects too many Lemire draws for the device path (the engine then draws on the host). */
+int apg_rng_device_payload(int32_t device, apg_pcg64_state* g0, apg_pcg64_state* g1, apg_pcg64_state* g2,
+                           int64_t global_n, int64_t env_offset, int64_t num_envs, uint64_t n_items,
+                           int32_t localization, int32_t invert, int64_t* h_idx, double* h_pos, float* h_target,
+                           uint8_t* h_inv);
+
 /* ------------------------------------------------------------------------------------------------------
  * DLPack export of engine-owned device memory (north_star: PyTorch only sees DLPack tensors).
  * Returns a malloc'ed DLManagedTensor* (DLPack v0.8 layout) whose deleter frees only the descriptor.
