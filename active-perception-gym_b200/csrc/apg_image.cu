@@ -1085,6 +1085,7 @@ struct apg_image_env {
   unsigned* d_rej = nullptr;
   size_t words_cap = 0;
   bool streams_on_device = false;
+  int pp = 0;  // which half of d_streams / d_rej holds the current states / the clean rejection list
   bool host_rng = false;  // APG_IMG_HOST_RNG=1: always draw payloads on the host
   int64_t global_n = 0, env_offset = 0;
   std::vector<int64_t> h_idx;
@@ -1221,7 +1222,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
 // -> :159-161)
 int streams_to_host(apg_image_env* e) {
   if (!e->streams_on_device) return APG_OK;
-  APG_CUDA(cudaMemcpyAsync(e->h_streams, e->d_streams, sizeof(e->h_streams), cudaMemcpyDeviceToHost, e->stream));
+  APG_CUDA(cudaMemcpyAsync(e->h_streams, e->d_streams + 3 * e->pp, sizeof(e->h_streams), cudaMemcpyDeviceToHost, e->stream));
   APG_CUDA(cudaStreamSynchronize(e->stream));
   e->g0 = e->h_streams[0]; e->g1 = e->h_streams[1]; e->g2 = e->h_streams[2];
   e->streams_on_device = false;
@@ -1232,8 +1233,8 @@ int streams_to_device(apg_image_env* e) {
   if (e->streams_on_device) return APG_OK;
   const size_t need = apg::payload_scratch_words(e->global_n);
   if (!e->d_streams) {
-    APG_CUDA(cudaMalloc(&e->d_streams, sizeof(e->h_streams)));
-    APG_CUDA(apg::dev_alloc(&e->d_rej, (size_t)apg::kPayloadSlack + 1));
+    APG_CUDA(cudaMalloc(&e->d_streams, 2 * sizeof(e->h_streams)));
+    APG_CUDA(apg::dev_alloc(&e->d_rej, 2 * ((size_t)apg::kPayloadSlack + 1)));
   }
   if (need > e->words_cap) {
     if (e->d_words) cudaFree(e->d_words);
@@ -1243,7 +1244,7 @@ int streams_to_device(apg_image_env* e) {
   }
   APG_CUDA(cudaStreamSynchronize(e->stream));  // h_streams may still feed an earlier upload
   e->h_streams[0] = e->g0; e->h_streams[1] = e->g1; e->h_streams[2] = e->g2;
-  APG_CUDA(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(e->h_streams), cudaMemcpyHostToDevice, e->stream));
+  APG_CUDA(cudaMemcpyAsync(e->d_streams + 3 * e->pp, e->h_streams, sizeof(e->h_streams), cudaMemcpyHostToDevice, e->stream));
   e->streams_on_device = true;
   return APG_OK;
 }
@@ -1257,11 +1258,14 @@ int generate_payload(apg_image_env* e) {
     if (rc != APG_OK) return rc;
     apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
     apg::PayloadArgs a{};
-    a.streams = e->d_streams; a.Ng = e->global_n; a.off = e->env_offset; a.N = e->cfg.num_envs;
+    a.streams = e->d_streams + 3 * e->pp; a.streams_out = e->d_streams + 3 * (e->pp ^ 1); a.Ng = e->global_n; a.off = e->env_offset; a.N = e->cfg.num_envs;
     a.M = (unsigned long long)e->n_items; a.loc = e->cfg.task == APG_TASK_LOCALIZATION ? 1 : 0;
     a.inv = e->cfg.randomly_invert_labels ? 1 : 0;
     a.d_idx = reinterpret_cast<long long*>(s.d_idx); a.d_pos = s.d_pos; a.d_target = s.d_target; a.d_inv = s.d_inv;
-    a.words = e->d_words; a.rej = e->d_rej;
+    a.words = e->d_words;
+    a.rej = e->d_rej + (size_t)e->pp * (apg::kPayloadSlack + 1);
+    a.rej_next = e->d_rej + (size_t)(e->pp ^ 1) * (apg::kPayloadSlack + 1);
+    e->pp ^= 1;
     const int n = apg::launch_device_payload(a, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "payload kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);

@@ -95,8 +95,26 @@ __global__ void payload_words_kernel(const PayloadArgs a) {
   }
 }
 
+// (c) one thread: the stream states after the payload (into the other state buffer, the value threads are still
+// reading this one) and a clean rejection list for the next payload
+__device__ __forceinline__ void payload_finish(const PayloadArgs& a) {
+  Pcg64 g0 = a.streams[0], g1 = a.streams[1], g2 = a.streams[2];
+  if (a.loc) pcg64_advance(g0, (uint64_t)(2 * a.Ng));
+  if (a.M > 1) consume_words(g2, accepted_word(a.rej, a.Ng - 1) + 1);
+  if (a.inv) consume_words(g1, a.Ng);
+  pcg64_advance(g1, (uint64_t)(2 * a.Ng));
+  a.streams_out[0] = g0;
+  a.streams_out[1] = g1;
+  a.streams_out[2] = g2;
+  a.rej_next[0] = 0u;
+}
+
 // (b) this shard's slice of the payload
 __global__ void payload_values_kernel(const PayloadArgs a) {
+  if (blockIdx.x == gridDim.x - 1) {  // an extra block: its first thread advances the streams, side by side
+    if (threadIdx.x == 0) payload_finish(a);
+    return;
+  }
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // bank indices
   if (q < a.N) {
@@ -122,21 +140,6 @@ __global__ void payload_values_kernel(const PayloadArgs a) {
   }
 }
 
-// (c) one thread: the stream states after the payload; clears the rejection list for the next payload
-__global__ void payload_finish_kernel(const PayloadArgs a) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Pcg64 g0 = a.streams[0], g1 = a.streams[1], g2 = a.streams[2];
-  if (a.loc) pcg64_advance(g0, (uint64_t)(2 * a.Ng));
-  if (a.M > 1) consume_words(g2, accepted_word(a.rej, a.Ng - 1) + 1);
-  if (a.inv) consume_words(g1, a.Ng);
-  pcg64_advance(g1, (uint64_t)(2 * a.Ng));
-  a.streams[0] = g0;
-  a.streams[1] = g1;
-  a.streams[2] = g2;
-  const int R = min((int)a.rej[0], kPayloadSlack);
-  for (int i = 0; i <= R; ++i) a.rej[i] = 0u;
-}
-
 }  // namespace
 
 bool payload_device_ok(unsigned long long M, long long Ng) {
@@ -151,11 +154,10 @@ int launch_device_payload(const PayloadArgs& a, cudaStream_t stream) {
   const long long raws = (a.Ng + kPayloadSlack + 1) / 2 + 1;  // one thread per raw draw of the g2 word stream
   payload_words_kernel<<<(unsigned)((raws + 255) / 256), 256, 0, stream>>>(a);
   static_assert(kDrawsPerThread >= 2, "N threads must cover the 2N uniform draws");
-  payload_values_kernel<<<(unsigned)((a.N + 255) / 256), 256, 0, stream>>>(a);
-  payload_finish_kernel<<<1, 32, 0, stream>>>(a);
+  payload_values_kernel<<<(unsigned)((a.N + 255) / 256) + 1, 256, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -(int)e;
-  return 3;
+  return 2;
 }
 
 }  // namespace apg
@@ -184,25 +186,28 @@ extern "C" int apg_rng_device_payload(int32_t device, apg_pcg64_state* g0, apg_p
   a.Ng = global_n; a.off = env_offset; a.N = num_envs; a.M = n_items; a.loc = localization; a.inv = invert;
   cudaError_t err = cudaSuccess;
   auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
-  A(cudaMalloc(&a.streams, 3 * sizeof(apg::Pcg64)));
+  apg::Pcg64* d_st = nullptr;
+  A(cudaMalloc(&d_st, 6 * sizeof(apg::Pcg64)));
+  a.streams = d_st; a.streams_out = d_st + 3;
   A(cudaMalloc(&a.d_idx, num_envs * 8)); A(cudaMalloc(&a.d_pos, num_envs * 16));
   A(cudaMalloc(&a.d_target, num_envs * 8)); A(cudaMalloc(&a.d_inv, num_envs));
   A(cudaMalloc(&a.words, apg::payload_scratch_words(global_n) * 4));
-  A(cudaMalloc(&a.rej, (apg::kPayloadSlack + 1) * 4));
+  A(cudaMalloc(&a.rej, 2 * (apg::kPayloadSlack + 1) * 4));
   if (err == cudaSuccess) {
-    A(cudaMemset(a.rej, 0, (apg::kPayloadSlack + 1) * 4));
-    A(cudaMemcpy(a.streams, st, sizeof(st), cudaMemcpyHostToDevice));
+    a.rej_next = a.rej + apg::kPayloadSlack + 1;
+    A(cudaMemset(a.rej, 0, 2 * (apg::kPayloadSlack + 1) * 4));
+    A(cudaMemcpy(d_st, st, sizeof(st), cudaMemcpyHostToDevice));
     const int rc = apg::launch_device_payload(a, nullptr);
     if (rc < 0) A((cudaError_t)(-rc));
     else apg::count_launch(rc);
     A(cudaDeviceSynchronize());
-    A(cudaMemcpy(st, a.streams, sizeof(st), cudaMemcpyDeviceToHost));
+    A(cudaMemcpy(st, a.streams_out, sizeof(st), cudaMemcpyDeviceToHost));
     A(cudaMemcpy(h_idx, a.d_idx, num_envs * 8, cudaMemcpyDeviceToHost));
     A(cudaMemcpy(h_pos, a.d_pos, num_envs * 16, cudaMemcpyDeviceToHost));
     if (localization && h_target) A(cudaMemcpy(h_target, a.d_target, num_envs * 8, cudaMemcpyDeviceToHost));
     if (invert && h_inv) A(cudaMemcpy(h_inv, a.d_inv, num_envs, cudaMemcpyDeviceToHost));
   }
-  cudaFree(a.streams); cudaFree(a.d_idx); cudaFree(a.d_pos); cudaFree(a.d_target); cudaFree(a.d_inv);
+  cudaFree(d_st); cudaFree(a.d_idx); cudaFree(a.d_pos); cudaFree(a.d_target); cudaFree(a.d_inv);
   cudaFree(a.words); cudaFree(a.rej);
   if (err != cudaSuccess) return apg::fail(APG_ERR_CUDA, "apg_rng_device_payload: %s", cudaGetErrorString(err));
   apg_pcg64_state* out[3] = {g0, g1, g2};

@@ -21,7 +21,8 @@ namespace apg {
 constexpr int kPayloadSlack = 1024;  // rejected bank-index draws one payload may hold (see payload_device_ok)
 
 struct PayloadArgs {
-  Pcg64* streams;        // device, [3] = g0, g1, g2: read, then advanced by the finish kernel
+  const Pcg64* streams;  // device, [3] = g0, g1, g2 before the payload
+  Pcg64* streams_out;    // device, [3]: the states after the payload (a different buffer: written while others read)
   long long Ng, off, N;  // global batch, this shard's first env, this shard's envs
   unsigned long long M;  // len(dataset)
   int loc, inv;
@@ -31,13 +32,14 @@ struct PayloadArgs {
   unsigned char* d_inv;  // (N)   (inv)
   unsigned* words;       // scratch: Ng + kPayloadSlack + 2 32-bit words of the g2 stream
   unsigned* rej;         // scratch: [0] = number of rejected words, [1 .. kPayloadSlack] their positions; zero on entry
+  unsigned* rej_next;    // the other rejection list, cleared here for the next payload
 };
 
 // true when the device generator may be used: 2 <= M <= 2^32 and so few expected rejections that kPayloadSlack
 // cannot overflow (otherwise the host generator draws the payload)
 bool payload_device_ok(unsigned long long M, long long Ng);
 size_t payload_scratch_words(long long Ng);
-// three launches on `stream`; returns the number of launches or a negative cudaError
+// two launches on `stream`; returns the number of launches or a negative cudaError
 int launch_device_payload(const PayloadArgs& a, cudaStream_t stream);
 
 }  // namespace apg
