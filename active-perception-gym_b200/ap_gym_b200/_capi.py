@@ -31,7 +31,7 @@ class ImageCfg(C.Structure):
         ("sensor_h", C.c_int32), ("sensor_w", C.c_int32),
         ("sensor_scale", C.c_double), ("max_step_length", C.c_double * 2),
         ("step_limit", C.c_int32), ("num_classes", C.c_int32), ("bank_dtype", C.c_int32),
-        ("randomly_invert_labels", C.c_int32), ("track_visited", C.c_int32), ("payload_ring", C.c_int32), ("blend_f32", C.c_int32),
+        ("randomly_invert_labels", C.c_int32), ("track_visited", C.c_int32), ("payload_ring", C.c_int32), ("blend_f32", C.c_int32), ("sparse_reward", C.c_int32),
     ]
 
 
@@ -73,7 +73,7 @@ class LidarCfg(C.Structure):
         ("device", C.c_int32), ("num_envs", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
         ("beam_count", C.c_int32), ("lidar_range", C.c_float), ("step_limit", C.c_int32),
         ("static_map", C.c_int32), ("static_map_index", C.c_int32), ("emit_cells", C.c_int32),
-        ("env_offset", C.c_int64),
+        ("env_offset", C.c_int64), ("sparse_reward", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

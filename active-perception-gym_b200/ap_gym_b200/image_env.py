@@ -63,12 +63,16 @@ class _ImageVectorEnvBase:
                  env_offset: int = 0, global_num_envs: int | None = None, track_visited: bool = True,
                  check_errors: Literal["step", "lazy", "never"] = "lazy",
                  output: Literal["torch", "numpy"] = "torch", payload_ring: int = 4,
-                 blend: Literal["float64", "float32"] = "float64"):
+                 blend: Literal["float64", "float32"] = "float64", sparse: bool = False):
+        """`sparse=True` is the reference's `<id>-sparse` registration (SparsifyVectorWrapper, sparsify_wrapper.py:23-88):
+        reward = base_reward - loss * weight with weight = terminated, and info["prediction"]["target"] becomes
+        {"target": ..., "weight": float32(terminated)}."""
         if render_mode not in self.metadata["render_modes"]:
             raise ValueError(f"Unsupported render mode: {render_mode}")
         if blend not in ("float64", "float32"):
             raise ValueError("blend must be 'float64' (the reference's arithmetic, bit-exact) or 'float32'")
         self.blend = blend
+        self.sparse = bool(sparse)
         cfg = image_perception_config
         self._config = cfg
         self._render_mode = render_mode
@@ -104,7 +108,7 @@ class _ImageVectorEnvBase:
             max_step_length=(C.c_double * 2)(float(msl[0]), float(msl[1])), step_limit=int(cfg.step_limit),
             num_classes=self._K, bank_dtype=_capi.BANK_U8 if bank.is_u8 else _capi.BANK_F32,
             randomly_invert_labels=int(cfg.randomly_invert_labels), track_visited=int(track_visited),
-            payload_ring=int(payload_ring), blend_f32=int(blend == "float32"))
+            payload_ring=int(payload_ring), blend_f32=int(blend == "float32"), sparse_reward=int(bool(sparse)))
         self._ring = max(1, min(int(payload_ring) if payload_ring > 0 else _capi.PAYLOAD_RING_DEFAULT,
                                 _capi.PAYLOAD_RING_MAX))
         h = C.c_void_p()
@@ -323,6 +327,9 @@ class _ImageVectorEnvBase:
             "base_reward": self._out("base_reward", host_mode),
             "prediction": {"target": self._out(self._TARGET_VIEW, host_mode), "loss": self._out("loss", host_mode)},
         }
+        if self.sparse:
+            w = terminated.astype(np.float32) if host_mode else terminated.to(dtype=self._views["reward"].dtype)
+            info["prediction"]["target"] = {"target": info["prediction"]["target"], "weight": w}
         if self._buffers().needs_reset:  # this step ended every episode: the LogWrapper's info["stats"]
             info["stats"] = self._stats_info(host_mode, terminated)
         return obs, reward, terminated, truncated, info

@@ -41,7 +41,11 @@ class LIDARLocalization2DVectorEnv:
                  static_map: bool = False, lidar_beam_count: int = 8, lidar_range: float = 5,
                  static_map_index: int = 0, prefetch: bool = True, prefetch_buffer_size: int = 128, *,
                  max_episode_steps: int = 100, device: int = 0, env_offset: int = 0, emit_cells: bool = False,
-                 check_errors: Literal["step", "lazy", "never"] = "lazy", output: Literal["torch", "numpy"] = "torch"):
+                 check_errors: Literal["step", "lazy", "never"] = "lazy", output: Literal["torch", "numpy"] = "torch",
+                 sparse: bool = False):
+        """`sparse=True` = the reference's `<id>-sparse` registration (SparsifyWrapper around every env,
+        sparsify_wrapper.py:95-150): the loss only enters the reward of the step that terminates an env's episode and
+        info["prediction"]["target"] becomes {"target": ..., "weight": float32(terminated)}."""
         if render_mode not in self.metadata["render_modes"]:
             raise ValueError(f"Invalid render mode: {render_mode}")
         self._render_mode = render_mode
@@ -61,7 +65,9 @@ class LIDARLocalization2DVectorEnv:
         cfg = _capi.LidarCfg(device=self._device, num_envs=self.num_envs, width=self._W, height=self._H,
                              beam_count=self._B, lidar_range=float(lidar_range), step_limit=self._T,
                              static_map=int(self._static), static_map_index=int(static_map_index),
-                             emit_cells=int(self._emit), env_offset=int(env_offset))
+                             emit_cells=int(self._emit), env_offset=int(env_offset),
+                             sparse_reward=int(bool(sparse)))
+        self.sparse = bool(sparse)
         h = C.c_void_p()
         _capi.check(self._lib.apg_lidar_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -205,6 +211,9 @@ class LIDARLocalization2DVectorEnv:
                                  "return": self._out("ep_return", host_mode)},
                       "_scalar": terminated},
         }
+        if self.sparse:
+            w = terminated.astype(np.float32) if host_mode else terminated.to(dtype=self._views["reward"].dtype)
+            info["prediction"]["target"] = {"target": info["prediction"]["target"], "weight": w}
         return obs, reward, terminated, truncated, info
 
     def episode_stats(self, reduce: bool = True, clear: bool = False) -> dict[str, float]:

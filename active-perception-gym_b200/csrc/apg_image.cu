@@ -50,6 +50,7 @@ struct ImgParams {
   int tb_consec;     // thread-blend path: use the consecutive-row variants
   int ctr_off;       // byte offset of the EnvCtr array in dynamic shared memory (split phase A)
   int split;         //  phase A split into per-env scalars (one thread) + taps / staging (all threads)
+  int sparse;        // 1: the loss only enters the reward of the step that ends the episode (`-sparse` ids)
   int fast;          // 1: float32 blend (within the 1e-5 bar), 0: the reference's float64 blend (bit-exact)
   int tb;            // thread-blend path: threads that share one environment's sensor columns
   int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
@@ -403,10 +404,17 @@ __device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_st
     // step, whose base reward is np.zeros(N) (float64)
     if (cls) reward_f = (float)((double)base + neg_loss_d);
     else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
-    p.reward[n] = reward_f;
+    float reward_out = reward_f;
+    if (p.sparse) {  // base_reward - loss * weight, weight = float32(terminated)  (sparsify_wrapper.py:60-83)
+      const bool w1 = (p.mode == 0) && p.terminated;
+      if (cls) reward_out = (float)((double)base - (-neg_loss_d) * (w1 ? 1.0 : 0.0));
+      else if (p.mode == 0) reward_out = __fsub_rn(base, __fmul_rn(loss_f, w1 ? 1.0f : 0.0f));
+      else reward_out = (float)(0.0 - (double)__fmul_rn(loss_f, 0.0f));
+    }
+    p.reward[n] = reward_out;
     p.base_reward[n] = base;
     p.loss[n] = loss_f;
-    if (p.reward2) p.reward2[n] = reward_f;
+    if (p.reward2) p.reward2[n] = reward_out;
     if (p.done2) p.done2[n] = p.terminated;
     // ---- episode statistics (the *VectorLogWrapper loops): real steps only, cleared by the reset step
     if (p.mode == 0) {
@@ -1138,7 +1146,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.split = e->split; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;

@@ -31,7 +31,7 @@ constexpr int kEnvsPerBlock = 32;
 
 struct LidarParams {
   int N, W, H, words, B, G, T, M;
-  int static_map, static_idx, emit_cells;
+  int static_map, static_idx, emit_cells, sparse;
   int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams), 3 = explicit reset (keep streams)
   float range;
   unsigned long long seed;  // mode 2: env i is seeded with seed + env_offset + i
@@ -399,12 +399,14 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
       } else {
         p.acc1[n] = s1; p.acc2[n] = s2; p.acc_ret[n] = sr;
       }
-      p.reward[n] = rew;
+      // `-sparse` ids: base_reward - loss * weight, weight = 1.0 on the terminating step, else 0.0
+      const float rew_out = p.sparse ? __fsub_rn(base, __fmul_rn(loss, term ? 1.0f : 0.0f)) : rew;
+      p.reward[n] = rew_out;
       p.base_reward[n] = base;
       p.loss[n] = loss;
       p.target[2 * n] = t0; p.target[2 * n + 1] = t1;
       p.stepped[n] = 1;
-      if (p.reward2) p.reward2[n] = rew;
+      if (p.reward2) p.reward2[n] = rew_out;
     }
     // ---- state write-back + scalar observations
     p.map_idx_out[n] = (long long)midx;
@@ -501,7 +503,7 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   LidarParams p{};
   p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
   p.T = c.step_limit; p.M = (int)e->n_maps; p.static_map = c.static_map; p.static_idx = c.static_map_index;
-  p.emit_cells = c.emit_cells; p.mode = mode; p.range = c.lidar_range; p.seed = seed; p.env_offset = c.env_offset;
+  p.emit_cells = c.emit_cells; p.sparse = c.sparse_reward ? 1 : 0; p.mode = mode; p.range = c.lidar_range; p.seed = seed; p.env_offset = c.env_offset;
   p.bank = e->d_bank; p.dirs = e->d_dirs; p.action = d_action; p.pred = d_pred;
   p.pos = e->b.d_pos; p.init = e->b.d_initial_pos; p.aliased = e->d_aliased; p.elapsed = e->d_elapsed;
   p.map_idx = e->d_map_idx; p.prev_done = e->d_prev_done; p.g0 = e->d_g0; p.g2 = e->d_g2;

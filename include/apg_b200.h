@@ -77,6 +77,9 @@ typedef struct {
   int32_t blend_f32;              /* 0: the reference's float64 blend (bit-exact pixels); 1: float32 blend with weights
                                      rounded once from float64 (pixels within a few float32 ulps, i.e. inside the
                                      1e-5 relative bar; about twice the throughput on large glimpses) */
+  int32_t sparse_reward;          /* 1: the reference's `-sparse` ids (SparsifyVectorWrapper, sparsify_wrapper.py:74-88):
+                                     reward = base_reward - loss * weight with weight = terminated, i.e. the loss is
+                                     only charged by the step that ends the episode.  loss / statistics unchanged. */
 } apg_image_cfg;
 
 /* Engine-owned persistent device buffers.  Views stay valid until apg_image_destroy; contents are
@@ -216,6 +219,9 @@ typedef struct {
   int32_t static_map_index; /* static_map_index */
   int32_t emit_cells;       /* also write the per-beam contact cells and raw distances (parity / rendering) */
   int64_t env_offset;       /* global index of env 0 of this shard: env i is seeded with seed + env_offset + i */
+  int32_t sparse_reward;    /* 1: `-sparse` ids (SparsifyWrapper, sparsify_wrapper.py:137-150): the loss is only charged by
+                               the step that terminates the env's episode */
+  int32_t reserved;
 } apg_lidar_cfg;
 
 typedef struct {

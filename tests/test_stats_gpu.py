@@ -79,3 +79,80 @@ def test_lidar_episode_stats(name):
             n_done += 1
     assert env.episode_stats(reduce=False)["episodes"] == n_done
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# `-sparse` ids (SparsifyVectorWrapper / SparsifyWrapper, sparsify_wrapper.py:60-88, 137-150):
+# reward = base_reward - loss * weight, weight = float32(terminated); everything else as in the dense env.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("task", ["cls", "loc"])
+def test_sparse_image_env_matches_dense_run(task):
+    import ap_gym_b200 as apg
+    from oracle.datasets import synthetic_u8_bank
+
+    N, K, T = 193, 7, 5
+    imgs, labels = synthetic_u8_bank(seed=9, M=200, H=28, W=28, C=1, K=K)
+    cls = apg.ImageClassificationVectorEnv if task == "cls" else apg.ImageLocalizationVectorEnv
+    kw = dict(target_sampling="uniform") if task == "loc" else {}
+    envs = []
+    for sparse in (False, True):
+        cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K), step_limit=T)
+        env = cls(N, cfg, output="numpy", sparse=sparse, **kw)
+        env.reset(seed=4)
+        envs.append(env)
+    rng = np.random.default_rng(2)
+    saw_terminal = 0
+    for s in range(3 * (T + 1)):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        p = rng.standard_normal((N, K if task == "cls" else 2)).astype(np.float32)
+        od, rd, ted, _, infd = envs[0].step({"action": a, "prediction": p})
+        os_, rs, tes, _, infs = envs[1].step({"action": a, "prediction": p})
+        for k in od:
+            assert np.array_equal(od[k], os_[k])
+        assert np.array_equal(ted, tes)
+        w = tes.astype(np.float32)
+        assert np.array_equal(infs["prediction"]["target"]["weight"], w)
+        assert np.array_equal(infs["prediction"]["target"]["target"], infd["prediction"]["target"])
+        assert np.array_equal(infs["prediction"]["loss"], infd["prediction"]["loss"])
+        base, loss = infd["base_reward"], infd["prediction"]["loss"]
+        if task == "cls":  # float32 base - float64(loss) * float32 weight -> float64 (numpy promotion), emitted as f32
+            want = (base.astype(np.float64) - loss.astype(np.float64) * w).astype(np.float32)
+            assert np.allclose(rs, want, rtol=1e-6, atol=1e-7)  # loss itself is only available rounded to float32
+        else:
+            assert np.array_equal(rs, base - loss * w)
+        assert np.array_equal(rs[tes], rd[tes])  # the terminating step charges the full loss
+        assert np.array_equal(rs[~tes], base[~tes])
+        saw_terminal += int(tes.any())
+    assert saw_terminal == 3
+    for e in envs:
+        e.close()
+
+
+def test_sparse_lidar_env_matches_dense_run():
+    import ap_gym_b200 as apg
+    bank = apg.FloorMapBank.from_maps(load_bank("rooms32", 64))
+    N = 300
+    envs = [apg.LIDARLocalization2DVectorEnv(N, bank, lidar_beam_count=8, max_episode_steps=7, output="numpy",
+                                             sparse=sp) for sp in (False, True)]
+    for e in envs:
+        e.reset(seed=11)
+    rng = np.random.default_rng(5)
+    n_term = 0
+    for s in range(30):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        p = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        od, rd, ted, _, infd = envs[0].step({"action": a, "prediction": p})
+        os_, rs, tes, _, infs = envs[1].step({"action": a, "prediction": p})
+        for k in od:
+            assert np.array_equal(od[k], os_[k])
+        assert np.array_equal(ted, tes)
+        stepped = infd["_base_reward"]
+        w = tes.astype(np.float32)
+        assert np.array_equal(infs["prediction"]["target"]["weight"], w)
+        base, loss = infd["base_reward"], infd["prediction"]["loss"]
+        assert np.array_equal(rs[stepped], (base - loss * w)[stepped])
+        assert np.array_equal(rs[~stepped], rd[~stepped])  # autoreset steps: reward 0 in both
+        n_term += int(tes.sum())
+    assert n_term > N
+    for e in envs:
+        e.close()
