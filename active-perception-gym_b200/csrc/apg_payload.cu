@@ -61,38 +61,36 @@ __device__ __forceinline__ long long accepted_word(const unsigned* rej, long lon
   }
 }
 
-// (a) the g2 word stream of the whole global batch (+ slack) and the positions Lemire's method rejects
+// (a) the g2 word stream of the whole global batch (+ slack) and the positions Lemire's method rejects; every thread
+// jumps once and then steps through kRawsPerThread consecutive raw draws (two words each)
+constexpr int kRawsPerThread = 8;
+
+__device__ __forceinline__ void note_word(const PayloadArgs& a, long long t, uint32_t w, uint32_t threshold) {
+  a.words[t] = w;
+  if (lemire_rejects(w, a.M, threshold)) {
+    const unsigned slot = atomicAdd(&a.rej[0], 1u);
+    if (slot < (unsigned)kPayloadSlack) a.rej[1 + slot] = (unsigned)t;
+  }
+}
+
 __global__ void payload_words_kernel(const PayloadArgs a) {
   const long long n_words = a.Ng + kPayloadSlack;
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // raw draw
+  const long long r0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kRawsPerThread;  // first raw draw
   const Pcg64 g2 = a.streams[2];
   const int has = g2.has_uint32 ? 1 : 0;
   const uint32_t threshold = (a.M >= 0x100000000ull) ? 0u : (uint32_t)((0x100000000ull - a.M) % a.M);
-  uint32_t w[2];
-  long long t0 = has + 2 * r;
-  if (t0 < n_words) {
+  if (has + 2 * r0 < n_words) {
     Pcg64 g = g2;
-    pcg64_advance(g, (uint64_t)r);
-    const uint64_t n = pcg64_next64(g);
-    w[0] = (uint32_t)n;
-    w[1] = (uint32_t)(n >> 32);
-    for (int h = 0; h < 2; ++h) {
-      const long long t = t0 + h;
-      if (t >= n_words) break;
-      a.words[t] = w[h];
-      if (lemire_rejects(w[h], a.M, threshold)) {
-        const unsigned slot = atomicAdd(&a.rej[0], 1u);
-        if (slot < (unsigned)kPayloadSlack) a.rej[1 + slot] = (unsigned)t;
-      }
+    pcg64_advance(g, (uint64_t)r0);
+    for (int i = 0; i < kRawsPerThread; ++i) {
+      const long long t0 = has + 2 * (r0 + i);
+      if (t0 >= n_words) break;
+      const uint64_t n = pcg64_next64(g);
+      note_word(a, t0, (uint32_t)n, threshold);
+      if (t0 + 1 < n_words) note_word(a, t0 + 1, (uint32_t)(n >> 32), threshold);
     }
   }
-  if (r == 0 && has) {
-    a.words[0] = g2.uinteger;
-    if (lemire_rejects(g2.uinteger, a.M, threshold)) {
-      const unsigned slot = atomicAdd(&a.rej[0], 1u);
-      if (slot < (unsigned)kPayloadSlack) a.rej[1 + slot] = 0u;
-    }
-  }
+  if (r0 == 0 && has) note_word(a, 0, g2.uinteger, threshold);
 }
 
 // (c) one thread: the stream states after the payload (into the other state buffer, the value threads are still
@@ -151,8 +149,9 @@ bool payload_device_ok(unsigned long long M, long long Ng) {
 size_t payload_scratch_words(long long Ng) { return (size_t)(Ng + kPayloadSlack + 2); }
 
 int launch_device_payload(const PayloadArgs& a, cudaStream_t stream) {
-  const long long raws = (a.Ng + kPayloadSlack + 1) / 2 + 1;  // one thread per raw draw of the g2 word stream
-  payload_words_kernel<<<(unsigned)((raws + 255) / 256), 256, 0, stream>>>(a);
+  const long long raws = (a.Ng + kPayloadSlack + 1) / 2 + 1;  // raw draws behind the g2 word stream
+  const long long wthreads = (raws + kRawsPerThread - 1) / kRawsPerThread;
+  payload_words_kernel<<<(unsigned)((wthreads + 127) / 128), 128, 0, stream>>>(a);
   static_assert(kDrawsPerThread >= 2, "N threads must cover the 2N uniform draws");
   payload_values_kernel<<<(unsigned)((a.N + 255) / 256) + 1, 256, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
