@@ -124,6 +124,7 @@ SYMBOLS = {
     "apg_lidar_get_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "apg_lidar_poll_error": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_int]),
     "apg_lidar_sync": (C.c_int, [_P]),
+    "apg_struct_sizes": (None, [C.POINTER(C.c_int32)]),
     "apg_rng_host_stream": (C.c_int, [C.c_uint64, C.c_int32, _P, _P, _P]),
     "apg_rng_device_payload": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int32,
                                          C.c_int32, _P, _P, _P, _P]),

@@ -35,6 +35,14 @@ const char* apg_last_error(void) { return apg::last_error().c_str(); }
 
 int64_t apg_launch_count(void) { return apg::g_launches.load(std::memory_order_relaxed); }
 
+void apg_struct_sizes(int32_t out[5]) {
+  out[0] = (int32_t)sizeof(apg_image_cfg);
+  out[1] = (int32_t)sizeof(apg_image_buffers);
+  out[2] = (int32_t)sizeof(apg_lidar_cfg);
+  out[3] = (int32_t)sizeof(apg_lidar_buffers);
+  out[4] = (int32_t)sizeof(apg_pcg64_state);
+}
+
 // ---- DLPack v0.8 descriptor (layout restated from the public dlpack.h; no header dependency) ----------
 typedef struct {
   int32_t device_type;  // kDLCUDA = 2

@@ -44,6 +44,10 @@ int apg_version(void);
 const char* apg_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 int64_t apg_launch_count(void);
+/* sizeof() of the five structs of this header as compiled into the library, in the order apg_image_cfg,
+ * apg_image_buffers, apg_lidar_cfg, apg_lidar_buffers, apg_pcg64_state: lets a binding verify its own declarations
+ * (tests/test_capi_symbols.py does it for the bundled ctypes layer).  No GPU needed. */
+void apg_struct_sizes(int32_t out[5]);
 
 /* ------------------------------------------------------------------------------------------------------
  * Image environments.  Replaces, for one shard of `num_envs` environments:

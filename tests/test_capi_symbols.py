@@ -30,6 +30,16 @@ def test_header_symbols_are_exported_and_bound():
     assert _capi.lib().apg_version() == 100
 
 
+def test_ctypes_struct_layouts_match_the_compiled_header():
+    from ap_gym_b200 import _capi
+
+    out = (ctypes.c_int32 * 5)()
+    _capi.lib().apg_struct_sizes(out)
+    mine = [ctypes.sizeof(c) for c in (_capi.ImageCfg, _capi.ImageBuffers, _capi.LidarCfg, _capi.LidarBuffers,
+                                       _capi.Pcg64State)]
+    assert list(out) == mine, f"library {list(out)} vs ctypes {mine}"
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 
