@@ -45,7 +45,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=340)
+    ap.add_argument("--steps", type=int, default=0,
+                    help="timed steps (default: per workload, ~0.4 s of device time: mnist 20400, tinyloc 3400, "
+                         "lidar_rooms 680, lidar_maze 340)")
     ap.add_argument("--warmup", type=int, default=34)
     ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -57,12 +59,16 @@ def parse():
     ap.add_argument("--blend", default="float64", choices=["float64", "float32"],
                     help="image workloads: float64 = the reference's blend arithmetic (bit-exact pixels, default); "
                          "float32 = opt-in blend within the 1e-5 relative bar")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps <= 0:
+        args.steps = {"mnist": 20400, "tinyloc": 3400, "lidar_rooms": 680, "lidar_maze": 340}[args.workload]
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; stop(t0, t1) keeps the samples that arrived inside the
+    timed region [t0, t1] (wall clock) and falls back to all of them, saying so, when the region was too short."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -76,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -85,9 +91,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -98,7 +104,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if t0 is not None and t0 <= t <= t1 + 0.05]
+        in_region = len(inside) > 0
+        for ln in (inside if in_region else [ln for (_, ln) in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -111,7 +119,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "sampled": "inside the timed region" if in_region else
+                "around the timed region (shorter than the 50 ms sampling period)", "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
@@ -273,12 +282,12 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # distinct inputs for every step: streamed from HBM, total larger than L2
     chunk = 17 * 3  # steps per rollout call (3 episodes)
-    tot = K + W
-    acts = torch.rand((tot, n, 2), generator=gen, device=dev) * 2 - 1
+    pool = min(K + W, 7 * chunk)  # distinct per-step inputs; longer runs walk the pool cyclically (it is >> L2)
+    acts = torch.rand((pool, n, 2), generator=gen, device=dev) * 2 - 1
     if pw == 2:
-        preds = torch.rand((tot, n, 2), generator=gen, device=dev) * 2 - 1
+        preds = torch.rand((pool, n, 2), generator=gen, device=dev) * 2 - 1
     else:
-        preds = torch.randn((tot, n, pw), generator=gen, device=dev)
+        preds = torch.randn((pool, n, pw), generator=gen, device=dev)
     t_reset0 = time.perf_counter()
     env.reset(seed=0)
     env.sync()
@@ -287,9 +296,10 @@ def main():
     def run(s0, s1, env=env):
         s = s0
         while s < s1:
-            e = min(s + chunk, s1)
-            env.rollout(acts[s:e], preds[s:e])
-            s = e
+            a = s % pool
+            m = min(chunk, s1 - s, pool - a)
+            env.rollout(acts[a:a + m], preds[a:a + m])
+            s += m
 
     def barrier():
         if world > 1:
@@ -306,13 +316,15 @@ def main():
     l0 = _capi.lib().apg_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.time()
     ev0.record()
     run(W, W + K)
     ev1.record()
     barrier()
+    t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = _capi.lib().apg_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -404,7 +416,7 @@ def main():
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}", "blend": None if is_lidar else args.blend, "explicit_reset_s": round(reset_s, 3),
-                       "l2": "per-step inputs are distinct and streamed from HBM (%.0f MB total > 126 MB L2); engine-owned obs buffers are rewritten every step" % (acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
+                       "l2": "per-step inputs come from a pool of %d distinct steps streamed from HBM (%.0f MB > 126 MB L2, walked cyclically); engine-owned obs buffers are rewritten every step" % (pool, acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "api": ("apg_lidar_step_host" if is_lidar else "apg_image_step_host") + " (pinned host action/prediction in, reward/terminated/truncated out)"},
