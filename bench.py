@@ -393,6 +393,15 @@ def main():
     # ---- final NCCL reduce of the device-side episode statistics (the only collective of the data path)
     stats = env.episode_stats(reduce=True)
     env.sync()
+    # sticky device-side error bits (NaN input, tap outside the image grid) of everything this process stepped: the
+    # benchmark runs with check_errors="never", so look once at the end -- a non-zero value invalidates the run
+    import ctypes
+    flags = ctypes.c_uint32(0)
+    _capi.check((lib.apg_lidar_poll_error if is_lidar else lib.apg_image_poll_error)(env._h, ctypes.byref(flags), 0))
+    t_f = torch.tensor([int(flags.value)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
+    error_flags = int(t_f.item())
 
     if rank == 0:
         peaks = {}
@@ -430,7 +439,10 @@ def main():
                          "note": "achieved = algorithmic bytes of one step / device time of one step; with 2 launches per "
                                  "step (image_head_kernel + image_step_kernel, warp path) the step time covers both"},
             "episode_stats_allreduce": stats,
+            "error_flags": error_flags,
         }
+        if error_flags:
+            sys.stderr.write("bench.py: device error flags 0x%x were raised during the run -- result INVALID\n" % error_flags)
         if alt is not None:
             alt["roofline_frac"] = (bytes_per_launch / (alt["ms_per_step"] * 1e-3) / 1e9) / peak
             line["alt_blend"] = alt
