@@ -47,6 +47,7 @@ struct ImgParams {
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
   EnvHdr* g_hdr;     // split == 2: tile headers / centres written by image_head_kernel, (n_sets, N)
   EnvCtr* g_ctr;
+  int pdl;           // launched with programmatic stream serialization: wait for the previous grid explicitly
   int tb_consec;     // thread-blend path: use the consecutive-row variants
   int ctr_off;       // byte offset of the EnvCtr array in dynamic shared memory (split phase A)
   int split;         //  phase A split into per-env scalars (one thread) + taps / staging (all threads)
@@ -773,12 +774,25 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
   }
 }
 
+// Programmatic dependent launch: consecutive vector steps are launched back to back on one stream; with the launch
+// attribute set, the blocks of step k+1 are scheduled while step k drains and park here until step k's memory is
+// visible.  Every block lets its own dependents go at once (they wait at the same place).
+__device__ __forceinline__ void grid_dependency_wait(int pdl) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  if (pdl) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+  }
+#endif
+}
+
 // Two-kernel variant of the warp-per-environment path (split == 2): the scalar chains and the tile headers of ALL
 // environments, one thread each.  Inside the blend kernel this work occupied one warp of eight for ~18 % of a block's
 // lifetime (memory round trip + serial float64 taps) with the other seven parked at a barrier; here 10^5 threads hide
 // each other's latency.  The headers travel through L2 (48 bytes per environment and glimpse set).
 template <typename BankT>
 __global__ void __launch_bounds__(256) image_head_kernel(const ImgParams p) {
+  grid_dependency_wait(p.pdl);
   __shared__ double s_stats[6];
   const bool ep_end = (p.mode == 0) && p.terminated;
   if (ep_end && threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
@@ -809,6 +823,7 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
   if (S0T > 0) {
     p.S0 = S0T; p.S1 = S1T; p.C = CT; p.P = S0T * S1T * CT;
   }
+  grid_dependency_wait(p.pdl);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvHdr* s_hdr = reinterpret_cast<EnvHdr*>(smem_raw);
   Tap* s_taps = reinterpret_cast<Tap*>(smem_raw + (size_t)p.E * sizeof(EnvHdr));
@@ -1053,7 +1068,7 @@ struct apg_image_env {
   cudaStream_t stream = nullptr;
   int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
   size_t pipe_smem = 0;
-  int split = 0, ctr_off = 0, spec = 0, tile_bytes = 0, tb_consec = 1;
+  int split = 0, ctr_off = 0, spec = 0, tile_bytes = 0, tb_consec = 1, pdl = 1;
   void* d_ghdr = nullptr;
   void* d_gctr = nullptr;
   size_t smem = 0;
@@ -1147,7 +1162,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.pdl = e->pdl; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode;
   int t_after;
   if (mode == 0) {
     p.t_stamp = e->t;
@@ -1200,10 +1215,21 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   p.inv_k = (float)(1.0 / (double)(c.num_classes > 0 ? c.num_classes : 1));
 
   const int grid = apg::ceil_div(c.num_envs, e->E);
+  // one launch path for every kernel of a step: plain, or with programmatic stream serialization (e->pdl)
+  auto go = [&](auto kernel, int g, int threads, size_t smem) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, p);
+  };
   if (e->split == 2 && !e->pipelined) {
     const int hgrid = apg::ceil_div(c.num_envs, 256);
-    if (c.bank_dtype == APG_BANK_U8) image_head_kernel<unsigned char><<<hgrid, 256, 0, e->stream>>>(p);
-    else image_head_kernel<float><<<hgrid, 256, 0, e->stream>>>(p);
+    if (c.bank_dtype == APG_BANK_U8) go(image_head_kernel<unsigned char>, hgrid, 256, 0);
+    else go(image_head_kernel<float>, hgrid, 256, 0);
     apg::count_launch();
   }
   if (e->pipelined) {
@@ -1213,11 +1239,11 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
     else
       image_step_pipelined_kernel<float><<<pgrid, kPipeThreads, e->pipe_smem, e->stream>>>(p);
   } else if (c.bank_dtype == APG_BANK_U8) {
-    if (e->spec == 1) image_step_kernel<unsigned char, 10, 10, 3><<<grid, e->threads, e->smem, e->stream>>>(p);
-    else if (e->spec == 2) image_step_kernel<unsigned char, 5, 5, 1><<<grid, e->threads, e->smem, e->stream>>>(p);
-    else image_step_kernel<unsigned char, 0, 0, 0><<<grid, e->threads, e->smem, e->stream>>>(p);
+    if (e->spec == 1) go(image_step_kernel<unsigned char, 10, 10, 3>, grid, e->threads, e->smem);
+    else if (e->spec == 2) go(image_step_kernel<unsigned char, 5, 5, 1>, grid, e->threads, e->smem);
+    else go(image_step_kernel<unsigned char, 0, 0, 0>, grid, e->threads, e->smem);
   } else {
-    image_step_kernel<float, 0, 0, 0><<<grid, e->threads, e->smem, e->stream>>>(p);
+    go(image_step_kernel<float, 0, 0, 0>, grid, e->threads, e->smem);
   }
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
@@ -1510,6 +1536,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   if (const char* ov = getenv("APG_IMG_SPEC")) { if (!atoi(ov)) e->spec = 0; }
   if (const char* ov = getenv("APG_IMG_TB_CONSEC")) e->tb_consec = atoi(ov) ? 1 : 0;
   if (const char* ov = getenv("APG_IMG_HOST_RNG")) e->host_rng = atoi(ov) != 0;
+  if (const char* ov = getenv("APG_IMG_PDL")) e->pdl = atoi(ov) ? 1 : 0;
   if (e->thread_blend != (e->P <= kThreadBlendMaxP ? 1 : 0)) e->spec = 0;  // path forced by APG_IMG_THREAD_BLEND
   if (err != cudaSuccess) {
     apg_image_destroy(e);
