@@ -29,161 +29,13 @@
 #include "apg_payload.h"
 #include "apg_rng.h"
 
+#include "apg_image_dev.cuh"
+#include "apg_image_small.h"
+#include "apg_image_tma.h"
+
+using namespace apg_img;
+
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kThreadBlendMaxP = 96;  // glimpses up to this many floats are blended by one or two threads per env
-constexpr int kMaxK = 4096;
-
-struct EnvHdr;
-struct EnvCtr;
-struct ImgParams {
-  int N, H, W, C, S0, S1, P, K, task, invert, track, words, T;
-  int E;             // environments per block
-  int bank_pitch;    // bytes per bank image row (W*C*elem rounded up to 16: every row is 16-byte aligned)
-  int pitch;         // bytes per staged tile row
-  int tile_rows;     // staged rows per environment
-  int tile_bytes;    // pitch * tile_rows
-  int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
-  EnvHdr* g_hdr;     // split == 2: tile headers / centres written by image_head_kernel, (n_sets, N)
-  EnvCtr* g_ctr;
-  int pdl;           // launched with programmatic stream serialization: wait for the previous grid explicitly
-  int tb_consec;     // thread-blend path: use the consecutive-row variants
-  int ctr_off;       // byte offset of the EnvCtr array in dynamic shared memory (split phase A)
-  int split;         //  phase A split into per-env scalars (one thread) + taps / staging (all threads)
-  int sparse;        // 1: the loss only enters the reward of the step that ends the episode (`-sparse` ids)
-  int fast;          // 1: float32 blend (within the 1e-5 bar), 0: the reference's float64 blend (bit-exact)
-  int tb;            // thread-blend path: threads that share one environment's sensor columns
-  int mode;          // 0 = move step, 1 = autoreset step, 2 = explicit reset
-  int t_stamp;       // overlay stamp slot of this step (pre-move time index), mode 0 only
-  float time_obs;    // obs["time_step"] value after this step
-  unsigned char terminated;
-  double scale, msl_x, msl_y, lim_x, lim_y, offy, offx, half0, half1;
-  double rs, half_wr, half_hr;
-  double ce_scale, ce_offset;
-  float mse_scale, mse_offset;
-  // inputs
-  const void* bank;
-  const int* bank_labels;
-  const float* action;
-  const float* pred;
-  // reset payload (modes 1, 2)
-  const long long* new_idx;
-  const double* new_pos;
-  const float* new_target;
-  const unsigned char* new_inv;
-  // state
-  double* pos;
-  int* st_idx;
-  int* st_label;
-  float* st_target;
-  unsigned char* st_inv;
-  // outputs
-  float* glimpse;
-  float* target_glimpse;
-  float* glimpse_pos;
-  float* time_step;
-  int* inverted_label;
-  float* reward;
-  float* base_reward;
-  float* loss;
-  int* target_label;
-  float* target_xy;
-  unsigned char* terminated_out;
-  unsigned char* truncated_out;
-  long long* index;
-  float* reward2;           // optional per-step rollout outputs
-  unsigned char* done2;
-  // episode statistics
-  float* acc1; float* acc2; float* acc_ret;   // per-env running sums of the current episode
-  float* ep_avg1; float* ep_final1; float* ep_avg2; float* ep_final2; float* ep_return;
-  int* first_correct; int* last_incorrect;
-  double* stats;            // (APG_NUM_STATS) shard-wide sums
-  float inv_k;              // float32(1 / num_classes)
-  // overlay
-  int* stamp_xy;
-  float* stamp_q;
-  unsigned* visited;
-  unsigned* err;
-};
-
-// scipy find_indices on the grid g[k] = k - off (see oracle/image_oracle.py:tap_indices)
-__device__ __forceinline__ void tap(double coord, double off, int len, int& k_out, double& w_out) {
-  int k = (int)floor(coord + off);
-  if ((double)k - off > coord) k -= 1;
-  else if ((double)(k + 1) - off <= coord) k += 1;
-  k = max(0, min(k, len - 2));
-  k_out = k;
-  w_out = coord - ((double)k - off);
-}
-
-// Row taps of uint8 banks keep the unclamped index len-1 when the coordinate sits exactly on the last grid point (the
-// sensor touches the bottom edge): scipy's clamped tap (len-2, w = 1) and this one (len-1, w = 0) blend the same row
-// with the same products, the other row gets weight +0 (finite uint8 pixels, exact), and the tap rows stay
-// CONSECUTIVE, which is what the fast blend variants need.  Readers of row k+1 must not leave the image.
-__device__ __forceinline__ void tap_row(double coord, double off, int len, bool keep_last, int& k_out, double& w_out) {
-  int k = (int)floor(coord + off);
-  if ((double)k - off > coord) k -= 1;
-  else if ((double)(k + 1) - off <= coord) k += 1;
-  k = max(0, min(k, keep_last ? len - 1 : len - 2));
-  k_out = k;
-  w_out = coord - ((double)k - off);
-}
-
-// bank pixel -> the float64 value the reference blends with: float64(float32(u8) / 255) or float64(f32 pixel).
-// float32(u8)/255 is reproduced exactly for all 256 values by q0 = u*r, q = fma(fma(-255, q0, u), r, q0) with
-// r = float32(1/255): no table, no division.
-__device__ __forceinline__ double px_to_f64(unsigned char u) {
-  const float r = 0.003921568859368563f;  // float32(1)/float32(255)
-#ifndef APG_ALU_CONVERSIONS
-  const float uf = (float)u;
-#else
-  // integer -> float without the conversion unit: 2^23 + u is exact in float32
-  const float uf = __fsub_rn(__uint_as_float(0x4B000000u | (unsigned)u), 8388608.0f);
-#endif
-  const float q0 = __fmul_rn(uf, r);
-  const float e = __fmaf_rn(-255.0f, q0, uf);
-  const float q = __fmaf_rn(e, r, q0);
-#ifndef APG_ALU_CONVERSIONS
-  return (double)q;
-#else
-  // exact float32 -> float64 widening by re-biasing the exponent (q is 0 or a normal float >= 1/255).  Measured on
-  // B200: trading the 3 conversion-pipe instructions for 8 ALU/FMA ones is 3 % SLOWER (the loop is issue-bound), so
-  // this variant is compiled only with -DAPG_ALU_CONVERSIONS
-  const unsigned b = __float_as_uint(q);
-  const unsigned hi = b ? ((b >> 3) + 0x38000000u) : 0u;
-  return __hiloint2double((int)hi, (int)(b << 29));
-#endif
-}
-__device__ __forceinline__ double px_to_f64(float v) { return (double)v; }
-
-struct __align__(16) Tap {
-  union {
-    double w;  // exact blend: normalised distance to the lower grid point (float64, like scipy)
-    struct {
-      float wf, omwf;  // float32 blend: w and 1 - w, each rounded once from the float64 values
-    };
-  };
-  int k;  // tap index relative to the staged tile (row) / absolute column
-  int pad;
-};
-
-struct __align__(16) EnvHdr {  // 16 bytes: the per-environment shared-memory footprint decides blocks per SM
-  unsigned short lead;   // bits 0-3: byte offset of the tile's first needed column inside the staged (aligned-down)
-                         // row; bit 15 (kNonConsec): the row taps are NOT k0, k0+1, ..., k0+S0-1
-  unsigned short nrows;  // staged rows
-  unsigned short cmin;   // first tap column of the tile
-  unsigned short rmin;   // first tap row of the tile
-  unsigned colbits[2];   // visited-mask column bits of this glimpse, words 0 and 1 (columns {j0, j0+1} of every tap)
-};
-
-constexpr unsigned kNonConsec = 0x8000u;
-constexpr unsigned kLeadMask = 15u;
-
-// float32 blend (opt-in): pixel -> float32 without the exact-division emulation; the result differs from the reference's
-// float64 blend by a few float32 ulps of the (non-negative) sum, far inside the 1e-5 relative bar.
-__device__ __forceinline__ float px_to_f32(unsigned char u) { return __fmul_rn((float)u, 0.003921568859368563f); }
-__device__ __forceinline__ float px_to_f32(float v) { return v; }
 
 template <typename BankT, int CT, bool VREUSE>
 __device__ __forceinline__ void blend_column_f32(const BankT* __restrict__ colp, const Tap* __restrict__ tp, int tap_step,
@@ -247,201 +99,6 @@ __device__ __forceinline__ void blend_column(const BankT* __restrict__ colp, con
     const float v = (sizeof(BankT) == 1) ? (float)acc : (float)fmin(fmax(acc, 0.0), 1.0);
     if (store_ok) *outp = v;
   }
-}
-
-// A block owns E consecutive environments and works in three phases per glimpse set:
-//   A  thread e: the per-environment scalars (move, loss, reward, flags, overlay stamp), the S0+S1 bilinear
-//      taps (-> shared memory) and the asynchronous staging (cp.async, LDGSTS) of the glimpse's bank footprint
-//      -- rows [i0[0], i0[S0-1]+1] x the aligned byte range covering columns [j0[0], j0[S1-1]+1] -- into the
-//      block's shared-memory tile.  All E footprints of the block are in flight at once (no registers held), which
-//      is what hides the HBM/L2 latency of the random bank gather.
-//   B  warp w walks environments w, w+4, ...; lane = (row-in-pass, column, channel) of the sensor window.  Taps come
-//      from the tile (LDS.U8), with one sensor row per pass the bottom taps of row i are the top taps of row i+1;
-//      the blend is the reference's 4-term float64 sum in the same order (bit-exact pixels); each output row is one
-//      contiguous run of stores.  The visited bitmask rows of the environment are updated by the warp.
-// The per-environment scalar work of one step is two INDEPENDENT chains with disjoint state, so that two threads can run
-// them side by side (and neither waits for the other's memory round trips):
-//   env_move   position state: pre-move overlay stamp, float64 position update, bank index; leaves the glimpse position
-//              (px, py), the target centre (tcx, tcy; localization reset steps) and the bank index behind -- everything
-//              the taps / staging need;
-//   env_loss   labels / targets, loss, reward, flags, overlay colour, episode statistics.
-// Both read the (read-only) action; env_move alone touches pos / st_idx, env_loss alone st_label / st_target / acc*.
-__device__ __forceinline__ void env_move(const ImgParams& p, int n, double& px, double& py, double& tcx, double& tcy,
-                                         int& idx, unsigned& err) {
-  if (p.mode == 0) {
-    const float2 aa = reinterpret_cast<const float2*>(p.action)[n];
-    const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
-    idx = p.st_idx[n];
-    px = pp.x;
-    py = pp.y;
-    const float a0 = aa.x, a1 = aa.y;
-    if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
-    if (p.track) {  // overlay stamp of the PRE-move position
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
-    }
-    const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
-    float q0 = a0, q1 = a1;
-    if (m > 1.0f) {
-      const float den = fmaxf(m, 1.0f);
-      q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
-      q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
-    }
-    px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
-    py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
-  } else {
-    const long long ni = p.new_idx[n];
-    const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[n];
-    idx = (int)ni;
-    px = pp.x;
-    py = pp.y;
-    p.st_idx[n] = idx;
-    p.index[n] = ni;
-    if (p.task != APG_TASK_CLASSIFICATION) {
-      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
-      tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
-      tcy = (double)nt.y * p.lim_y;
-    }
-  }
-  reinterpret_cast<double2*>(p.pos)[n] = make_double2(px, py);
-  reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
-}
-
-__device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_stats, bool ep_end, unsigned& err) {
-  float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
-  float m1 = 0.0f, m2 = 0.0f;  // LogWrapper metrics of this step
-  double neg_loss_d = 0.0;
-  const bool cls = p.task == APG_TASK_CLASSIFICATION;
-  // Everything an ordinary step reads is requested here, back to back, before the first store: loads that sit behind
-  // stores they might alias cost one memory round trip each.
-  float2 in_action = make_float2(0.f, 0.f), in_pred2 = make_float2(0.f, 0.f), in_target = make_float2(0.f, 0.f);
-  float in_acc1 = 0.0f, in_acc2 = 0.0f, in_accr = 0.0f, x_first = 0.0f, x_last = 0.0f;
-  int in_fc = -1, in_lic = -1, label = 0;
-  if (p.mode == 0) {
-    in_action = reinterpret_cast<const float2*>(p.action)[n];
-    if (p.t_stamp != 0) {
-      in_acc1 = p.acc1[n];
-      in_acc2 = p.acc2[n];
-      in_accr = p.acc_ret[n];
-      if (cls) {
-        in_fc = p.first_correct[n];
-        in_lic = p.last_incorrect[n];
-      }
-    }
-    if (cls) label = p.st_label[n];
-  }
-  if (cls && p.mode != 2) {  // pulls the environment's logits into L1 with the other inputs
-    x_first = p.pred[(size_t)n * p.K];
-    x_last = p.pred[(size_t)n * p.K + p.K - 1];
-  }
-  if (!cls && p.mode != 2) {
-    in_target = reinterpret_cast<const float2*>(p.st_target)[n];
-    in_pred2 = reinterpret_cast<const float2*>(p.pred)[n];
-  }
-  // ---- labels / targets and the loss (the reset step still charges a loss)
-  if (cls) {
-    unsigned char inv = 0;
-    if (p.mode != 0) {
-      label = p.bank_labels[(int)p.new_idx[n]];
-      if (p.invert) {
-        inv = p.new_inv[n];
-        if (inv) label = p.K - label - 1;
-      }
-      p.st_label[n] = label;
-    }
-    if (p.invert) p.inverted_label[n] = (p.mode == 0) ? 2 : (int)inv;
-    p.target_label[n] = label;
-    if (p.mode != 2) {
-      const float* x = p.pred + (size_t)n * p.K;
-      float mx = fmaxf(x_first, x_last);
-      bool has_nan = isnan(x_first) || isnan(x_last);
-      for (int k = 1; k < p.K - 1; ++k) {
-        const float v = x[k];
-        has_nan |= isnan(v);
-        mx = fmaxf(mx, v);
-      }
-      if (has_nan) err |= APG_FLAG_NAN_PRED;
-      if (!isfinite(mx)) mx = 0.0f;
-      float s = 0.0f;
-      for (int k = 0; k < p.K; ++k) s = __fadd_rn(s, expf(__fsub_rn(x[k], mx)));
-      const float tl = __fsub_rn(x[label], mx);
-      const float ce = -__fsub_rn(tl, logf(s));  // -log_softmax(x)[label], float32 like scipy
-      pq = __fdiv_rn(expf(tl), s);               // softmax(x)[label], overlay colour only
-      const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
-      loss_f = (float)loss_d;
-      neg_loss_d = -loss_d;
-      m1 = pq;                            // correct_label_prob (active_classification_env.py:157-161)
-      m2 = (pq > p.inv_k) ? 1.0f : 0.0f;  // accuracy (:166-168)
-    }
-  } else {
-    if (p.mode != 2) {
-      const float t0 = in_target.x, t1 = in_target.y;
-      const float2 qq = in_pred2;
-      if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
-      const float d0 = __fsub_rn(qq.x, t0), d1 = __fsub_rn(qq.y, t1);
-      const float ss = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
-      loss_f = __fadd_rn(__fmul_rn(__fdiv_rn(ss, 2.0f), p.mse_scale), p.mse_offset);
-      m1 = __fsqrt_rn(ss);       // euclidean_distance (active_regression_env.py:211)
-      m2 = __fdiv_rn(ss, 2.0f);  // mse (:212)
-      if (p.mode == 0 && p.track)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64)
-        pq = (float)fmin(fmax(1.0 - (double)__fsqrt_rn(ss) / 2.0, 0.0), 1.0);
-      reinterpret_cast<float2*>(p.target_xy)[n] = make_float2(t0, t1);
-    }
-    if (p.mode != 0) {
-      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
-      reinterpret_cast<float2*>(p.st_target)[n] = nt;
-      if (p.mode == 2) reinterpret_cast<float2*>(p.target_xy)[n] = nt;
-    }
-  }
-  if (p.mode == 0) {
-    const float a0 = in_action.x, a1 = in_action.y;
-    if (p.track) p.stamp_q[(size_t)p.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
-    const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
-    base = __fmul_rn(-m, 1e-3f);
-  }
-  if (p.mode != 2) {
-    float reward_f;
-    // classification: float32 base - float64 loss -> float64; localization stays float32 except on the reset
-    // step, whose base reward is np.zeros(N) (float64)
-    if (cls) reward_f = (float)((double)base + neg_loss_d);
-    else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
-    float reward_out = reward_f;
-    if (p.sparse) {  // base_reward - loss * weight, weight = float32(terminated)  (sparsify_wrapper.py:60-83)
-      const bool w1 = (p.mode == 0) && p.terminated;
-      if (cls) reward_out = (float)((double)base - (-neg_loss_d) * (w1 ? 1.0 : 0.0));
-      else if (p.mode == 0) reward_out = __fsub_rn(base, __fmul_rn(loss_f, w1 ? 1.0f : 0.0f));
-      else reward_out = (float)(0.0 - (double)__fmul_rn(loss_f, 0.0f));
-    }
-    p.reward[n] = reward_out;
-    p.base_reward[n] = base;
-    p.loss[n] = loss_f;
-    if (p.reward2) p.reward2[n] = reward_out;
-    if (p.done2) p.done2[n] = p.terminated;
-    // ---- episode statistics (the *VectorLogWrapper loops): real steps only, cleared by the reset step
-    if (p.mode == 0) {
-      const float a1 = __fadd_rn(in_acc1, m1);
-      const float a2 = __fadd_rn(in_acc2, m2);
-      const float ar = __fadd_rn(in_accr, reward_f);
-      if (cls) {
-        int fc = in_fc, lic = in_lic;
-        if (m2 > 0.5f) { if (fc < 0) fc = p.t_stamp; } else lic = p.t_stamp;
-        p.first_correct[n] = fc;
-        p.last_incorrect[n] = lic;
-      }
-      if (ep_end) {
-        const float nt = (float)(p.t_stamp + 1);
-        const float avg1 = __fdiv_rn(a1, nt), avg2 = __fdiv_rn(a2, nt);
-        p.ep_avg1[n] = avg1; p.ep_final1[n] = m1; p.ep_avg2[n] = avg2; p.ep_final2[n] = m2; p.ep_return[n] = ar;
-        atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)avg1); atomicAdd(&s_stats[2], (double)m1);
-        atomicAdd(&s_stats[3], (double)avg2); atomicAdd(&s_stats[4], (double)m2); atomicAdd(&s_stats[5], (double)ar);
-      } else {
-        p.acc1[n] = a1; p.acc2[n] = a2; p.acc_ret[n] = ar;
-      }
-    }
-  }
-  p.terminated_out[n] = p.terminated;
-  p.truncated_out[n] = 0;
-  p.time_step[n] = p.time_obs;
 }
 
 // Taps of one glimpse (-> shared memory) and the asynchronous staging of its bank footprint (thread = environment).
@@ -557,11 +214,6 @@ __device__ __forceinline__ void blend_column_consec_f32(const BankT* __restrict_
 // samples).  Split: the environment's thread only does the scalars and the tile header (first / last tap per axis);
 // after a barrier ALL threads compute the taps (one tap per work item) and issue the copies (one 16-byte chunk per item,
 // consecutive threads -> consecutive chunks of a row).
-struct __align__(16) EnvCtr {  // two 16-byte halves: what the tap items read / what the copy items read
-  double ccx, ccy;   // sensor centre (pixels)
-  long long src0;    // byte offset of the tile's first copied byte inside the bank
-  int span, nrows;   // bytes per tile row to copy (multiple of 16), tile rows
-};
 
 template <typename BankT>
 __device__ __forceinline__ void stage_head(const ImgParams& p, int el, EnvHdr* s_hdr, EnvCtr* s_ctr, double ccx, double ccy,
@@ -774,18 +426,6 @@ __device__ __forceinline__ void blend_env_warp(const ImgParams& p, const WarpLan
   }
 }
 
-// Programmatic dependent launch: consecutive vector steps are launched back to back on one stream; with the launch
-// attribute set, the blocks of step k+1 are scheduled while step k drains and park here until step k's memory is
-// visible.  Every block lets its own dependents go at once (they wait at the same place).
-__device__ __forceinline__ void grid_dependency_wait(int pdl) {
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
-  if (pdl) {
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
-  }
-#endif
-}
-
 // Two-kernel variant of the warp-per-environment path (split == 2): the scalar chains and the tile headers of ALL
 // environments, one thread each.  Inside the blend kernel this work occupied one warp of eight for ~18 % of a block's
 // lifetime (memory round trip + serial float64 taps) with the other seven parked at a barrier; here 10^5 threads hide
@@ -982,81 +622,6 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
   }
 }
 
-// Persistent, software-pipelined variant of the warp-per-environment path (large glimpses): the block walks its tiles of
-// E environments with two shared-memory stages; warp 0 PRODUCES tile k+1 (per-environment scalars, taps, cp.async staging
-// of the bank footprints, wait) while warps 1..8 CONSUME tile k (blend + stores + visited mask).  The serial, latency-bound
-// producer phase of one tile is hidden behind the throughput-bound blend of the previous one; one __syncthreads per
-// pipeline step hands the stages over.
-constexpr int kPipeConsumers = 8;
-constexpr int kPipeThreads = (kPipeConsumers + 1) * 32;
-
-template <typename BankT>
-__global__ void __launch_bounds__(kPipeThreads) image_step_pipelined_kernel(const ImgParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int n_tiles = (p.N + p.E - 1) / p.E;
-  const bool two_sets = (p.task == APG_TASK_LOCALIZATION) && (p.mode != 0);
-  const int n_sets = two_sets ? 2 : 1;
-  const size_t hdr_bytes = (size_t)p.E * sizeof(EnvHdr), taps_bytes = (size_t)p.E * (p.S0 + p.S1) * sizeof(Tap);
-  const size_t stage_bytes = hdr_bytes + taps_bytes + (size_t)p.E * p.tile_bytes;
-
-  __shared__ double s_stats[6];
-  const bool ep_end = (p.mode == 0) && p.terminated;
-  if (tid < 6) s_stats[tid] = 0.0;
-  __syncthreads();
-
-  // producer-lane state of the tile being produced (survives from the observation set to the target set)
-  double px = 0.0, py = 0.0, tcx = 0.0, tcy = 0.0;
-  int idx = 0;
-  const WarpLane L = warp_lane<BankT>(p, lane);
-
-  int prod_tile = blockIdx.x, prod_set = 0;
-  int cons_tile = -1, cons_set = 0;
-  for (int q = 0;; ++q) {
-    const bool have_prod = prod_tile < n_tiles;
-    const bool have_cons = cons_tile >= 0;
-    if (!have_prod && !have_cons) break;
-    unsigned char* st_p = smem_raw + (size_t)(q & 1) * stage_bytes;        // stage being filled
-    unsigned char* st_c = smem_raw + (size_t)((q & 1) ^ 1) * stage_bytes;  // stage filled in the previous step
-    if (warp == 0) {
-      if (have_prod) {
-        const int env0 = prod_tile * p.E;
-        const int nE = min(p.E, p.N - env0);
-        if (lane < nE) {
-          unsigned err = 0;
-          if (prod_set == 0) {
-            env_move(p, env0 + lane, px, py, tcx, tcy, idx, err);
-            env_loss(p, env0 + lane, s_stats, ep_end, err);
-          }
-          stage_env<BankT>(p, lane, reinterpret_cast<EnvHdr*>(st_p), reinterpret_cast<Tap*>(st_p + hdr_bytes),
-                           st_p + hdr_bytes + taps_bytes, prod_set == 0 ? px * p.lim_x : tcx,
-                           prod_set == 0 ? py * p.lim_y : tcy, idx, err);
-          if (err) atomicOr(p.err, err);
-        }
-        __pipeline_commit();
-        __pipeline_wait_prior(0);
-      }
-    } else if (have_cons) {
-      const int env0 = cons_tile * p.E;
-      const int nE = min(p.E, p.N - env0);
-      float* out_set = (cons_set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env0 * p.P;
-      for (int el = warp - 1; el < nE; el += kPipeConsumers)
-        blend_env_warp<BankT>(p, L, lane, el, env0 + el, cons_set, reinterpret_cast<const EnvHdr*>(st_c),
-                              reinterpret_cast<const Tap*>(st_c + hdr_bytes), st_c + hdr_bytes + taps_bytes,
-                              out_set + el * p.P);
-    }
-    __syncthreads();
-    cons_tile = have_prod ? prod_tile : -1;
-    cons_set = prod_set;
-    if (have_prod && ++prod_set == n_sets) {
-      prod_set = 0;
-      prod_tile += gridDim.x;
-    }
-  }
-  if (ep_end && tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);  // one RED per block and statistic
-}
 
 }  // namespace
 
@@ -1066,12 +631,17 @@ __global__ void __launch_bounds__(kPipeThreads) image_step_pipelined_kernel(cons
 struct apg_image_env {
   apg_image_cfg cfg{};
   cudaStream_t stream = nullptr;
-  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1, pipelined = 0, pipe_grid = 0;
-  size_t pipe_smem = 0;
+  int P = 0, words = 0, E = 0, bank_pitch = 0, pitch = 0, tile_rows = 0, thread_blend = 0, threads = 0, tb = 1;
   int split = 0, ctr_off = 0, spec = 0, tile_bytes = 0, tb_consec = 1, pdl = 1;
   void* d_ghdr = nullptr;
   void* d_gctr = nullptr;
   size_t smem = 0;
+  // large glimpses on uint8 banks: TMA-staged persistent kernel (csrc/apg_image_tma.cu)
+  apg_img::TmaPlan tma;
+  // small glimpses, classification, uint8 single-channel banks: persistent rollout kernel (csrc/apg_image_small.cu)
+  apg_img::SmallPlan small;
+  void* d_thdr = nullptr;
+  int force_slow = 0;
   // bank
   void* d_bank = nullptr;
   int32_t* d_bank_labels = nullptr;
@@ -1093,6 +663,9 @@ struct apg_image_env {
     uint8_t* d_inv = nullptr;
     unsigned char* h_pin = nullptr;  // pinned staging: idx | pos | target | inv
     cudaEvent_t copied = nullptr;
+    bool drawn = false;              // drawn from the reset streams (not queued by the caller)
+    int snap = 0;                    // device mode: d_streams entry the payload was drawn from
+    apg::Pcg64 h_snap[3];            // host mode: the stream states before the payload
   };
   std::vector<Slot> ring;
   int ring_head = 0, ring_count = 0;
@@ -1102,14 +675,13 @@ struct apg_image_env {
   // numpy-compatible reset streams (optional): autoreset payloads are drawn by the engine when the ring is empty
   apg::Pcg64 g0{}, g1{}, g2{};
   bool have_streams = false;
-  // device-side payload generation (csrc/apg_payload.cu): the stream states live in d_streams while streams_on_device
+  // device-side payload generation (csrc/apg_payload.cu): see configure_rng
   apg::Pcg64* d_streams = nullptr;
-  apg::Pcg64 h_streams[3];
   unsigned* d_words = nullptr;
   unsigned* d_rej = nullptr;
-  size_t words_cap = 0;
-  bool streams_on_device = false;
-  int pp = 0;  // which half of d_streams / d_rej holds the current states / the clean rejection list
+  bool device_rng = false;
+  int cur = 0;  // d_streams entry holding the current states
+  int pp = 0;   // which half of d_rej is the clean rejection list
   bool host_rng = false;  // APG_IMG_HOST_RNG=1: always draw payloads on the host
   int64_t global_n = 0, env_offset = 0;
   std::vector<int64_t> h_idx;
@@ -1155,25 +727,13 @@ int stage_payload(apg_image_env* e, apg_image_env::Slot& s, const int64_t* h_idx
   return APG_OK;
 }
 
-// mode: 0 move, 1 autoreset, 2 explicit reset
-int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pred,
-           const apg_image_env::Slot* slot, float* reward2, uint8_t* done2) {
+// everything of the kernel parameter block that does not depend on the step
+void fill_params(const apg_image_env* e, ImgParams& p, int mode, const float* d_action, const float* d_pred,
+                 const apg_image_env::Slot* slot, float* reward2, uint8_t* done2) {
   const apg_image_cfg& c = e->cfg;
-  ImgParams p{};
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.pdl = e->pdl; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode;
-  int t_after;
-  if (mode == 0) {
-    p.t_stamp = e->t;
-    t_after = e->t + 1;
-    p.terminated = (t_after >= c.step_limit) ? 1 : 0;
-  } else {
-    p.t_stamp = 0;
-    t_after = 0;
-    p.terminated = 0;
-  }
-  p.time_obs = (float)(((double)t_after / (double)c.step_limit) * 2.0 - 1.0);
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.pdl = e->pdl; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode; p.t_hdr = e->d_thdr; p.force_slow = e->force_slow;
   p.scale = c.sensor_scale;
   p.msl_x = c.max_step_length[0]; p.msl_y = c.max_step_length[1];
   // sensor_pos_lim_pixels (image_perception_module.py:419-423): x uses sensor_size[0], y uses sensor_size[1]
@@ -1213,6 +773,36 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return;
   p.first_correct = e->b.d_first_correct; p.last_incorrect = e->b.d_last_incorrect; p.stats = e->d_stats;
   p.inv_k = (float)(1.0 / (double)(c.num_classes > 0 ? c.num_classes : 1));
+}
+
+// mode: 0 move, 1 autoreset, 2 explicit reset
+int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pred,
+           const apg_image_env::Slot* slot, float* reward2, uint8_t* done2) {
+  const apg_image_cfg& c = e->cfg;
+  ImgParams p{};
+  fill_params(e, p, mode, d_action, d_pred, slot, reward2, done2);
+  if (e->small.spec) {  // explicit reset through the persistent kernel (steps go through rollout_small)
+    apg_img::SmallRollout ro{};
+    ro.n_steps = 1; ro.t0 = 0; ro.need_reset0 = 0; ro.first_mode = 2;
+    ro.slot_idx[0] = reinterpret_cast<const long long*>(slot->d_idx); ro.slot_pos[0] = slot->d_pos; ro.slot_inv[0] = slot->d_inv;
+    const int n = apg_img::small_launch(e->small, p, ro, e->stream);
+    if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
+    apg::count_launch(n);
+    e->t = 0;
+    e->needs_reset = false;
+    return APG_OK;
+  }
+  int t_after;
+  if (mode == 0) {
+    p.t_stamp = e->t;
+    t_after = e->t + 1;
+    p.terminated = (t_after >= c.step_limit) ? 1 : 0;
+  } else {
+    p.t_stamp = 0;
+    t_after = 0;
+    p.terminated = 0;
+  }
+  p.time_obs = (float)(((double)t_after / (double)c.step_limit) * 2.0 - 1.0);
 
   const int grid = apg::ceil_div(c.num_envs, e->E);
   // one launch path for every kernel of a step: plain, or with programmatic stream serialization (e->pdl)
@@ -1226,19 +816,21 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
     cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, p);
   };
-  if (e->split == 2 && !e->pipelined) {
+  if (e->tma.spec && e->tma.have_map) {
+    const int n = apg_img::tma_launch_step(e->tma, p, e->stream);
+    if (n < 0) return apg::fail(APG_ERR_CUDA, "image step kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
+    apg::count_launch(n);
+    e->t = t_after;
+    e->needs_reset = (mode == 0) && p.terminated;
+    return APG_OK;
+  }
+  if (e->split == 2) {
     const int hgrid = apg::ceil_div(c.num_envs, 256);
     if (c.bank_dtype == APG_BANK_U8) go(image_head_kernel<unsigned char>, hgrid, 256, 0);
     else go(image_head_kernel<float>, hgrid, 256, 0);
     apg::count_launch();
   }
-  if (e->pipelined) {
-    const int pgrid = grid < e->pipe_grid ? grid : e->pipe_grid;
-    if (c.bank_dtype == APG_BANK_U8)
-      image_step_pipelined_kernel<unsigned char><<<pgrid, kPipeThreads, e->pipe_smem, e->stream>>>(p);
-    else
-      image_step_pipelined_kernel<float><<<pgrid, kPipeThreads, e->pipe_smem, e->stream>>>(p);
-  } else if (c.bank_dtype == APG_BANK_U8) {
+  if (c.bank_dtype == APG_BANK_U8) {
     if (e->spec == 1) go(image_step_kernel<unsigned char, 10, 10, 3>, grid, e->threads, e->smem);
     else if (e->spec == 2) go(image_step_kernel<unsigned char, 5, 5, 1>, grid, e->threads, e->smem);
     else go(image_step_kernel<unsigned char, 0, 0, 0>, grid, e->threads, e->smem);
@@ -1252,48 +844,71 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   return APG_OK;
 }
 
+// ---- the reference's three reset-path Generators ---------------------------------------------------------------------
+// Device mode (the normal case): the states live in d_streams, (ring + 1) x 3 entries -- entry `cur` holds the states
+// after every payload drawn so far, and the entry a payload was drawn FROM stays intact until that payload has been
+// consumed, so that the streams can be rewound to the oldest unconsumed payload (apg_image_get_streams, explicit reset).
+// Everything is allocated and uploaded by configure_rng (bank / stream setup time): nothing on the step path allocates,
+// synchronises or loads a kernel for the first time.
+int configure_rng(apg_image_env* e) {
+  e->device_rng = false;
+  if (!e->have_streams || !e->d_bank) return APG_OK;
+  if (e->host_rng || !apg::payload_device_ok((unsigned long long)e->n_items, e->global_n)) return APG_OK;
+  const size_t n_states = 3 * (e->ring.size() + 1);
+  if (!e->d_streams) {
+    APG_CUDA(cudaMalloc(&e->d_streams, n_states * sizeof(apg::Pcg64)));
+    APG_CUDA(apg::dev_alloc(&e->d_rej, 2 * ((size_t)apg::kPayloadSlack + 1)));
+    APG_CUDA(cudaMalloc(&e->d_words, apg::payload_scratch_words(e->cfg.num_envs) * sizeof(unsigned)));
+    APG_CUDA(apg::payload_preload());
+  }
+  apg::Pcg64 h[3] = {e->g0, e->g1, e->g2};
+  APG_CUDA(cudaMemcpyAsync(e->d_streams + 3 * e->cur, h, sizeof(h), cudaMemcpyHostToDevice, e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  e->device_rng = true;
+  return APG_OK;
+}
+
+// host copies of the current states (device mode: fetched from entry `cur`; synchronises the stream)
+int streams_to_host(apg_image_env* e) {
+  if (!e->device_rng) return APG_OK;
+  apg::Pcg64 h[3];
+  APG_CUDA(cudaMemcpyAsync(h, e->d_streams + 3 * e->cur, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  e->g0 = h[0]; e->g1 = h[1]; e->g2 = h[2];
+  return APG_OK;
+}
+
+// Drops the queued payloads that were drawn from the streams and rewinds the streams to the state before the oldest
+// of them (payloads queued by the caller are the caller's business: they make the rewind impossible).
+int rewind_streams(apg_image_env* e) {
+  if (e->ring_count == 0) return APG_OK;
+  for (int i = 0; i < e->ring_count; ++i)
+    APG_CHECK(e->ring[(e->ring_head + i) % (int)e->ring.size()].drawn, APG_ERR_STATE,
+              "%d caller-queued reset payloads are pending", e->ring_count);
+  const apg_image_env::Slot& first = e->ring[e->ring_head];
+  if (e->device_rng) {
+    e->cur = first.snap;
+    // the rejection list of the half `pp` points at was cleared by the last payload that was drawn: still clean
+  } else {
+    e->g0 = first.h_snap[0]; e->g1 = first.h_snap[1]; e->g2 = first.h_snap[2];
+  }
+  e->ring_count = 0;
+  return APG_OK;
+}
+
 // One autoreset payload from the reference's streams, in the reference's draw order, for the global batch; this
 // shard keeps its slice.  (image_localization.py:153-156 -> dataset_iterator.py:57 -> image_perception_module.py:131-133
 // -> :159-161)
-int streams_to_host(apg_image_env* e) {
-  if (!e->streams_on_device) return APG_OK;
-  APG_CUDA(cudaMemcpyAsync(e->h_streams, e->d_streams + 3 * e->pp, sizeof(e->h_streams), cudaMemcpyDeviceToHost, e->stream));
-  APG_CUDA(cudaStreamSynchronize(e->stream));
-  e->g0 = e->h_streams[0]; e->g1 = e->h_streams[1]; e->g2 = e->h_streams[2];
-  e->streams_on_device = false;
-  return APG_OK;
-}
-
-int streams_to_device(apg_image_env* e) {
-  if (e->streams_on_device) return APG_OK;
-  const size_t need = apg::payload_scratch_words(e->global_n);
-  if (!e->d_streams) {
-    APG_CUDA(cudaMalloc(&e->d_streams, 2 * sizeof(e->h_streams)));
-    APG_CUDA(apg::dev_alloc(&e->d_rej, 2 * ((size_t)apg::kPayloadSlack + 1)));
-  }
-  if (need > e->words_cap) {
-    if (e->d_words) cudaFree(e->d_words);
-    e->d_words = nullptr;
-    APG_CUDA(cudaMalloc(&e->d_words, need * sizeof(unsigned)));
-    e->words_cap = need;
-  }
-  APG_CUDA(cudaStreamSynchronize(e->stream));  // h_streams may still feed an earlier upload
-  e->h_streams[0] = e->g0; e->h_streams[1] = e->g1; e->h_streams[2] = e->g2;
-  APG_CUDA(cudaMemcpyAsync(e->d_streams + 3 * e->pp, e->h_streams, sizeof(e->h_streams), cudaMemcpyHostToDevice, e->stream));
-  e->streams_on_device = true;
-  return APG_OK;
-}
-
 int generate_payload(apg_image_env* e) {
   APG_CHECK(e->have_streams, APG_ERR_NEED_PAYLOAD, "no reset payload queued and no reset streams set");
   APG_CHECK(e->ring_count < (int)e->ring.size(), APG_ERR_STATE, "reset payload ring is full");
-  if (!e->host_rng && apg::payload_device_ok((unsigned long long)e->n_items, e->global_n)) {
+  apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
+  if (e->device_rng) {
     // drawn on the device, in-stream, bit-identical to the numpy draws below (tests/test_rng_gpu.py)
-    int rc = streams_to_device(e);
-    if (rc != APG_OK) return rc;
-    apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
+    const int n_states = (int)e->ring.size() + 1;
+    const int next = (e->cur + 1) % n_states;
     apg::PayloadArgs a{};
-    a.streams = e->d_streams + 3 * e->pp; a.streams_out = e->d_streams + 3 * (e->pp ^ 1); a.Ng = e->global_n; a.off = e->env_offset; a.N = e->cfg.num_envs;
+    a.streams = e->d_streams + 3 * e->cur; a.streams_out = e->d_streams + 3 * next; a.Ng = e->global_n; a.off = e->env_offset; a.N = e->cfg.num_envs;
     a.M = (unsigned long long)e->n_items; a.loc = e->cfg.task == APG_TASK_LOCALIZATION ? 1 : 0;
     a.inv = e->cfg.randomly_invert_labels ? 1 : 0;
     a.d_idx = reinterpret_cast<long long*>(s.d_idx); a.d_pos = s.d_pos; a.d_target = s.d_target; a.d_inv = s.d_inv;
@@ -1304,13 +919,12 @@ int generate_payload(apg_image_env* e) {
     const int n = apg::launch_device_payload(a, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "payload kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
+    s.drawn = true; s.snap = e->cur;
+    e->cur = next;
     e->ring_count += 1;
     return APG_OK;
   }
-  {
-    int rc = streams_to_host(e);
-    if (rc != APG_OK) return rc;
-  }
+  s.h_snap[0] = e->g0; s.h_snap[1] = e->g1; s.h_snap[2] = e->g2;
   const int64_t N = e->cfg.num_envs, Ng = e->global_n, off = e->env_offset;
   const bool loc = e->cfg.task == APG_TASK_LOCALIZATION, inv = e->cfg.randomly_invert_labels != 0;
   e->h_idx.resize(N); e->h_pos.resize(2 * N);
@@ -1334,15 +948,66 @@ int generate_payload(apg_image_env* e) {
   apg::pcg64_advance(e->g1, (uint64_t)(2 * off));  // g1.uniform(-1, 1, (Ng, 2))
   for (int64_t i = 0; i < 2 * N; ++i) e->h_pos[i] = apg::rng_uniform(e->g1, -1.0, 2.0);
   apg::pcg64_advance(e->g1, (uint64_t)(2 * (Ng - off - N)));
-  apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
   int rc = stage_payload(e, s, e->h_idx.data(), e->h_pos.data(), loc ? e->h_target.data() : nullptr,
                          inv ? e->h_inv.data() : nullptr);
   if (rc != APG_OK) return rc;
+  s.drawn = true;
   e->ring_count += 1;
   return APG_OK;
 }
 
+// n_steps consecutive steps of the persistent small-glimpse kernel: as few launches as the autoreset payload ring and the
+// per-launch limits allow (one for the bench's 51-step windows).  Payloads of the autoresets inside a window are drawn
+// in-stream before its launch.
+int rollout_small(apg_image_env* e, const float* d_actions, const float* d_preds, int n_steps, float* d_rewards,
+                  uint8_t* d_dones) {
+  const size_t N = e->cfg.num_envs;
+  const int ring = (int)e->ring.size();
+  const int max_resets = ring < apg_img::kSmallMaxSlots ? ring : apg_img::kSmallMaxSlots;
+  int done = 0;
+  while (done < n_steps) {
+    apg_img::SmallRollout ro{};
+    ro.t0 = e->t; ro.need_reset0 = e->needs_reset ? 1 : 0; ro.first_mode = 0;
+    int t = e->t, m = 0, resets = 0;
+    bool need = e->needs_reset;
+    while (done + m < n_steps && m < apg_img::kSmallMaxSteps) {
+      if (need) {
+        if (resets == max_resets) break;
+        ro.reset_slot[m] = (unsigned char)resets++;
+        t = 0; need = false;
+      } else {
+        t++; need = t >= e->cfg.step_limit;
+      }
+      m++;
+    }
+    while (e->ring_count < resets) {
+      APG_CHECK(e->have_streams, APG_ERR_NEED_PAYLOAD,
+                "autoreset step is due but no reset payload is queued (apg_image_queue_reset_payload)");
+      int rc = generate_payload(e);
+      if (rc != APG_OK) return rc;
+    }
+    for (int i = 0; i < resets; ++i) {
+      const apg_image_env::Slot& s = e->ring[(e->ring_head + i) % ring];
+      ro.slot_idx[i] = reinterpret_cast<const long long*>(s.d_idx); ro.slot_pos[i] = s.d_pos; ro.slot_inv[i] = s.d_inv;
+    }
+    ro.n_steps = m;
+    ImgParams p{};
+    fill_params(e, p, 0, d_actions + (size_t)done * N * 2, d_preds + (size_t)done * N * e->pred_width, nullptr,
+                d_rewards ? d_rewards + (size_t)done * N : nullptr, d_dones ? d_dones + (size_t)done * N : nullptr);
+    const int n = apg_img::small_launch(e->small, p, ro, e->stream);
+    if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
+    apg::count_launch(n);
+    e->ring_head = (e->ring_head + resets) % ring;
+    e->ring_count -= resets;
+    e->t = t;
+    e->needs_reset = need;
+    done += m;
+  }
+  return APG_OK;
+}
+
 int step_once(apg_image_env* e, const float* d_action, const float* d_pred, float* reward2, uint8_t* done2) {
+  if (e->small.spec) return rollout_small(e, d_action, d_pred, 1, reward2, done2);
   if (e->needs_reset && e->ring_count == 0 && e->have_streams) {
     int rc = generate_payload(e);
     if (rc != APG_OK) return rc;
@@ -1413,16 +1078,13 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     size_t per_env = sizeof(EnvHdr) + (size_t)(cfg->sensor_h + cfg->sensor_w) * 16 + (size_t)e->tile_bytes;
     // small glimpses (<= 96 floats, e.g. 5x5x1 / 5x5x3): one thread blends a whole environment
     e->thread_blend = e->P <= kThreadBlendMaxP ? 1 : 0;
-    if (const char* ov = getenv("APG_IMG_THREAD_BLEND")) e->thread_blend = atoi(ov) ? 1 : 0;
     int E;
     if (e->thread_blend) {
       per_env += (size_t)(e->P | 1) * 4;  // parked output floats
       E = (int)((64 * 1024) / per_env);
       E = E >= 64 ? 64 : 32;  // swept on B200: 64 beats 32 and 128 for the 5x5x1 MNIST glimpse
       e->tb = cfg->sensor_w >= 2 ? 2 : 1;
-      if (const char* ov = getenv("APG_IMG_TB")) { const int v = atoi(ov); if (v >= 1 && v <= 4) e->tb = v; }
       e->threads = E * e->tb;
-      if (const char* ov = getenv("APG_IMG_SPLIT")) e->split = atoi(ov) == 1 ? 1 : 0;
     } else {
       // small blocks: many blocks per SM overlap each other's staging / blend phases (swept on B200: 64 envs per
       // block is best for 5x5x1 glimpses, 32 for 10x10x3 ones)
@@ -1431,16 +1093,6 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
       if (per_env > 768 && E > 32) E = 32;
       e->threads = kThreads;
       e->split = 2;  // 0: one thread per env does all of phase A; 1: taps / copies by all threads; 2: + head kernel
-      if (const char* ov = getenv("APG_IMG_SPLIT")) { const int v = atoi(ov); if (v >= 0 && v <= 2) e->split = v; }
-      if (const char* ov = getenv("APG_IMG_THREADS")) {
-        const int v = atoi(ov);
-        if (v >= 32 && v <= kThreads && v % 32 == 0) e->threads = v;
-      }
-    }
-    if (const char* ov = getenv("APG_IMG_ENVS_PER_BLOCK")) {
-      const int v = atoi(ov);
-      if (v >= 1 && v <= kThreads && (size_t)v * per_env <= 200 * 1024) E = v;
-      if (e->thread_blend) e->threads = (((E + 31) / 32) * 32) * e->tb;
     }
     E = E >= 8 ? (E & ~7) : (E >= 4 ? 4 : (E >= 2 ? 2 : 1));
     e->E = E;
@@ -1448,8 +1100,9 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     if (e->split) per_env += sizeof(EnvCtr);
     e->smem = per_env * E + (size_t)e->pitch;
     if (e->smem > 200 * 1024) {
+      const size_t need = e->smem;
       delete e;
-      return apg::fail(APG_ERR_INVALID, "sensor window too large for the shared-memory tile (%zu bytes)", e->smem);
+      return apg::fail(APG_ERR_INVALID, "sensor window too large for the shared-memory tile (%zu bytes)", need);
     }
   }
   e->pred_width = cfg->task == APG_TASK_CLASSIFICATION ? cfg->num_classes : 2;
@@ -1502,28 +1155,6 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     A(cudaMallocHost(reinterpret_cast<void**>(&s.h_pin), slot_bytes(e)));
     A(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
   }
-  if (err == cudaSuccess && !e->thread_blend) {
-    // large glimpses: persistent two-stage pipeline (one producer warp, 8 consumer warps), E = 32 environments per tile
-    const char* ov = getenv("APG_IMG_PIPELINE");
-    const size_t stage = e->smem;  // bytes of one stage at the current E
-    // measured on B200 (TinyImageNetLoc): 190.6 us vs 185.8 us for the block-staged kernel -- the blend is bound by
-    // instruction issue, not by the latency the pipeline hides -- so it is opt-in (APG_IMG_PIPELINE=1)
-    if (ov && atoi(ov) != 0 && e->E == 32 && 2 * stage <= 100 * 1024) {
-      e->pipe_smem = 2 * stage;
-      A(cudaFuncSetAttribute(image_step_pipelined_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pipe_smem));
-      A(cudaFuncSetAttribute(image_step_pipelined_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pipe_smem));
-      int sms = 0, per_sm = 0;
-      A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-      if (cfg->bank_dtype == APG_BANK_U8)
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_step_pipelined_kernel<unsigned char>, kPipeThreads, e->pipe_smem));
-      else
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_step_pipelined_kernel<float>, kPipeThreads, e->pipe_smem));
-      if (err == cudaSuccess && sms > 0 && per_sm > 0) {
-        e->pipelined = 1;
-        e->pipe_grid = sms * per_sm;
-      }
-    }
-  }
   if (err == cudaSuccess && e->smem > 48 * 1024) {
     A(cudaFuncSetAttribute(image_step_kernel<unsigned char, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     A(cudaFuncSetAttribute(image_step_kernel<unsigned char, 10, 10, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -1533,11 +1164,37 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   // compile-time geometry for the benchmark shapes
   if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 10 && cfg->sensor_w == 10 && cfg->channels == 3) e->spec = 1;
   if (cfg->bank_dtype == APG_BANK_U8 && cfg->sensor_h == 5 && cfg->sensor_w == 5 && cfg->channels == 1) e->spec = 2;
-  if (const char* ov = getenv("APG_IMG_SPEC")) { if (!atoi(ov)) e->spec = 0; }
-  if (const char* ov = getenv("APG_IMG_TB_CONSEC")) e->tb_consec = atoi(ov) ? 1 : 0;
+  // developer / test switches (none of them changes results): APG_IMG_GENERIC=1 keeps every shape on the generic staged
+  // kernels, APG_IMG_FORCE_SLOW=1 sends every environment of the TMA path through its general per-output branch,
+  // APG_IMG_HOST_RNG=1 draws the autoreset payloads on the host, APG_IMG_PDL=0 turns programmatic dependent launch off
+  const char* ov_generic = getenv("APG_IMG_GENERIC");
+  const bool generic_only = ov_generic && atoi(ov_generic) != 0;
+  if (generic_only) e->spec = 0;
+  if (const char* ov = getenv("APG_IMG_FORCE_SLOW")) e->force_slow = atoi(ov) != 0;
   if (const char* ov = getenv("APG_IMG_HOST_RNG")) e->host_rng = atoi(ov) != 0;
   if (const char* ov = getenv("APG_IMG_PDL")) e->pdl = atoi(ov) ? 1 : 0;
-  if (e->thread_blend != (e->P <= kThreadBlendMaxP ? 1 : 0)) e->spec = 0;  // path forced by APG_IMG_THREAD_BLEND
+  if (err == cudaSuccess && !generic_only && e->thread_blend && apg_img::small_plan(e->small, *cfg, e->words))
+    A(apg_img::small_preload(e->small));
+  if (err == cudaSuccess && !generic_only && !e->thread_blend) {
+    cudaError_t terr = cudaSuccess;
+    if (apg_img::tma_plan(e->tma, *cfg, e->bank_pitch, e->words, &terr)) {
+      A(cudaMalloc(&e->d_thdr, apg_img::tma_header_bytes((long long)N)));
+      A(apg_img::tma_preload(e->tma));
+    }
+    A(terr);
+  }
+  if (err == cudaSuccess) {  // load every kernel a step can launch now (lazy module loading would do it on first use)
+    cudaFuncAttributes fa;
+    if (cfg->bank_dtype == APG_BANK_U8) {
+      A(cudaFuncGetAttributes(&fa, image_head_kernel<unsigned char>));
+      A(cudaFuncGetAttributes(&fa, image_step_kernel<unsigned char, 0, 0, 0>));
+      A(cudaFuncGetAttributes(&fa, image_step_kernel<unsigned char, 10, 10, 3>));
+      A(cudaFuncGetAttributes(&fa, image_step_kernel<unsigned char, 5, 5, 1>));
+    } else {
+      A(cudaFuncGetAttributes(&fa, image_head_kernel<float>));
+      A(cudaFuncGetAttributes(&fa, image_step_kernel<float, 0, 0, 0>));
+    }
+  }
   if (err != cudaSuccess) {
     apg_image_destroy(e);
     return apg::fail(APG_ERR_CUDA, "apg_image_create: allocation failed: %s", cudaGetErrorString(err));
@@ -1555,6 +1212,7 @@ void apg_image_destroy(apg_image_env* e) {
   if (e->d_rej) cudaFree(e->d_rej);
   if (e->d_ghdr) cudaFree(e->d_ghdr);
   if (e->d_gctr) cudaFree(e->d_gctr);
+  if (e->d_thdr) cudaFree(e->d_thdr);
   if (e->own_bank) cudaFree(e->d_bank);
   if (e->own_bank) cudaFree(e->d_bank_labels);
   apg::dev_free(e->b.d_glimpse); apg::dev_free(e->b.d_target_glimpse); apg::dev_free(e->b.d_glimpse_pos);
@@ -1613,7 +1271,8 @@ int apg_image_set_bank(apg_image_env* e, const void* bank, const int32_t* labels
     APG_CUDA(cudaMemcpy(e->d_bank_labels, labels, (size_t)n_items * 4, cudaMemcpyHostToDevice));
   }
   e->n_items = n_items;
-  return APG_OK;
+  if (e->tma.spec) apg_img::tma_encode(e->tma, e->d_bank, e->bank_pitch, (long long)n_items, e->cfg.height);
+  return configure_rng(e);
 }
 
 int apg_image_reset(apg_image_env* e, const int64_t* h_idx, const double* h_pos, const float* h_target,
@@ -1644,6 +1303,7 @@ int apg_image_queue_reset_payload(apg_image_env* e, const int64_t* h_idx, const 
   apg_image_env::Slot& s = e->ring[(e->ring_head + e->ring_count) % (int)e->ring.size()];
   int rc = stage_payload(e, s, h_idx, h_pos, h_target, h_invert);
   if (rc != APG_OK) return rc;
+  s.drawn = false;
   e->ring_count += 1;
   return APG_OK;
 }
@@ -1667,20 +1327,22 @@ int apg_image_set_streams(apg_image_env* e, const apg_pcg64_state* g0, const apg
             (long long)(env_offset + e->cfg.num_envs), (long long)global_num_envs);
   APG_CHECK(e->ring_count == 0, APG_ERR_STATE, "cannot replace the reset streams while %d payloads drawn from the old ones are queued",
             e->ring_count);
+  APG_CUDA(cudaSetDevice(e->cfg.device));
   to_internal(g0, e->g0); to_internal(g1, e->g1); to_internal(g2, e->g2);
   e->global_n = global_num_envs; e->env_offset = env_offset;
   e->have_streams = true;
-  e->streams_on_device = false;  // the host copies are the truth until the next device-drawn payload
-  return APG_OK;
+  return configure_rng(e);  // device mode: scratch allocation + state upload happen here, off the step path
 }
 
 int apg_image_get_streams(apg_image_env* e, apg_pcg64_state* g0, apg_pcg64_state* g1, apg_pcg64_state* g2) {
   APG_CHECK(e && g0 && g1 && g2, APG_ERR_INVALID, "apg_image_get_streams: null argument");
   APG_CHECK(e->have_streams, APG_ERR_STATE, "no reset streams set");
-  APG_CHECK(e->ring_count == 0, APG_ERR_STATE, "%d prefetched payloads have already advanced the streams", e->ring_count);
   {
+    // payloads drawn ahead of time have advanced the streams past the reference's position: drop them and rewind
     APG_CUDA(cudaSetDevice(e->cfg.device));
-    int rc = streams_to_host(e);
+    int rc = rewind_streams(e);
+    if (rc != APG_OK) return rc;
+    rc = streams_to_host(e);
     if (rc != APG_OK) return rc;
   }
   from_internal(e->g0, g0); from_internal(e->g1, g1); from_internal(e->g2, g2);
@@ -1721,6 +1383,7 @@ int apg_image_rollout(apg_image_env* e, const float* d_actions, const float* d_p
     APG_CHECK(e->have_streams || resets <= e->ring_count, APG_ERR_NEED_PAYLOAD,
               "rollout of %d steps needs %d reset payloads, %d queued", n_steps, resets, e->ring_count);
   }
+  if (e->small.spec) return rollout_small(e, d_actions, d_preds, n_steps, d_rewards, d_dones);
   const size_t N = e->cfg.num_envs;
   for (int k = 0; k < n_steps; ++k) {
     int rc = step_once(e, d_actions + (size_t)k * N * 2, d_preds + (size_t)k * N * e->pred_width,
@@ -1783,7 +1446,12 @@ int apg_image_bank_info(apg_image_env* e, const void** d_bank, int32_t* bank_pit
   return APG_OK;
 }
 
-int apg_image_variant(apg_image_env* e) { return !e ? APG_ERR_INVALID : (e->thread_blend ? 1 : (e->pipelined ? 2 : 0)); }
+int apg_image_variant(apg_image_env* e) {
+  if (!e) return APG_ERR_INVALID;
+  if (e->tma.spec && e->tma.have_map) return 3;
+  if (e->small.spec) return 4;
+  return e->thread_blend ? 1 : 0;
+}
 
 int apg_image_sync(apg_image_env* e) {
   APG_CHECK(e, APG_ERR_INVALID, "null env");

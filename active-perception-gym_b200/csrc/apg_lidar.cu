@@ -31,6 +31,7 @@ constexpr int kEnvsPerBlock = 32;
 
 struct LidarParams {
   int N, W, H, words, B, G, T, M;
+  int pad, pw, prows;  // shared-memory maps carry a free border of `pad` cells: (H + 2 pad) rows of pw words
   int static_map, static_idx, emit_cells, sparse;
   int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams), 3 = explicit reset (keep streams)
   float range;
@@ -73,14 +74,17 @@ struct LidarParams {
   unsigned* err;
 };
 
+// One environment's occupancy bitmap in shared memory with a FREE border of `pad` cells on every side: a ray of length
+// <= lidar_range that starts inside the map never leaves the padded bitmap, so the walk needs no bounds test (cells
+// outside the map are free: the reference's union only has in-map boxes).  Coordinates passed to is_wall are PADDED
+// cell coordinates (x + pad, y + pad).
 struct MapView {
-  const unsigned* bits;  // shared memory, H*words
-  int W, H, words;
+  const unsigned* bits;  // shared memory, (H + 2 pad) rows of pw words
+  int pw, pad;
 };
 
-__device__ __forceinline__ int is_wall(const MapView& m, int x, int y) {
-  if ((unsigned)x >= (unsigned)m.W || (unsigned)y >= (unsigned)m.H) return 0;
-  return (int)((m.bits[y * m.words + (x >> 5)] >> (x & 31)) & 1u);
+__device__ __forceinline__ int is_wall(const MapView& m, int xp, int yp) {
+  return (int)((m.bits[yp * m.pw + (xp >> 5)] >> (xp & 31)) & 1u);
 }
 
 __device__ __forceinline__ float norm2f(float a, float b) {
@@ -93,8 +97,11 @@ struct WalkState {
   double iv_t0, fex, fey;
 };
 
-// The grid walk of scan_one from the start cell to the end of the segment.  NB = the ray runs along a grid line, so the
-// cells on its other side touch it too (general, rare); NB = false drops those lookups from the loop.
+// The grid walk of scan_one from the start cell to the end of the segment (cell coordinates are padded ones).  NB = the
+// ray runs along a grid line, so the cells on its other side touch it too (general, rare); NB = false drops those
+// lookups from the loop.  An ordinary iteration is: next crossing, step the cell, one bit test, the crossing parameter
+// of the next grid line -- the interval bookkeeping of oracle/lidar_oracle.c runs only when the wall state changes or
+// a lattice corner is touched (about twice per ray).
 template <bool NB>
 __device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px, double py, double dx, double dy, int sx,
                                      int sy, double inv_dx, double inv_dy, bool nbx, bool nby) {
@@ -102,7 +109,8 @@ __device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px,
   bool have_first = ws.have_first, in_iv = ws.in_iv;
   double iv_t0 = ws.iv_t0, fex = ws.fex, fey = ws.fey;
   const double sxd = (double)sx, syd = (double)sy;
-  double gx = (double)(sx > 0 ? cx + 1 : cx), gy = (double)(sy > 0 ? cy + 1 : cy);  // next grid lines (exact integers)
+  // next grid lines in MAP coordinates (exact integers)
+  double gx = (double)((sx > 0 ? cx + 1 : cx) - m.pad), gy = (double)((sy > 0 ? cy + 1 : cy) - m.pad);
   double tX = sx != 0 ? (gx - px) * inv_dx : INFINITY;
   double tY = sy != 0 ? (gy - py) * inv_dy : INFINITY;
   for (;;) {
@@ -114,24 +122,24 @@ __device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px,
     if (NB) next_wall = next_wall || (nbx && is_wall(m, ncx - 1, ncy)) || (nby && is_wall(m, ncx, ncy - 1));
     bool side_wall = false;
     if (stepx && stepy) side_wall = is_wall(m, ncx, cy) || is_wall(m, cx, ncy);  // lattice corner
-    const bool opens = !in_iv && next_wall;
-    const bool touches = !in_iv && !next_wall && side_wall;
-    const bool closes = in_iv && !next_wall;
-    if ((opens || touches) && !have_first) {  // entry vertex of the first piece: crossed coordinates are integral
-      have_first = true;
-      fex = stepx ? gx : px + tN * dx;
-      fey = stepy ? gy : py + tN * dy;
+    if (next_wall != in_iv || side_wall) {
+      if (in_iv) {
+        if (!next_wall) {  // the interval closes at tN (a touching side cell adds nothing to a closed interval)
+          if (tN > iv_t0) n_pos++; else n_zero++;
+          in_iv = false;
+        }
+      } else {  // next_wall || side_wall
+        if (!have_first) {  // entry vertex of the first piece: crossed coordinates are integral
+          have_first = true;
+          fex = stepx ? gx : px + tN * dx;
+          fey = stepy ? gy : py + tN * dy;
+        }
+        if (next_wall) { in_iv = true; iv_t0 = tN; } else n_zero++;
+      }
     }
-    const bool pos_len = tN > iv_t0;
-    n_pos += (closes && pos_len) ? 1 : 0;
-    n_zero += ((closes && !pos_len) ? 1 : 0) + (touches ? 1 : 0);
-    iv_t0 = opens ? tN : iv_t0;
-    in_iv = next_wall;
     cx = ncx; cy = ncy;
     if (stepx) { gx += sxd; tX = (gx - px) * inv_dx; }
     if (stepy) { gy += syd; tY = (gy - py) * inv_dy; }
-    // (no early exit for rays that leave the map: cells outside are free, the walk ends with the segment, and the
-    //  per-iteration bounds test cost more than the few iterations it saved -- measured on B200)
   }
   if (in_iv) { if (iv_t0 < 1.0) n_pos++; else n_zero++; }
   ws.n_pos = n_pos; ws.n_zero = n_zero; ws.fex = fex; ws.fey = fey;
@@ -147,7 +155,7 @@ __device__ float scan_one(const MapView& m, float posx, float posy, float tx, fl
   const double inv_dx = sx != 0 ? __ddiv_rn(1.0, dx) : 0.0, inv_dy = sy != 0 ? __ddiv_rn(1.0, dy) : 0.0;
   const double fpx = floor(px), fpy = floor(py);
   const bool px_int = (px == fpx), py_int = (py == fpy);
-  int cx = (int)fpx, cy = (int)fpy;
+  int cx = (int)fpx + m.pad, cy = (int)fpy + m.pad;  // padded cell coordinates from here on
   if (px_int && sx < 0) cx -= 1;
   if (py_int && sy < 0) cy -= 1;
   const bool nbx = (sx == 0 && px_int), nby = (sy == 0 && py_int);
@@ -250,7 +258,7 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
 //   phase 5  beams: a group of G = min(32, pow2 >= B) lanes owns one environment, lane l casts beams l, l+G, ...
 //            and stores coalesced runs of the lidar row.
 __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarParams p) {
-  extern __shared__ unsigned smem_maps[];  // kEnvsPerBlock x (H*words)
+  extern __shared__ unsigned smem_maps[];  // kEnvsPerBlock x (prows * pw): padded bitmaps, see MapView
   __shared__ float s_posx[kEnvsPerBlock], s_posy[kEnvsPerBlock];
   __shared__ int s_midx[kEnvsPerBlock];
   __shared__ unsigned char s_reset[kEnvsPerBlock];
@@ -259,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   const int warp = tid >> 5;
   const int env0 = blockIdx.x * kEnvsPerBlock;
   const int nE = min(kEnvsPerBlock, p.N - env0);
-  const int mw = p.H * p.words;
+  const int mw = p.H * p.words;    // words of one bank map
+  const int pmw = p.prows * p.pw;  // words of one padded shared-memory map
   const float Wf = (float)p.W, Hf = (float)p.H;
 
   // ---------------------------------------------------------------- phase 1
@@ -295,16 +304,27 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   __syncthreads();
 
   // ---------------------------------------------------------------- phase 2: stage the maps
-  for (int q = tid; q < nE * mw; q += kThreads) {
-    const int e = q / mw;
-    smem_maps[q] = p.bank[(size_t)s_midx[e] * mw + (q - e * mw)];
+  // padded word j of padded row yp holds the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad (pad <= 31)
+  for (int q = tid; q < nE * pmw; q += kThreads) {
+    const int e = q / pmw, r = q - e * pmw;
+    const int yp = r / p.pw, j = r - yp * p.pw;
+    const int y = yp - p.pad;
+    unsigned v = 0u;
+    if (y >= 0 && y < p.H) {
+      const unsigned* row = p.bank + (size_t)s_midx[e] * mw + (size_t)y * p.words;
+      const unsigned lo = (j >= 1 && j - 1 < p.words) ? row[j - 1] : 0u;
+      const unsigned hi = (j < p.words) ? row[j] : 0u;
+      v = __funnelshift_l(lo, hi, p.pad);  // (hi << pad) | (lo >> (32 - pad))
+    }
+    smem_maps[q] = v;
   }
   __syncthreads();
 
   // ---------------------------------------------------------------- phase 3: lane = environment
   if (act) {
-    MapView mv{smem_maps + (size_t)lane * mw, p.W, p.H, p.words};
+    MapView mv{smem_maps + (size_t)lane * pmw, p.pw, p.pad};
     const int midx = s_midx[lane];
+    const unsigned* gbits = p.bank + (size_t)midx * mw;  // the unpadded bitmap (reset only: free-cell count / pick)
     float posx, posy, initx, inity;
     int elapsed;
     bool aliased;
@@ -312,10 +332,10 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
     unsigned char term = 0;
     if (do_reset) {
       apg::Pcg64 g0 = p.g0[n];
-      const unsigned n_free = count_free(mv.bits, p.W, p.H, p.words);
+      const unsigned n_free = count_free(gbits, p.W, p.H, p.words);
       const unsigned k = (unsigned)apg::rng_integers_below(g0, (uint64_t)n_free);
       int col, row;
-      kth_free_cell(mv.bits, p.W, p.H, p.words, k, col, row);
+      kth_free_cell(gbits, p.W, p.H, p.words, k, col, row);
       p.g0[n] = g0;
       posx = __fadd_rn((float)col, 0.5f);
       posy = __fadd_rn((float)row, 0.5f);
@@ -436,10 +456,11 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
     for (int e = 0; e < nE; ++e) {
       if (!s_reset[e]) continue;
       float* mo = p.map_obs + (size_t)(env0 + e) * hw;
-      const unsigned* bits = smem_maps + (size_t)e * mw;
+      const unsigned* bits = smem_maps + (size_t)e * pmw;
       for (int q = tid; q < hw; q += kThreads) {
         const int y = q / p.W, x = q - y * p.W;
-        mo[q] = ((bits[y * p.words + (x >> 5)] >> (x & 31)) & 1u) ? one : 0.0f;
+        const int xp = x + p.pad;
+        mo[q] = ((bits[(y + p.pad) * p.pw + (xp >> 5)] >> (xp & 31)) & 1u) ? one : 0.0f;
       }
     }
   }
@@ -449,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   const int gi = lane / p.G;            // group inside the warp
   const int li = lane - gi * p.G;
   for (int e = warp * envs_per_warp + gi; e < nE; e += kWarpsPerBlock * envs_per_warp) {
-    MapView mv{smem_maps + (size_t)e * mw, p.W, p.H, p.words};
+    MapView mv{smem_maps + (size_t)e * pmw, p.pw, p.pad};
     const float posx = s_posx[e], posy = s_posy[e];
     const size_t row = (size_t)(env0 + e) * p.B;
     for (int b = li; b < p.B; b += p.G) {
@@ -474,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
 struct apg_lidar_env {
   apg_lidar_cfg cfg{};
   cudaStream_t stream = nullptr;
-  int words = 0, G = 0;
+  int words = 0, G = 0, pad = 0, pw = 0, prows = 0;
   size_t smem = 0;
   unsigned* d_bank = nullptr;
   int64_t n_maps = 0;
@@ -502,6 +523,7 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   const apg_lidar_cfg& c = e->cfg;
   LidarParams p{};
   p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
+  p.pad = e->pad; p.pw = e->pw; p.prows = e->prows;
   p.T = c.step_limit; p.M = (int)e->n_maps; p.static_map = c.static_map; p.static_idx = c.static_map_index;
   p.emit_cells = c.emit_cells; p.sparse = c.sparse_reward ? 1 : 0; p.mode = mode; p.range = c.lidar_range; p.seed = seed; p.env_offset = c.env_offset;
   p.bank = e->d_bank; p.dirs = e->d_dirs; p.action = d_action; p.pred = d_pred;
@@ -547,7 +569,20 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
   while (G < cfg->beam_count && G < 32) G <<= 1;
   if (G < 4) G = 4;
   e->G = G;
-  e->smem = (size_t)kEnvsPerBlock * cfg->height * e->words * sizeof(unsigned);
+  // free border of the shared-memory bitmaps: a ray (<= lidar_range, or <= 1 for the collision rays) that starts inside
+  // the map stays within range + 1 cells of it
+  e->pad = (int)std::ceil((double)(cfg->lidar_range > 1.0f ? cfg->lidar_range : 1.0f)) + 2;
+  if (e->pad > 31) {
+    delete e;
+    return apg::fail(APG_ERR_INVALID, "lidar_range %g too large (at most 29 cells)", (double)cfg->lidar_range);
+  }
+  e->pw = (cfg->width + 2 * e->pad + 31) / 32;
+  e->prows = cfg->height + 2 * e->pad;
+  e->smem = (size_t)kEnvsPerBlock * e->prows * e->pw * sizeof(unsigned);
+  if (e->smem > 200 * 1024) {
+    delete e;
+    return apg::fail(APG_ERR_INVALID, "map too large for the shared-memory bitmaps (%zu bytes per block)", e->smem);
+  }
   const size_t N = cfg->num_envs, B = cfg->beam_count;
   cudaError_t err = cudaSuccess;
   auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
@@ -635,8 +670,14 @@ int apg_lidar_set_map_bank(apg_lidar_env* e, const uint32_t* h_bits, int64_t n_m
         if (!((h_bits[((size_t)m * e->cfg.height + y) * e->words + (x >> 5)] >> (x & 31)) & 1u)) { any_free = true; break; }
     APG_CHECK(any_free, APG_ERR_INVALID, "map %lld has no free cell", (long long)m);
   }
+  // bits past the map width must be zero (they would be phantom walls in the padded shared-memory bitmaps)
+  std::vector<uint32_t> clean(h_bits, h_bits + count);
+  if (e->cfg.width & 31) {
+    const uint32_t last_mask = (1u << (e->cfg.width & 31)) - 1u;
+    for (size_t r = 0; r < (size_t)n_maps * e->cfg.height; ++r) clean[r * e->words + e->words - 1] &= last_mask;
+  }
   APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_bank), count * sizeof(uint32_t)));
-  APG_CUDA(cudaMemcpy(e->d_bank, h_bits, count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  APG_CUDA(cudaMemcpy(e->d_bank, clean.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice));
   e->n_maps = n_maps;
   return APG_OK;
 }

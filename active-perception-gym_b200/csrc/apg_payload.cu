@@ -66,7 +66,9 @@ __device__ __forceinline__ long long accepted_word(const unsigned* rej, long lon
 constexpr int kRawsPerThread = 8;
 
 __device__ __forceinline__ void note_word(const PayloadArgs& a, long long t, uint32_t w, uint32_t threshold) {
-  a.words[t] = w;
+  // only this shard's window [off, off + N + slack) is kept; the rejections of the WHOLE global stream are listed (the
+  // accepted word of rank j and the final stream state depend on every rejection before it)
+  if (t >= a.off && t < a.off + a.N + kPayloadSlack) a.words[t - a.off] = w;
   if (lemire_rejects(w, a.M, threshold)) {
     const unsigned slot = atomicAdd(&a.rej[0], 1u);
     if (slot < (unsigned)kPayloadSlack) a.rej[1 + slot] = (unsigned)t;
@@ -117,7 +119,7 @@ __global__ void payload_values_kernel(const PayloadArgs a) {
   // bank indices
   if (q < a.N) {
     const long long t = accepted_word(a.rej, a.off + q);
-    a.d_idx[q] = (a.M == 1) ? 0ll : (long long)(((uint64_t)a.words[t] * a.M) >> 32);
+    a.d_idx[q] = (a.M == 1) ? 0ll : (long long)(((uint64_t)a.words[t - a.off] * a.M) >> 32);
   }
   // label inversion: integers(0, 2) never rejects, value = top bit of the word
   if (a.inv && q < a.N) a.d_inv[q] = (unsigned char)(stream_word(a.streams[1], a.off + q) >> 31);
@@ -146,7 +148,14 @@ bool payload_device_ok(unsigned long long M, long long Ng) {
   return p_reject * (double)(Ng + kPayloadSlack) <= 64.0;  // Poisson(64) never reaches kPayloadSlack = 1024
 }
 
-size_t payload_scratch_words(long long Ng) { return (size_t)(Ng + kPayloadSlack + 2); }
+size_t payload_scratch_words(long long N) { return (size_t)(N + kPayloadSlack + 2); }
+
+cudaError_t payload_preload() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, payload_words_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, payload_values_kernel);
+  return e;
+}
 
 int launch_device_payload(const PayloadArgs& a, cudaStream_t stream) {
   const long long raws = (a.Ng + kPayloadSlack + 1) / 2 + 1;  // raw draws behind the g2 word stream
@@ -190,7 +199,7 @@ extern "C" int apg_rng_device_payload(int32_t device, apg_pcg64_state* g0, apg_p
   a.streams = d_st; a.streams_out = d_st + 3;
   A(cudaMalloc(&a.d_idx, num_envs * 8)); A(cudaMalloc(&a.d_pos, num_envs * 16));
   A(cudaMalloc(&a.d_target, num_envs * 8)); A(cudaMalloc(&a.d_inv, num_envs));
-  A(cudaMalloc(&a.words, apg::payload_scratch_words(global_n) * 4));
+  A(cudaMalloc(&a.words, apg::payload_scratch_words(num_envs) * 4));
   A(cudaMalloc(&a.rej, 2 * (apg::kPayloadSlack + 1) * 4));
   if (err == cudaSuccess) {
     a.rej_next = a.rej + apg::kPayloadSlack + 1;

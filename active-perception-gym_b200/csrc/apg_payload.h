@@ -30,7 +30,7 @@ struct PayloadArgs {
   double* d_pos;         // (N,2) float64
   float* d_target;       // (N,2) float32 (loc)
   unsigned char* d_inv;  // (N)   (inv)
-  unsigned* words;       // scratch: Ng + kPayloadSlack + 2 32-bit words of the g2 stream
+  unsigned* words;       // scratch: this shard's window of the g2 word stream, words [off, off + N + kPayloadSlack)
   unsigned* rej;         // scratch: [0] = number of rejected words, [1 .. kPayloadSlack] their positions; zero on entry
   unsigned* rej_next;    // the other rejection list, cleared here for the next payload
 };
@@ -38,7 +38,9 @@ struct PayloadArgs {
 // true when the device generator may be used: 2 <= M <= 2^32 and so few expected rejections that kPayloadSlack
 // cannot overflow (otherwise the host generator draws the payload)
 bool payload_device_ok(unsigned long long M, long long Ng);
-size_t payload_scratch_words(long long Ng);
+size_t payload_scratch_words(long long N);  // N = this shard's envs
+// loads the two kernels (module load off the step path)
+cudaError_t payload_preload();
 // two launches on `stream`; returns the number of launches or a negative cudaError
 int launch_device_payload(const PayloadArgs& a, cudaStream_t stream);
 

@@ -1,13 +1,19 @@
 """bench.py -- env-steps/s of the B200 stepping engine on the BASELINE.json configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mnist|tinyloc|lidar_rooms|lidar_maze]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mnist|tinyloc|lidar_rooms|lidar_maze] [--only]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...     # the CPU restatement of the reference path on the host cores
 
-A "step" is one vector step: every environment of the batch advances once through the fused kernel
-(position update, resample, loss, reward, flags, autoreset).  `value` = env-steps/s with all inputs resident
-in HBM (device-timed, max over ranks); `e2e` = the same through the host-buffer C-ABI call with the
-host<->device copies inside the timed region.  Prints ONE JSON line (rank 0).
+A "step" is one vector step: every environment of the batch advances once through the fused kernels (position
+update, resample, loss, reward, flags, autoreset).  `value` = env-steps/s with all inputs resident in HBM
+(device-timed with CUDA events, max over ranks); `e2e` = the same through the host-buffer C-ABI call with the
+host<->device copies inside the timed region.  Prints ONE JSON line (rank 0): the headline workload (default `mnist` =
+BASELINE.json configs[1]) at the top level and every workload of BASELINE.json's configs 2-5 under `workloads`, each
+measured under the same --steps/--warmup discipline (`--only` keeps the headline workload alone).
+
+Before the W warm-up steps every workload runs an UNTIMED priming phase (at least two whole episode cycles and at
+least --prime-ms of device work): first-use costs (module loads, the first autoreset payload) and the clock ramp of
+an idle GPU are not part of a step, and the driver's --warmup 5 is shorter than one 17-step image episode cycle.
 """
 from __future__ import annotations
 
@@ -26,53 +32,61 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "active-perception-gym_b200"))
 sys.path.insert(0, ROOT)
 
-# algorithmic bytes per env-step (DESIGN.md "Roofline"; SURVEY.md section 8d with the uint8 bank)
+# algorithmic bytes per env-step (SURVEY.md section 8d with the uint8 bank), frozen
 WORKLOADS = {
-    # name: (description, per-GPU envs, bytes per env-step)
     "mnist": dict(desc="MNIST-v0 shape: synthetic 60000x28x28x1 u8 bank, ImageClassificationVectorEnv, K=10, S=5, T=16",
-                  n_envs=65536, bytes_per_step=300),
+                  n_envs=65536, bytes_per_step=300, cycle=17, default_steps=20400),
     "tinyloc": dict(desc="TinyImageNetLoc-v0 shape: synthetic 100000x64x64x3 u8 bank, ImageLocalizationVectorEnv, S=10, T=16",
-                    n_envs=131072, bytes_per_step=1930),
+                    n_envs=131072, bytes_per_step=1930, cycle=17, default_steps=6800),
     "lidar_rooms": dict(desc="LIDARLocRooms-v0: 4096 procedural 32x32 rooms maps (reference generator), 64 beams, range 5, T=100",
-                        n_envs=262144, bytes_per_step=510),
+                        n_envs=262144, bytes_per_step=510, cycle=101, default_steps=808),
     "lidar_maze": dict(desc="LIDARLocMaze-v0 large: 256 procedural 63x63 mazes (reference generator), 256 beams, range 5, T=100",
-                       n_envs=131072, bytes_per_step=1800),
+                       n_envs=131072, bytes_per_step=1800, cycle=101, default_steps=404),
 }
+ORDER = ["mnist", "tinyloc", "lidar_rooms", "lidar_maze"]
 LIDAR = {"lidar_rooms": ("maps_rooms32.npz", 64), "lidar_maze": ("maps_maze63.npz", 256)}
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+CPU_SAMPLE = {"mnist": (4096, 340), "tinyloc": (256, 510), "lidar_rooms": (2048, 101), "lidar_maze": (256, 202)}
+REF_ARM_ENVS = {"mnist": 4096, "tinyloc": 256, "lidar_rooms": 1024, "lidar_maze": 128}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=0,
-                    help="timed steps (default: per workload, ~0.4 s of device time: mnist 20400, tinyloc 3400, "
-                         "lidar_rooms 680, lidar_maze 340)")
+                    help="timed steps (default: per workload, ~0.3 s of device time)")
     ap.add_argument("--warmup", type=int, default=34)
-    ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS), help="headline workload of the line")
+    ap.add_argument("--only", action="store_true", help="measure the headline workload only (no `workloads` table)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="override per-GPU num_envs")
     ap.add_argument("--bank", type=int, default=0, help="override bank length")
-    ap.add_argument("--e2e-steps", type=int, default=68)
+    ap.add_argument("--e2e-steps", type=int, default=34)
+    ap.add_argument("--prime-ms", type=float, default=60.0, help="minimum device time of the untimed priming phase")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-alt-blend", action="store_true", help="skip the extra float32-blend timing of image workloads")
     ap.add_argument("--blend", default="float64", choices=["float64", "float32"],
                     help="image workloads: float64 = the reference's blend arithmetic (bit-exact pixels, default); "
                          "float32 = opt-in blend within the 1e-5 relative bar")
-    args = ap.parse_args()
-    if args.steps <= 0:
-        args.steps = {"mnist": 20400, "tinyloc": 3400, "lidar_rooms": 680, "lidar_maze": 340}[args.workload]
-    return args
+    return ap.parse_args()
+
+
+def workload_config(name: str, n: int, world: int, blend: str | None):
+    """The `config` object of a line -- the SAME keys in the GPU arm and in the reference arm."""
+    w = WORKLOADS[name]
+    return {"workload": w["desc"], "name": name, "num_envs_per_gpu": n, "global_num_envs": world * n,
+            "sharding": f"env-index x{world}", "blend": None if name in LIDAR else blend}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms; stop(t0, t1) keeps the samples that arrived inside the
-    timed region [t0, t1] (wall clock) and falls back to all of them, saying so, when the region was too short."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms for the whole run; window(t0, t1) summarises the samples
+    that arrived inside [t0, t1] (wall clock) and falls back to the nearest ones, saying so, when the region was shorter
+    than the sampling period."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
@@ -93,20 +107,29 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0=None, t1=None):
+    def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        deadline = time.time() + 0.3
+        while time.time() < deadline and not any(t >= t1 for (t, _) in self.lines):
+            time.sleep(0.02)
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.06]
+        how = "inside the timed region"
+        if not inside:
+            near = sorted(self.lines, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))[:3]
+            inside = [ln for (_, ln) in near]
+            how = "the 3 samples nearest to the timed region (shorter than the 50 ms sampling period)"
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [ln for (t, ln) in self.lines if t0 is not None and t0 <= t <= t1 + 0.05]
-        in_region = len(inside) > 0
-        for ln in (inside if in_region else [ln for (_, ln) in self.lines]):
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -115,17 +138,16 @@ class ClockSampler:
                 mx.append(float(f[2]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[4:8]):
+            for nm, v in zip(self.NAMES, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "sampled": "inside the timed region" if in_region else
-                "around the timed region (shorter than the 50 ms sampling period)", "reasons": sorted(reasons)}
+                "samples": len(sm), "sampled": how, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
 def cpu_oracle_run(workload: str, n_envs: int, steps: int, seed: int = 0):
-    """One process of the CPU restatement (oracle/) on a bounded sample; returns env-steps/s."""
+    """One process of the CPU restatement (oracle/) on a bounded sample; returns (env-steps/s, seconds)."""
     from oracle.datasets import synthetic_u8_bank
     from oracle.image_oracle import ImageEnvOracle
 
@@ -183,45 +205,70 @@ def _cpu_worker(args):
     return cpu_oracle_run(*args)
 
 
-def cpu_baseline(workload: str, procs: int, n_envs: int, steps: int):
-    if procs <= 1:
-        v, dt = cpu_oracle_run(workload, n_envs, steps)
-        return v, dt
-    import multiprocessing as mp
+def cpu_pool_run(pool, workload: str, procs: int, n_envs: int, steps: int):
+    """`procs` independent processes of the restatement, each with its own `n_envs` environments; the rate is all
+    env-steps over the wall time of the slowest worker."""
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, [(workload, n_envs, steps, i) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    return procs * n_envs * steps / wall, wall
 
-    with mp.get_context("spawn").Pool(procs) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(workload, n_envs, steps, i) for i in range(procs)])
-        wall = time.perf_counter() - t0
-    return sum(r[0] for r in res), wall
+
+def real_reference_figure(workload: str):
+    """env-steps/s of the UNMODIFIED reference (/root/reference through the test-only gymnasium shim, one process -- the
+    reference's vector env is single-threaded by design).  Live where /root/reference exists (the build container),
+    else the figure recorded there (profiles/r02_real_reference.json), labelled as such; LIDAR has none (no GEOS)."""
+    rec = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_real_reference.json"))).get(workload)
+    except (OSError, ValueError):
+        pass
+    if not os.path.isdir("/root/reference/ap_gym") or workload in LIDAR:
+        if rec is not None:
+            rec = dict(rec, source="recorded in the build container (profiles/r02_real_reference.json); "
+                                   "/root/reference does not exist on the GPU box")
+        return rec
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_real_reference.py"), workload],
+                           capture_output=True, text=True, timeout=600)
+        out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        out["source"] = "live: unmodified /root/reference under oracle/shim, 1 process"
+        return out
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": repr(exc)[:200]} if rec is None else rec
 
 
 def run_reference_arm(args):
+    """The reference's CPU implementation of the path on the host cores: the oracle port on all cores, each timed step =
+    one vector step of every worker's bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
+    import multiprocessing as mp
+
+    name = args.workload
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
-    n_envs = {"mnist": 4096, "tinyloc": 256, "lidar_rooms": 1024, "lidar_maze": 128}[args.workload]
-    steps_per = 17
-    vals = []
-    for _ in range(max(1, args.warmup // 17)):
-        cpu_baseline(args.workload, procs, n_envs, 4)
-    t0 = time.perf_counter()
-    reps = max(1, min(args.steps // 17, 6))
-    for _ in range(reps):
-        v, _ = cpu_baseline(args.workload, procs, n_envs, steps_per)
-        vals.append(v)
-    wall = time.perf_counter() - t0
-    value = float(np.median(vals))
-    sample = f"{procs} processes x {n_envs} envs x {steps_per} steps of the CPU restatement (oracle/), median of {reps}"
+    n_envs = REF_ARM_ENVS[name]
+    K = args.steps if args.steps > 0 else 2 * w["cycle"]
+    W = max(args.warmup, 0)
+    with mp.get_context("spawn").Pool(procs) as pool:
+        if W:
+            cpu_pool_run(pool, name, procs, n_envs, W)
+        value, wall = cpu_pool_run(pool, name, procs, n_envs, K)
+    sample = (f"{procs} processes x {n_envs} envs x {K} steps of the CPU restatement (oracle/); every process also "
+              f"pays its own setup + 3 untimed steps inside the wall time")
+    cpu = {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": sample}
+    rr = real_reference_figure(name)
+    if rr is not None:
+        cpu["real_reference"] = rr
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs * procs / value,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * wall / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "num_envs_per_gpu": w["n_envs"]},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "config": workload_config(name, args.envs or w["n_envs"], int(os.environ.get("WORLD_SIZE", "1")), args.blend),
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -229,19 +276,19 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU side
-def build_env(args, rank, world, device):
+def build_env(name, args, rank, world, device):
     import ap_gym_b200 as apg
 
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS[name]
     n = args.envs or w["n_envs"]
-    if args.workload == "mnist":
+    if name == "mnist":
         ds = apg.SyntheticImageDataset("mnist", length=args.bank or None, seed=0)
         cfg = apg.ImagePerceptionConfig(dataset=ds)
         env = apg.ImageClassificationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
-                                               check_errors="never", payload_ring=64, blend=args.blend)
+                                               check_errors="never", payload_ring=8, blend=args.blend)
         pw = 10
-    elif args.workload in LIDAR:
-        fname, beams = LIDAR[args.workload]
+    elif name in LIDAR:
+        fname, beams = LIDAR[name]
         bank = apg.FloorMapBank.load_npz(os.path.join(GOLDEN, fname), args.bank or None)
         env = apg.LIDARLocalization2DVectorEnv(n, bank, lidar_beam_count=beams, device=device, env_offset=rank * n,
                                                check_errors="never")
@@ -250,9 +297,219 @@ def build_env(args, rank, world, device):
         ds = apg.SyntheticImageDataset("tinyimagenet", length=args.bank or None, seed=0)
         cfg = apg.ImagePerceptionConfig(dataset=ds, sensor_size=(10, 10))
         env = apg.ImageLocalizationVectorEnv(n, cfg, device=device, env_offset=rank * n, global_num_envs=world * n,
-                                             check_errors="never", payload_ring=64, blend=args.blend)
+                                             check_errors="never", payload_ring=8, blend=args.blend)
         pw = 2
     return env, n, pw
+
+
+def kernel_facts(name):
+    """Per-kernel facts measured under ncu and committed under profiles/ (DRAM traffic per launch, warp-instructions per
+    env-step): read, not measured, here."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_facts.json"))).get(name, {})
+    except (OSError, ValueError):
+        return {}
+
+
+def run_workload(name, args, rank, world, local_rank, dist, sampler, peaks):
+    import torch
+
+    from ap_gym_b200 import _capi
+
+    w = WORKLOADS[name]
+    is_lidar = name in LIDAR
+    env, n, pw = build_env(name, args, rank, world, local_rank)
+    lib = _capi.lib()
+    K = args.steps if args.steps > 0 else w["default_steps"]
+    W = args.warmup
+    dev = torch.device("cuda", local_rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # distinct inputs for every step, streamed from HBM (the pool is much larger than L2 and walked cyclically)
+    chunk = 51 if not is_lidar else 101  # steps per rollout call
+    pool = min(K + W + 2 * w["cycle"], 7 * 51)
+    acts = torch.rand((pool, n, 2), generator=gen, device=dev) * 2 - 1
+    if pw == 2:
+        preds = torch.rand((pool, n, 2), generator=gen, device=dev) * 2 - 1
+    else:
+        preds = torch.randn((pool, n, pw), generator=gen, device=dev)
+    t_reset0 = time.perf_counter()
+    env.reset(seed=0)
+    env.sync()
+    reset_s = time.perf_counter() - t_reset0
+    cursor = [0]
+
+    def run(steps):
+        done = 0
+        while done < steps:
+            a = cursor[0] % pool
+            m = min(chunk, steps - done, pool - a)
+            env.rollout(acts[a:a + m], preds[a:a + m])
+            cursor[0] += m
+            done += m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- priming (untimed): whole episode cycles until at least --prime-ms of device time has gone by.  Autoreset
+    # payloads are NOT staged ahead anywhere in this file: the engine draws each one on the device, in-stream, right
+    # before the step that consumes it (numpy-identical streams), inside the timed region as well.
+    prime_steps = 0
+    p0, p1 = ev(), ev()
+    p0.record()
+    while True:
+        run(2 * w["cycle"])
+        prime_steps += 2 * w["cycle"]
+        p1.record()
+        p1.synchronize()
+        if p0.elapsed_time(p1) >= args.prime_ms or prime_steps >= 200 * w["cycle"]:
+            break
+    run(W)
+    barrier()
+    l0 = lib.apg_launch_count()
+    ev0, ev1 = ev(), ev()
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    run(K)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.apg_launch_count() - l0
+    clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        all_ms = [torch.zeros_like(t_ms) for _ in range(world)]
+        dist.all_gather(all_ms, t_ms)
+        per_rank_ms = [float(x.item()) for x in all_ms]
+    else:
+        per_rank_ms = [ms]
+    ms_max = max(per_rank_ms)
+    value = world * n * K / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI call (the reference-facing step), copies inside the timed region;
+    # measured twice: reward / flags only, and with the observation (obs["glimpse"] / obs["lidar"]) copied back too
+    Ke = args.e2e_steps
+    obs_elems = n * (env._B if is_lidar else env._S0 * env._S1 * env._C)
+    h_a = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    h_p = torch.empty((n, pw), dtype=torch.float32).pin_memory()
+    h_r = torch.empty((n,), dtype=torch.float32).pin_memory()
+    h_te = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    h_tr = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    h_obs = torch.empty((obs_elems,), dtype=torch.float32).pin_memory()
+    h_a.copy_(acts[0].cpu())
+    h_p.copy_(preds[0].cpu())
+    step_host = lib.apg_lidar_step_host if is_lidar else lib.apg_image_step_host
+
+    def e2e(with_obs):
+        o = h_obs.data_ptr() if with_obs else None
+        for _ in range(5):
+            _capi.check(step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(), h_tr.data_ptr(), o))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            _capi.check(step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(), h_tr.data_ptr(), o))
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n * Ke / float(t.item())
+
+    e2e_value = e2e(False)
+    e2e_obs_value = e2e(True)
+    h2d = n * (2 + pw) * 4
+    d2h = n * (4 + 1 + 1)
+
+    # ---- final NCCL reduce of the device-side episode statistics (the only collective of the data path)
+    stats = env.episode_stats(reduce=True)
+    env.sync()
+    # sticky device-side error bits (NaN input, tap outside the image grid) of everything this process stepped: the
+    # benchmark runs with check_errors="never", so look once at the end -- a non-zero value invalidates the run
+    flags = C.c_uint32(0)
+    _capi.check((lib.apg_lidar_poll_error if is_lidar else lib.apg_image_poll_error)(env._h, C.byref(flags), 0))
+    t_f = torch.tensor([int(flags.value)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
+    error_flags = int(t_f.item())
+    variant = None if is_lidar else lib.apg_image_variant(env._h)
+    env.close()
+    del env, acts, preds
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    facts = kernel_facts(name)
+    bytes_per_launch = w["bytes_per_step"] * n
+    step_s = (ms_max * 1e-3) / K
+    achieved = bytes_per_launch / step_s / 1e9
+    if is_lidar:
+        kernel = "lidar_step_kernel"
+    else:
+        kernel = {0: "image_head_kernel + image_step_kernel (staged tiles, warp blend)",
+                  1: "image_step_kernel (staged tiles, thread blend)",
+                  3: "tma_head_kernel + tma_blend_kernel (TMA tiles, persistent warps)",
+                  4: "image_rollout_kernel (persistent thread-per-env rollout)"}.get(variant, str(variant))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": facts.get("dram_bytes_per_step"),
+                "algorithmic_bytes_per_launch": bytes_per_launch, "bytes_per_env_step": w["bytes_per_step"],
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "kernel": kernel, "avg_step_us": step_s * 1e6, "launches_per_step": launches / K,
+                "note": "achieved = algorithmic bytes of one vector step / device time of one vector step (all launches "
+                        "of the step together); traffic = dram read+write bytes per vector step from the committed ncu "
+                        "--set full capture (profiles/r02_kernel_facts.json)"}
+    if is_lidar:
+        # the ray walk is bound by instruction issue, not by bytes (DESIGN.md 4.2): the ALU-side figure is the achieved
+        # warp-instruction rate against 4 issue slots x SMs x clock, with the instruction count per env-step from ncu
+        ipe = facts.get("warp_instr_per_env_step")
+        sm_clock = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        issue_peak = 4.0 * sms * sm_clock * 1e6
+        roofline = dict(roofline, bound="issue", hbm_frac=roofline["frac"], hbm_achieved=achieved, hbm_peak=peak,
+                        unit="warp-instr/s", peak=issue_peak,
+                        achieved=None if ipe is None else ipe * (value / world),
+                        frac=None if ipe is None else ipe * (value / world) / issue_peak,
+                        warp_instr_per_env_step=ipe,
+                        note="issue-bound kernel: achieved = warp-instructions per env-step (ncu, profiles/) x "
+                             "env-steps/s per GPU; peak = 4 issue slots x SMs x SM clock; hbm_* keep the byte-side figures")
+    res = {
+        "value": value, "unit": "env-steps/s", "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+        "per_rank_ms": per_rank_ms, "primed_steps": prime_steps,
+        "config": workload_config(name, n, world, args.blend),
+        "timing": {"explicit_reset_s": round(reset_s, 3),
+                   "l2": "per-step inputs come from a pool of %d distinct steps streamed from HBM (%.0f MB > 126 MB L2, "
+                         "walked cyclically); engine-owned observation buffers are rewritten every step" %
+                         (pool, pool * n * (2 + pw) * 4 / 1e6),
+                   "priming": "%d untimed steps (whole episode cycles, >= %.0f ms of device time) before the %d warm-up "
+                              "steps" % (prime_steps, args.prime_ms, W)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "api": ("apg_lidar_step_host" if is_lidar else "apg_image_step_host") +
+                       " (pinned host action/prediction in, reward/terminated/truncated out)",
+                "with_obs": {"value": e2e_obs_value, "d2h_bytes_per_step": d2h + obs_elems * 4,
+                             "what": "the same call with the observation (" + ("lidar" if is_lidar else "glimpse") +
+                                     ") copied back to pinned host memory as well"}},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "episode_stats_allreduce": stats,
+        "error_flags": error_flags,
+    }
+    if error_flags:
+        sys.stderr.write("bench.py: device error flags 0x%x were raised during %s -- result INVALID\n" % (error_flags, name))
+    if not args.no_cpu_baseline and world == 1:
+        n_cpu, st_cpu = CPU_SAMPLE[name]
+        v, dt = cpu_oracle_run(name, n_cpu, st_cpu)
+        res["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                               "sample": f"CPU restatement (oracle/), 1 process, N={n_cpu} x {st_cpu} steps, {dt:.1f} s"}
+        rr = real_reference_figure(name)
+        if rr is not None:
+            res["cpu_baseline"]["real_reference"] = rr
+    return res
 
 
 def main():
@@ -271,188 +528,34 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from ap_gym_b200 import _capi
-
-    w = WORKLOADS[args.workload]
-    env, n, pw = build_env(args, rank, world, local_rank)
-    is_lidar = args.workload in LIDAR
-    T = 16
-    K, W = args.steps, args.warmup
-    dev = torch.device("cuda", local_rank)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    # distinct inputs for every step: streamed from HBM, total larger than L2
-    chunk = 17 * 3  # steps per rollout call (3 episodes)
-    pool = min(K + W, 7 * chunk)  # distinct per-step inputs; longer runs walk the pool cyclically (it is >> L2)
-    acts = torch.rand((pool, n, 2), generator=gen, device=dev) * 2 - 1
-    if pw == 2:
-        preds = torch.rand((pool, n, 2), generator=gen, device=dev) * 2 - 1
-    else:
-        preds = torch.randn((pool, n, pw), generator=gen, device=dev)
-    t_reset0 = time.perf_counter()
-    env.reset(seed=0)
-    env.sync()
-    reset_s = time.perf_counter() - t_reset0
-
-    def run(s0, s1, env=env):
-        s = s0
-        while s < s1:
-            a = s % pool
-            m = min(chunk, s1 - s, pool - a)
-            env.rollout(acts[a:a + m], preds[a:a + m])
-            s += m
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # warm-up.  Autoreset payloads are NOT staged ahead: the engine draws each one on the device, in-stream, right
-    # before the step that consumes it (numpy-identical streams, csrc/apg_payload.cu), inside the timed region.
-    run(0, W)
-    barrier()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = _capi.lib().apg_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    ev0.record()
-    run(W, W + K)
-    ev1.record()
-    barrier()
-    t_wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
-    launches = _capi.lib().apg_launch_count() - l0
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = world * n * K / (ms_max * 1e-3)
-
-    # ---- image workloads: the same timed region with the opt-in float32 blend (pixels within 1e-5 relative of the
-    # reference instead of bit-exact; tests/test_image_gpu.py holds both modes to their bars)
-    alt = None
-    if not is_lidar and args.blend == "float64" and not args.no_alt_blend:
-        import copy
-        a2 = copy.copy(args)
-        a2.blend = "float32"
-        env2, _, _ = build_env(a2, rank, world, local_rank)
-        env2.reset(seed=0)
-        run(0, W, env2)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run(W, W + K, env2)
-        e1.record()
-        barrier()
-        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms2 = float(t2.item())
-        alt = {"blend": "float32", "value": world * n * K / (ms2 * 1e-3), "ms_per_step": ms2 / K,
-               "parity": "glimpse pixels within 1e-5 relative of the reference (no absolute slack), everything else bit-exact"}
-        env2.close()
-        del env2
-
-    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
-    Ke = args.e2e_steps
-    h_a = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    h_p = torch.empty((n, pw), dtype=torch.float32).pin_memory()
-    h_r = torch.empty((n,), dtype=torch.float32).pin_memory()
-    h_te = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    h_tr = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    h_a.copy_(acts[0].cpu())
-    h_p.copy_(preds[0].cpu())
-    lib = _capi.lib()
-
-    def e2e_step():
-        if is_lidar:
-            _capi.check(lib.apg_lidar_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
-                                                h_tr.data_ptr(), None))
-            return
-        _capi.check(lib.apg_image_step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
-                                            h_tr.data_ptr(), None))
-
-    for _ in range(5):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * Ke / float(t_e.item())
-    h2d = n * (2 + pw) * 4
-    d2h = n * (4 + 1 + 1)
-
-    # ---- final NCCL reduce of the device-side episode statistics (the only collective of the data path)
-    stats = env.episode_stats(reduce=True)
-    env.sync()
-    # sticky device-side error bits (NaN input, tap outside the image grid) of everything this process stepped: the
-    # benchmark runs with check_errors="never", so look once at the end -- a non-zero value invalidates the run
-    import ctypes
-    flags = ctypes.c_uint32(0)
-    _capi.check((lib.apg_lidar_poll_error if is_lidar else lib.apg_image_poll_error)(env._h, ctypes.byref(flags), 0))
-    t_f = torch.tensor([int(flags.value)], device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
-    error_flags = int(t_f.item())
-
+    names = [args.workload] if args.only else [args.workload] + [x for x in ORDER if x != args.workload]
+    results = {}
+    for name in names:
+        results[name] = run_workload(name, args, rank, world, local_rank, dist, sampler, peaks)
+    sampler.stop()
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
-        try:  # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if args.workload in tj and n == w["n_envs"]:
-                traffic = tj[args.workload]["dram_bytes_per_launch"]
-        except (OSError, ValueError, KeyError):
-            pass
-        bytes_per_launch = w["bytes_per_step"] * n
-        avg_launch_s = (ms_max * 1e-3) / K
-        achieved = bytes_per_launch / avg_launch_s / 1e9
-        line = {
-            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "num_envs_per_gpu": n, "global_num_envs": world * n, "sharding": f"env-index x{world}", "blend": None if is_lidar else args.blend, "explicit_reset_s": round(reset_s, 3),
-                       "l2": "per-step inputs come from a pool of %d distinct steps streamed from HBM (%.0f MB > 126 MB L2, walked cyclically); engine-owned obs buffers are rewritten every step" % (pool, acts.numel() * 4 / 1e6 + preds.numel() * 4 / 1e6)},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": ("apg_lidar_step_host" if is_lidar else "apg_image_step_host") + " (pinned host action/prediction in, reward/terminated/truncated out)"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "kernel": "lidar_step_kernel" if is_lidar else
-                         ["image_step_kernel (warp blend)", "image_step_kernel (thread blend)",
-                          "image_step_pipelined_kernel"][lib.apg_image_variant(env._h)], "bytes_per_env_step": w["bytes_per_step"],
-                         "avg_launch_us": avg_launch_s * 1e6, "launches_per_step": launches / K,
-                         "note": "achieved = algorithmic bytes of one step / device time of one step; with 2 launches per "
-                                 "step (image_head_kernel + image_step_kernel, warp path) the step time covers both"},
-            "episode_stats_allreduce": stats,
-            "error_flags": error_flags,
-        }
-        if error_flags:
-            sys.stderr.write("bench.py: device error flags 0x%x were raised during the run -- result INVALID\n" % error_flags)
-        if alt is not None:
-            alt["roofline_frac"] = (bytes_per_launch / (alt["ms_per_step"] * 1e-3) / 1e9) / peak
-            line["alt_blend"] = alt
-        if not args.no_cpu_baseline and world == 1:
-            n_cpu, st_cpu = {"mnist": (4096, 680), "tinyloc": (256, 1020), "lidar_rooms": (2048, 303), "lidar_maze": (256, 808)}[args.workload]
-            v, dt = cpu_oracle_run(args.workload, n_cpu, st_cpu)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                    "sample": f"CPU restatement (oracle/), 1 process, N={n_cpu} x {st_cpu} steps, {dt:.1f} s"}
+        head = results[args.workload]
+        line = {"metric": "env-steps/sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world,
+                "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+        for k in ("config", "timing", "clocks", "e2e", "gpu_launches", "roofline", "per_rank_ms", "primed_steps",
+                  "episode_stats_allreduce", "error_flags", "cpu_baseline"):
+            if k in head:
+                line[k] = head[k]
+        line["gpu_launches"] = sum(r["gpu_launches"] for r in results.values())
+        line["gpu_launches_headline"] = head["gpu_launches"]
+        line["error_flags"] = max(r["error_flags"] for r in results.values())
+        if not args.only:
+            line["workloads"] = results
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,19 +30,35 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert sorted(d["config"]) == sorted(["workload", "name", "num_envs_per_gpu", "global_num_envs", "sharding", "blend"])
+    assert d["steps"] == 17 and d["warmup"] == 3
 
 
 @pytest.mark.gpu
 def test_gpu_arm_json_line():
-    d = _run(["--steps", "51", "--warmup", "17", "--e2e-steps", "5"], 900)
+    d = _run(["--steps", "51", "--warmup", "17", "--e2e-steps", "5", "--only"], 900)
     for k in COMMON + ["clocks", "roofline", "error_flags"]:
         assert k in d, k
     assert "impl" not in d or d["impl"] != "reference"
-    assert d["n_gpus"] == 1 and d["steps"] == 51 and d["value"] > 0 and d["gpu_launches"] >= 51
+    assert d["n_gpus"] == 1 and d["steps"] == 51 and d["value"] > 0 and d["gpu_launches"] >= 1
     assert d["error_flags"] == 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
-    assert d["alt_blend"]["blend"] == "float32" and d["alt_blend"]["value"] > 0
+    assert len(d["per_rank_ms"]) == 1 and d["primed_steps"] >= 34
+    assert "with_obs" in d["e2e"] and d["e2e"]["with_obs"]["value"] > 0
+    assert sorted(d["config"]) == sorted(["workload", "name", "num_envs_per_gpu", "global_num_envs", "sharding", "blend"])
+
+
+@pytest.mark.gpu
+def test_gpu_arm_workloads_table():
+    """The default line carries every BASELINE.json workload (small env counts here to keep the test short)."""
+    d = _run(["--steps", "20", "--warmup", "5", "--e2e-steps", "3", "--envs", "8192", "--bank", "2048", "--prime-ms", "5",
+              "--no-cpu-baseline"], 900)
+    assert sorted(d["workloads"]) == ["lidar_maze", "lidar_rooms", "mnist", "tinyloc"]
+    for name, w in d["workloads"].items():
+        assert w["value"] > 0 and w["steps"] == 20 and w["error_flags"] == 0, name
+        assert w["roofline"]["bound"] == ("issue" if name.startswith("lidar") else "hbm"), name
+        assert w["e2e"]["value"] > 0 and w["e2e"]["with_obs"]["value"] > 0, name
+    assert d["value"] == d["workloads"]["mnist"]["value"]

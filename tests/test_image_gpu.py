@@ -189,9 +189,12 @@ def test_unique_glimpse_targets_match_reference(name):
     env.close()
 
 
-def test_pipelined_variant_matches_default(monkeypatch):
-    """The opt-in persistent producer/consumer kernel (APG_IMG_PIPELINE=1) against the default kernel: bit-identical
-    observations, rewards and state over two episodes of the localisation env (target glimpse = second set)."""
+@pytest.mark.parametrize("flag", ["APG_IMG_GENERIC", "APG_IMG_FORCE_SLOW"])
+def test_tma_kernel_matches_staged_kernel_and_its_general_path(monkeypatch, flag):
+    """TinyImageNetLoc geometry (64x64x3 bank, 10x10 sensor): the TMA-tile kernel (default, variant 3) against (a) the
+    generic staged-tile kernel (APG_IMG_GENERIC=1) and (b) its own general per-output branch, which real inputs reach
+    with probability ~1e-15 (APG_IMG_FORCE_SLOW=1 sends every environment through it): bit-identical observations,
+    rewards, visited masks and statistics over two episodes, target glimpse (second set) included."""
     import ap_gym_b200 as apg
     from oracle.datasets import synthetic_u8_bank
 
@@ -201,15 +204,17 @@ def test_pipelined_variant_matches_default(monkeypatch):
     rng = np.random.default_rng(1)
     tgt = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
     envs = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("APG_IMG_PIPELINE", flag)
+    for v in ("0", "1"):
+        monkeypatch.setenv(flag, v)
         envs.append(apg.ImageLocalizationVectorEnv(N, cfg, output="numpy"))
-    assert envs[0]._lib.apg_image_variant(envs[0]._h) == 0 and envs[1]._lib.apg_image_variant(envs[1]._h) == 2
+    monkeypatch.delenv(flag)
+    assert envs[0]._lib.apg_image_variant(envs[0]._h) == 3
+    assert envs[1]._lib.apg_image_variant(envs[1]._h) == (0 if flag == "APG_IMG_GENERIC" else 3)
     obs = [e.reset(seed=4, options={"prediction_target": tgt})[0] for e in envs]
     for k in obs[0]:
         assert np.array_equal(obs[0][k], obs[1][k]), k
     for s in range(15):
-        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        a = (rng.uniform(-1, 1, (N, 2)) * 1.5).astype(np.float32)  # saturates at the image border regularly
         p = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
         out = [e.step({"action": a, "prediction": p}) for e in envs]
         for k in out[0][0]:
@@ -219,6 +224,51 @@ def test_pipelined_variant_matches_default(monkeypatch):
     assert envs[0].episode_stats(reduce=False) == envs[1].episode_stats(reduce=False)
     for e in envs:
         e.close()
+
+
+def test_tinyloc_benchmark_shape_matches_oracle_n4096():
+    """The BENCHMARKED TinyImageNetLoc kernel (uint8 64x64x3 bank, 10x10x3 sensor, T=16) against the oracle at N=4096
+    over 38 steps = two autoresets (both glimpse sets, the head kernel, persistent warps with several environments
+    each), plus a shard of the same global batch (env_offset) that must reproduce its slice."""
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+    import ap_gym_b200 as apg
+
+    N, K, M = 4096, 200, 512
+    imgs, labels = synthetic_u8_bank(seed=31, M=M, H=64, W=64, C=3, K=K)
+    kw = dict(sensor_size=(10, 10))
+    oracle = ImageEnvOracle(imgs, labels, N, task="loc", num_classes=K, track_overlay=False, **kw)
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K), **kw)
+    env = apg.ImageLocalizationVectorEnv(N, cfg, output="numpy")
+    assert env._lib.apg_image_variant(env._h) == 3
+    lo, hi = 1000, 1000 + 1111
+    shard = apg.ImageLocalizationVectorEnv(hi - lo, cfg, output="numpy", env_offset=lo, global_num_envs=N)
+    rng = np.random.default_rng(8)
+    tgt = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+    oo, _ = oracle.reset(seed=12, explicit_targets=tgt)
+    eo, _ = env.reset(seed=12, options={"prediction_target": tgt})
+    so, _ = shard.reset(seed=12, options={"prediction_target": tgt[lo:hi]})
+    for k in oo:
+        assert np.array_equal(eo[k], oo[k]), f"reset obs {k}"
+        assert np.array_equal(so[k], oo[k][lo:hi]), f"reset obs {k} (shard)"
+    for s in range(38):
+        a = (rng.uniform(-1, 1, (N, 2)) * 1.4).astype(np.float32)
+        p = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        oo, orw, ote, otr, oinf = oracle.step(a, p)
+        eo, erw, ete, etr, einf = env.step({"action": a, "prediction": p})
+        so, srw, ste, _, sinf = shard.step({"action": a[lo:hi], "prediction": p[lo:hi]})
+        for k in oo:
+            assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+            assert np.array_equal(so[k], oo[k][lo:hi]), f"step {s} obs {k} (shard)"
+        assert np.array_equal(_np(env.state()["pos"]), oracle.pos)
+        assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited), f"step {s} visited"
+        assert np.array_equal(ete, ote) and np.array_equal(etr, otr) and np.array_equal(ste, ote[lo:hi])
+        assert np.array_equal(einf["prediction"]["target"], oinf["prediction"]["target"])
+        assert np.array_equal(einf["index"], oinf["index"]) and np.array_equal(sinf["index"], oinf["index"][lo:hi])
+        assert np.array_equal(erw, orw.astype(np.float32)) or np.allclose(erw, orw, rtol=RTOL, atol=ATOL), f"step {s} reward"
+        assert np.array_equal(srw, erw[lo:hi])
+    env.close()
+    shard.close()
 
 
 def test_error_conventions():
