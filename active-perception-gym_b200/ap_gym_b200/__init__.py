@@ -11,5 +11,6 @@ from .datasets import ArrayImageDataset, ImageBank, SyntheticImageDataset, bank_
 from .floor_maps import FloorMapBank, pack_maps, unpack_maps
 from .lidar_env import LIDARLocalization2DVectorEnv, lidar_directions
 from .image_env import ImageClassificationVectorEnv, ImageLocalizationVectorEnv, ImagePerceptionConfig
+from .reference_compat import enable_reference_compat, register_envs
 
 __version__ = "0.1.0"

@@ -21,10 +21,10 @@ import numpy as np
 
 from . import _capi
 from .datasets import ImageBank, bank_from_dataset
-from .loss_fn import CrossEntropyLossFn, make_mse_loss_fn_and_target_space
+from .loss_fn import CrossEntropyLossFn, WeightedLossFn, make_mse_loss_fn_and_target_space
 from .reset_stream import ImageResetStream
 from .spaces import (NEXT_STEP, ActivePerceptionActionSpace, Box, Dict, Discrete, ImageSpace, LogitSpace,
-                     MultiDiscrete, batch_box)
+                     MultiDiscrete, VectorEnvBase, batch_box, sparse_target_spaces)
 
 
 @dataclass(frozen=True)
@@ -54,19 +54,29 @@ def _void(a: np.ndarray | None):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-class _ImageVectorEnvBase:
+class _ImageVectorEnvBase(VectorEnvBase):
+    """Common part of the two image environments.  A `gymnasium.vector.VectorEnv` when gymnasium is importable (the
+    reference's wrappers and `gymnasium.vector.VectorWrapper` check for it); `ap_gym_b200.enable_reference_compat()`
+    additionally registers the classes with the reference's `BaseActivePerceptionVectorEnv` ABC.
+
+    Aliasing contract: `step()` / `reset()` with CUDA tensors return DLPack VIEWS of engine-owned device buffers; the
+    next `step()` / `reset()` / `rollout()` overwrites them and `close()` frees them (the reference returns fresh
+    arrays).  Construct with `copy_outputs=True` to get private copies instead."""
+
     metadata: dict[str, Any] = {"render_modes": ["rgb_array"], "render_fps": 2, "autoreset_mode": NEXT_STEP}
     _TASK = _capi.TASK_CLASSIFICATION
+    closed = False
 
     def __init__(self, num_envs: int, image_perception_config: ImagePerceptionConfig,
                  render_mode: Literal["rgb_array"] = "rgb_array", *, device: int = 0,
                  env_offset: int = 0, global_num_envs: int | None = None, track_visited: bool = True,
                  check_errors: Literal["step", "lazy", "never"] = "lazy",
                  output: Literal["torch", "numpy"] = "torch", payload_ring: int = 4,
-                 blend: Literal["float64", "float32"] = "float64", sparse: bool = False):
+                 blend: Literal["float64", "float32"] = "float64", sparse: bool = False, copy_outputs: bool = False):
         """`sparse=True` is the reference's `<id>-sparse` registration (SparsifyVectorWrapper, sparsify_wrapper.py:23-88):
-        reward = base_reward - loss * weight with weight = terminated, and info["prediction"]["target"] becomes
-        {"target": ..., "weight": float32(terminated)}."""
+        reward = base_reward - loss * weight with weight = terminated, info["prediction"]["target"] becomes
+        {"target": ..., "weight": float32(terminated)}, `loss_fn` becomes WeightedLossFn(loss_fn) and the prediction
+        target spaces Dict{"target", "weight"}."""
         if render_mode not in self.metadata["render_modes"]:
             raise ValueError(f"Unsupported render mode: {render_mode}")
         if blend not in ("float64", "float32"):
@@ -120,7 +130,10 @@ class _ImageVectorEnvBase:
         self._views = self._make_views()
         self._build_spaces()
         self._closed = False
-        self.spec = None
+        self._copy = bool(copy_outputs)
+        self._spec = None
+        self._cuda_stream = 0       # the CUDA stream the engine queues on (0 = legacy default stream)
+        self._rng_exposed = False   # env.np_random was handed out: its state goes back to the engine before stepping
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _buffers(self) -> _capi.ImageBuffers:
@@ -198,6 +211,10 @@ class _ImageVectorEnvBase:
             batched_pred = batch_box(pred, N)
         self.single_action_space = ActivePerceptionActionSpace(inner, pred)
         self.action_space = ActivePerceptionActionSpace(batch_box(inner, N), batched_pred)
+        if self.sparse:  # SparsifyVectorWrapper.__init__ (sparsify_wrapper.py:49-60)
+            self.single_prediction_target_space, self.prediction_target_space = sparse_target_spaces(
+                self.single_prediction_target_space, N)
+            self.loss_fn = WeightedLossFn(self.loss_fn)
 
     # the reference's derived properties (active_perception_vector_env.py:52-66)
     prediction_space = property(lambda self: self.action_space["prediction"])
@@ -209,11 +226,45 @@ class _ImageVectorEnvBase:
     unwrapped = property(lambda self: self)
 
     @property
+    def spec(self):
+        return self._spec
+
+    @spec.setter
+    def spec(self, spec):
+        """Like the reference (image_classification.py:155-159): the episode length is the config's step limit."""
+        if spec is not None:
+            import copy
+
+            spec = copy.copy(spec)
+            try:
+                spec.max_episode_steps = int(self._config.step_limit)
+            except AttributeError:
+                pass
+        self._spec = spec
+
+    @property
     def np_random(self):
+        """The env-level Generator (g0 of SURVEY 3.4) in its CURRENT state.  Draws made from it are handed back to the
+        engine before the next step / rollout, so the reference's stream position is kept either way."""
         if self._stream is None:
             self._seed(None)
         self._pull_streams()
+        self._rng_exposed = True
         return self._stream.g0
+
+    def _before_device_work(self, tensor=None):
+        """Queue on torch's current stream (so that inputs produced on a side stream are complete and outputs are
+        ordered for their consumers) and hand back Generator states the caller may have advanced."""
+        if self._rng_exposed and getattr(self, "_engine_has_streams", False):
+            self._push_streams()
+            self._rng_exposed = False
+        if tensor is not None:
+            import torch
+
+            st = int(torch.cuda.current_stream(tensor.device).cuda_stream)
+            if st != self._cuda_stream:
+                _capi.check(self._lib.apg_image_set_stream(self._h, C.c_void_p(st)))
+                self._cuda_stream = st
 
     def _seed(self, seed):
         self._stream = ImageResetStream(seed, self._global_n, len(self._bank), self._slice)
@@ -267,10 +318,12 @@ class _ImageVectorEnvBase:
             self._seed(seed)
         else:
             self._pull_streams()
+        self._rng_exposed = False
         idx, inv, pos = self._stream.draw_episode(bool(self._config.randomly_invert_labels))
         target = self._explicit_targets(options, idx, pos)
         _capi.check(self._lib.apg_image_reset(self._h, _void(idx), _void(pos), _void(target), _void(inv)))
         self._push_streams()
+        self._last_prediction = None
         as_numpy = bool(options and options.get("numpy", False)) or self._numpy_mode
         return self._obs(as_numpy), {"index": self._out("index", as_numpy)}
 
@@ -282,7 +335,9 @@ class _ImageVectorEnvBase:
     # ------------------------------------------------------------------------------------------ step
     def _out(self, name: str, as_numpy: bool):
         v = self._views[name]
-        return v.cpu().numpy() if as_numpy else v
+        if as_numpy:
+            return v.cpu().numpy()
+        return v.clone() if self._copy else v
 
     def _obs(self, as_numpy: bool):
         keys = ["glimpse", "glimpse_pos", "time_step"]
@@ -292,14 +347,19 @@ class _ImageVectorEnvBase:
             keys.append("target_glimpse")
         return {k: self._out(k, as_numpy) for k in keys}
 
+    def _pred_width(self) -> int:
+        return self._K if self._TASK == _capi.TASK_CLASSIFICATION else 2
+
     def step(self, action):
         a, p = action["action"], action["prediction"]
         host_mode = not _is_torch(a)
+        want_a, want_p = (self.num_envs, 2), (self.num_envs, self._pred_width())
         if host_mode:
             a = np.ascontiguousarray(a, dtype=np.float32)
             p = np.ascontiguousarray(p, dtype=np.float32)
-            if a.shape != (self.num_envs, 2) or p.shape[0] != self.num_envs:
-                raise ValueError(f"bad action/prediction shapes {a.shape} {p.shape}")
+            if a.shape != want_a or p.shape != want_p:
+                raise ValueError(f"bad action/prediction shapes {a.shape} {p.shape}, expected {want_a} {want_p}")
+            self._before_device_work()
             N = self.num_envs
             reward = np.empty(N, np.float32)
             term = np.empty(N, np.bool_)
@@ -315,8 +375,9 @@ class _ImageVectorEnvBase:
             if not (a.is_cuda and p.is_cuda and a.is_contiguous() and p.is_contiguous()
                     and a.dtype == p.dtype and str(a.dtype) == "torch.float32"):
                 raise ValueError("torch inputs must be contiguous float32 CUDA tensors")
-            if tuple(a.shape) != (self.num_envs, 2) or p.shape[0] != self.num_envs:
-                raise ValueError(f"bad action/prediction shapes {tuple(a.shape)} {tuple(p.shape)}")
+            if tuple(a.shape) != want_a or tuple(p.shape) != want_p:
+                raise ValueError(f"bad action/prediction shapes {tuple(a.shape)} {tuple(p.shape)}, expected {want_a} {want_p}")
+            self._before_device_work(a)
             _capi.check(self._lib.apg_image_step(self._h, a.data_ptr(), p.data_ptr()))
             self._maybe_poll(False)
             obs = self._obs(False)
@@ -366,6 +427,20 @@ class _ImageVectorEnvBase:
         """`n_steps` consecutive steps from stacked CUDA tensors (n_steps, N, 2) / (n_steps, N, K|2); per-step
         rewards (f32) / dones (bool) land in the optional (n_steps, N) tensors.  Asynchronous."""
         n_steps = int(actions.shape[0])
+        N, K = self.num_envs, self._pred_width()
+
+        def _chk(t, shape, dtypes, what):
+            if t is None:
+                return
+            if not (_is_torch(t) and t.is_cuda and t.is_contiguous() and str(t.dtype) in dtypes and tuple(t.shape) == shape):
+                raise ValueError(f"rollout: {what} must be a contiguous CUDA tensor of shape {shape} and dtype "
+                                 f"{' or '.join(dtypes)}")
+
+        _chk(actions, (n_steps, N, 2), ("torch.float32",), "actions")
+        _chk(predictions, (n_steps, N, K), ("torch.float32",), "predictions")
+        _chk(rewards, (n_steps, N), ("torch.float32",), "rewards")
+        _chk(dones, (n_steps, N), ("torch.bool", "torch.uint8"), "dones")
+        self._before_device_work(actions)
         _capi.check(self._lib.apg_image_rollout(
             self._h, actions.data_ptr(), predictions.data_ptr(), n_steps,
             None if rewards is None else rewards.data_ptr(), None if dones is None else dones.data_ptr()))
@@ -410,12 +485,62 @@ class _ImageVectorEnvBase:
             quality[coords] = q[s][:, None, None]
         return counts, quality
 
-    def render(self):
-        raise NotImplementedError("render() is host-side tooling outside the hot path (DESIGN.md, out of scope)")
+    def _render_geometry(self):
+        H, W = self._H, self._W
+        Wr = max(128, self._S1)
+        rs = Wr / W
+        Hr = int(round(rs * H))
+        return Wr, Hr, rs
 
-    def close(self):
+    def _to_render_coords(self, pos_norm):
+        """image_perception_module.py:406-413: normalised (x, y) -> render pixels."""
+        Wr, Hr, rs = self._render_geometry()
+        eff = np.array(self._config.sensor_size) * self._config.sensor_scale
+        lim = (np.array([self._W, self._H]) - 1) / 2 - (eff - 1) / 2
+        return np.asarray(pos_norm, dtype=np.float64) * lim * rs + np.array([Wr, Hr]) / 2
+
+    def render(self, envs: Sequence[int] | None = None, return_pil_imgs: bool = False):
+        """ImagePerceptionModule.render (image_perception_module.py:333-401) rebuilt from the engine state: the bank
+        image of every environment, the visitation / prediction-quality overlay of the current episode (device stamp
+        log) and the sensor rectangle.  Host-side (PIL), not on the step path; `envs` limits the work to a subset."""
+        from PIL import Image, ImageDraw
+
+        from .style import COLOR_AGENT, quality_color
+
+        cfg = self._config
+        envs = np.arange(self.num_envs) if envs is None else np.asarray(envs)
+        Wr, Hr, rs = self._render_geometry()
+        self.sync()
+        idx = self._views["index"].cpu().numpy()[envs]
+        imgs = self._bank.images[idx]
+        imgs = imgs.astype(np.float32) / np.float32(255) if self._bank.is_u8 else imgs
+        if self._C == 1:
+            imgs = imgs[..., 0]
+        counts, quality = self.overlay_maps(envs)
+        visited = counts > 0
+        overlay = (visited[..., None] * np.concatenate(
+            [quality_color(quality), np.full_like(quality[..., None], int(255 * cfg.render_visited_opacity))], axis=-1)
+            + ~visited[..., None] * (0, 0, 0, int(255 * cfg.render_unvisited_opacity))).round().astype(np.uint8)
+        pos = self._to_render_coords(self._views["pos"].cpu().numpy()[envs])
+        size = np.array(cfg.sensor_size) * cfg.sensor_scale * rs
+        border = max(1, int(round(1 / 128 * Wr)))
+        out = []
+        for img, tl, br, ol in zip(imgs, pos - size / 2, pos + size / 2, overlay):
+            rgb = Image.fromarray((img * 255).astype(np.uint8)).resize((Wr, Hr), resample=Image.Resampling.NEAREST).convert("RGB")
+            if cfg.display_visitation:
+                alpha = ol[..., -1:] / 255
+                rgb = Image.fromarray((np.array(rgb) * (1 - alpha) + alpha * ol[..., :-1]).astype(np.uint8))
+            draw = ImageDraw.Draw(rgb, "RGBA")
+            rect = np.concatenate([tl, br])
+            draw.rectangle(tuple(rect + border), outline=(0, 0, 0, 80), width=border)
+            draw.rectangle(tuple(rect), outline=COLOR_AGENT, width=border)
+            out.append(rgb)
+        return out if return_pil_imgs else np.asarray(out)
+
+    def close(self, **kwargs):
         if not getattr(self, "_closed", True):
             self._closed = True
+            self.closed = True
             self._views = {}
             self._lib.apg_image_destroy(self._h)
             self._h = None
@@ -496,3 +621,35 @@ class ImageLocalizationVectorEnv(_ImageVectorEnvBase):
 
     def _autoreset_targets(self):
         return self._stream.draw_autoreset_targets()
+
+    def step(self, action):
+        out = super().step(action)
+        self._last_prediction = action["prediction"]
+        return out
+
+    def render(self, envs: Sequence[int] | None = None):
+        """ImageLocalizationVectorEnv.render (image_localization.py:183-220): the module's rendering plus the target
+        rectangle and the last prediction."""
+        from PIL import ImageDraw
+
+        from .style import COLOR_PRED
+
+        envs = np.arange(self.num_envs) if envs is None else np.asarray(envs)
+        imgs = super().render(envs, return_pil_imgs=True)
+        Wr, Hr, rs = self._render_geometry()
+        size = np.array(self._config.sensor_size) * self._config.sensor_scale * rs
+        border = max(1, int(round(1 / 128 * Wr)))
+        targets = self._views["cur_target_xy"].cpu().numpy()[envs]
+        last = getattr(self, "_last_prediction", None)
+        if last is not None:
+            last = (last.detach().cpu().numpy() if _is_torch(last) else np.asarray(last))[envs]
+        for i, (img, target) in enumerate(zip(imgs, targets)):
+            draw = ImageDraw.Draw(img, "RGBA")
+            t = self._to_render_coords(target)
+            draw.rectangle((tuple(t - size / 2), tuple(t + size / 2)), outline=COLOR_PRED + (100,), width=border)
+            if last is not None:
+                lp = self._to_render_coords(last[i])
+                rect = np.concatenate([lp - size / 2, lp + size / 2])
+                draw.rectangle(tuple(rect), outline=COLOR_PRED, width=border)
+                draw.rectangle(tuple(rect + border), outline=(0, 0, 0, 80), width=border)
+        return np.asarray(imgs)

@@ -15,8 +15,9 @@ import numpy as np
 
 from . import _capi
 from .floor_maps import FloorMapBank
-from .loss_fn import make_mse_loss_fn_and_target_space
-from .spaces import NEXT_STEP, ActivePerceptionActionSpace, Box, Dict, ImageSpace, batch_box
+from .loss_fn import WeightedLossFn, make_mse_loss_fn_and_target_space
+from .spaces import (NEXT_STEP, ActivePerceptionActionSpace, Box, Dict, ImageSpace, VectorEnvBase, batch_box,
+                     sparse_target_spaces)
 
 
 def _is_torch(x) -> bool:
@@ -34,15 +35,20 @@ def lidar_directions(beam_count: int, lidar_range: float) -> np.ndarray:
     return np.ascontiguousarray(unscaled * lidar_range, dtype=np.float32)
 
 
-class LIDARLocalization2DVectorEnv:
+class LIDARLocalization2DVectorEnv(VectorEnvBase):
+    """A `gymnasium.vector.VectorEnv` when gymnasium is importable.  Returned CUDA tensors are DLPack views of
+    engine-owned buffers: valid until the next step / reset / rollout, freed by close() (`copy_outputs=True` returns
+    private copies)."""
+
     metadata: dict[str, Any] = {"render_modes": ["rgb_array"], "render_fps": 4, "autoreset_mode": NEXT_STEP}
+    closed = False
 
     def __init__(self, num_envs: int, dataset, render_mode: Literal["rgb_array"] = "rgb_array",
                  static_map: bool = False, lidar_beam_count: int = 8, lidar_range: float = 5,
                  static_map_index: int = 0, prefetch: bool = True, prefetch_buffer_size: int = 128, *,
                  max_episode_steps: int = 100, device: int = 0, env_offset: int = 0, emit_cells: bool = False,
                  check_errors: Literal["step", "lazy", "never"] = "lazy", output: Literal["torch", "numpy"] = "torch",
-                 sparse: bool = False):
+                 sparse: bool = False, copy_outputs: bool = False):
         """`sparse=True` = the reference's `<id>-sparse` registration (SparsifyWrapper around every env,
         sparsify_wrapper.py:95-150): the loss only enters the reward of the step that terminates an env's episode and
         info["prediction"]["target"] becomes {"target": ..., "weight": float32(terminated)}."""
@@ -77,6 +83,8 @@ class LIDARLocalization2DVectorEnv:
         _capi.check(self._lib.apg_lidar_set_beams(self._h, _void(self._dirs)))
         self._views = self._make_views()
         self._has_reset = False
+        self._copy = bool(copy_outputs)
+        self._cuda_stream = 0
         self.spec = None
 
         obs = {"lidar": Box(low=0, high=1, shape=(self._B,), dtype=np.float32),
@@ -93,6 +101,10 @@ class LIDARLocalization2DVectorEnv:
         self.action_space = ActivePerceptionActionSpace(batch_box(inner, self.num_envs), batch_box(pred, self.num_envs))
         self.loss_fn, self.single_prediction_target_space = make_mse_loss_fn_and_target_space(2, -1, 1)
         self.prediction_target_space = batch_box(self.single_prediction_target_space, self.num_envs)
+        if self.sparse:  # SparsifyWrapper / SparsifyVectorWrapper (sparsify_wrapper.py:49-60): weighted loss + Dict target
+            self.single_prediction_target_space, self.prediction_target_space = sparse_target_spaces(
+                self.single_prediction_target_space, self.num_envs)
+            self.loss_fn = WeightedLossFn(self.loss_fn)
 
     prediction_space = property(lambda self: self.action_space["prediction"])
     inner_action_space = property(lambda self: self.action_space["action"])
@@ -133,7 +145,18 @@ class LIDARLocalization2DVectorEnv:
 
     def _out(self, name, as_numpy):
         v = self._views[name]
-        return v.cpu().numpy() if as_numpy else v
+        if as_numpy:
+            return v.cpu().numpy()
+        return v.clone() if self._copy else v
+
+    def _use_current_stream(self, tensor):
+        """Queue on torch's current stream: inputs produced on a side stream are complete, outputs ordered for readers."""
+        import torch
+
+        st = int(torch.cuda.current_stream(tensor.device).cuda_stream)
+        if st != self._cuda_stream:
+            _capi.check(self._lib.apg_lidar_set_stream(self._h, C.c_void_p(st)))
+            self._cuda_stream = st
 
     def _obs(self, as_numpy):
         keys = ["lidar", "odometry"] + ([] if self._static else ["map"]) + ["time_step"]
@@ -192,6 +215,7 @@ class LIDARLocalization2DVectorEnv:
                 raise ValueError("torch inputs must be contiguous float32 CUDA tensors")
             if tuple(a.shape) != (N, 2) or tuple(p.shape) != (N, 2):
                 raise ValueError(f"bad action/prediction shapes {tuple(a.shape)} {tuple(p.shape)}")
+            self._use_current_stream(a)
             _capi.check(self._lib.apg_lidar_step(self._h, a.data_ptr(), p.data_ptr()))
             self._maybe_poll(False)
             obs = self._obs(False)
@@ -233,6 +257,20 @@ class LIDARLocalization2DVectorEnv:
                 "avg_mse": t[3] / ep, "final_mse": t[4] / ep, "return": t[5] / ep}
 
     def rollout(self, actions, predictions, rewards=None, dones=None):
+        n_steps, N = int(actions.shape[0]), self.num_envs
+
+        def _chk(t, shape, dtypes, what):
+            if t is None:
+                return
+            if not (_is_torch(t) and t.is_cuda and t.is_contiguous() and str(t.dtype) in dtypes and tuple(t.shape) == shape):
+                raise ValueError(f"rollout: {what} must be a contiguous CUDA tensor of shape {shape} and dtype "
+                                 f"{' or '.join(dtypes)}")
+
+        _chk(actions, (n_steps, N, 2), ("torch.float32",), "actions")
+        _chk(predictions, (n_steps, N, 2), ("torch.float32",), "predictions")
+        _chk(rewards, (n_steps, N), ("torch.float32",), "rewards")
+        _chk(dones, (n_steps, N), ("torch.bool", "torch.uint8"), "dones")
+        self._use_current_stream(actions)
         _capi.check(self._lib.apg_lidar_rollout(
             self._h, actions.data_ptr(), predictions.data_ptr(), int(actions.shape[0]),
             None if rewards is None else rewards.data_ptr(), None if dones is None else dones.data_ptr()))
@@ -250,9 +288,10 @@ class LIDARLocalization2DVectorEnv:
     def render(self):
         raise NotImplementedError("render() is host-side tooling outside the hot path (DESIGN.md, out of scope)")
 
-    def close(self):
+    def close(self, **kwargs):
         if not getattr(self, "_closed", True):
             self._closed = True
+            self.closed = True
             self._views = {}
             self._lib.apg_lidar_destroy(self._h)
             self._h = None

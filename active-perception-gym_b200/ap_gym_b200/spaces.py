@@ -28,7 +28,11 @@ if _HAVE_GYM:
         NEXT_STEP = AutoresetMode.NEXT_STEP
     except AttributeError:  # gymnasium < 1.1
         NEXT_STEP = "NextStep"
+    # the engine's environments ARE gymnasium vector envs when gymnasium is there: VectorWrapper and the reference's
+    # wrappers assert isinstance(env, gymnasium.vector.VectorEnv)
+    VectorEnvBase = _gym.vector.VectorEnv
 else:
+    VectorEnvBase = object
 
     class Space:
         def __init__(self, shape=None, dtype=None, seed=None):
@@ -182,6 +186,19 @@ class ActivePerceptionActionSpace(Dict):
     @property
     def prediction_space(self):
         return self["prediction"]
+
+
+def sparse_target_spaces(single_target_space, n: int):
+    """`<id>-sparse` ids (SparsifyVectorWrapper, ap_gym/sparsify_wrapper.py:49-59): the prediction target becomes
+    Dict{"target": <space>, "weight": Box(0, 1, (), float32)}; returns (single, batched)."""
+    single = Dict({"target": single_target_space, "weight": Box(0, 1, (), np.float32)})
+    t = single_target_space
+    if isinstance(t, Discrete):
+        bt = MultiDiscrete(np.full((n,), t.n))
+    else:
+        bt = batch_box(t, n)
+    batched = Dict({"target": bt, "weight": Box(0, 1, (n,), np.float32)})
+    return single, batched
 
 
 def batch_box(space: Box, n: int, cls=None, **kw) -> Box:

@@ -640,8 +640,13 @@ struct apg_image_env {
   apg_img::TmaPlan tma;
   // small glimpses, classification, uint8 single-channel banks: persistent rollout kernel (csrc/apg_image_small.cu)
   apg_img::SmallPlan small;
-  void* d_thdr = nullptr;
   int force_slow = 0;
+  // *_host pipelining: the step kernels can be launched over a sub-range [r0, r1) of the environments, and `hold`
+  // keeps the episode clock / payload ring where they are until every chunk of the step has been launched
+  int r0 = 0, r1 = -1;
+  bool hold = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[8] = {};
   // bank
   void* d_bank = nullptr;
   int32_t* d_bank_labels = nullptr;
@@ -733,7 +738,7 @@ void fill_params(const apg_image_env* e, ImgParams& p, int mode, const float* d_
   const apg_image_cfg& c = e->cfg;
   p.N = c.num_envs; p.H = c.height; p.W = c.width; p.C = c.channels; p.S0 = c.sensor_h; p.S1 = c.sensor_w;
   p.P = e->P; p.K = c.num_classes; p.task = c.task; p.invert = c.randomly_invert_labels; p.track = c.track_visited;
-  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.pdl = e->pdl; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode; p.t_hdr = e->d_thdr; p.force_slow = e->force_slow;
+  p.words = e->words; p.T = c.step_limit; p.E = e->E; p.bank_pitch = e->bank_pitch; p.pitch = e->pitch; p.tile_rows = e->tile_rows; p.tile_bytes = e->tile_bytes; p.thread_blend = e->thread_blend; p.tb = e->tb; p.fast = e->cfg.blend_f32 ? 1 : 0; p.sparse = e->cfg.sparse_reward ? 1 : 0; p.split = e->split; p.pdl = e->pdl; p.tb_consec = e->tb_consec; p.g_hdr = static_cast<EnvHdr*>(e->d_ghdr); p.g_ctr = static_cast<EnvCtr*>(e->d_gctr); p.ctr_off = e->ctr_off; p.mode = mode; p.force_slow = e->force_slow; p.n0 = e->r0; p.n1 = e->r1 < 0 ? c.num_envs : e->r1;
   p.scale = c.sensor_scale;
   p.msl_x = c.max_step_length[0]; p.msl_y = c.max_step_length[1];
   // sensor_pos_lim_pixels (image_perception_module.py:419-423): x uses sensor_size[0], y uses sensor_size[1]
@@ -820,8 +825,10 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
     const int n = apg_img::tma_launch_step(e->tma, p, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "image step kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
-    e->t = t_after;
-    e->needs_reset = (mode == 0) && p.terminated;
+    if (!e->hold) {
+      e->t = t_after;
+      e->needs_reset = (mode == 0) && p.terminated;
+    }
     return APG_OK;
   }
   if (e->split == 2) {
@@ -839,8 +846,10 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   }
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
-  e->t = t_after;
-  e->needs_reset = (mode == 0) && p.terminated;
+  if (!e->hold) {
+    e->t = t_after;
+    e->needs_reset = (mode == 0) && p.terminated;
+  }
   return APG_OK;
 }
 
@@ -997,10 +1006,12 @@ int rollout_small(apg_image_env* e, const float* d_actions, const float* d_preds
     const int n = apg_img::small_launch(e->small, p, ro, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
-    e->ring_head = (e->ring_head + resets) % ring;
-    e->ring_count -= resets;
-    e->t = t;
-    e->needs_reset = need;
+    if (!e->hold) {
+      e->ring_head = (e->ring_head + resets) % ring;
+      e->ring_count -= resets;
+      e->t = t;
+      e->needs_reset = need;
+    }
     done += m;
   }
   return APG_OK;
@@ -1018,11 +1029,39 @@ int step_once(apg_image_env* e, const float* d_action, const float* d_pred, floa
     apg_image_env::Slot& s = e->ring[e->ring_head];
     int rc = launch(e, 1, d_action, d_pred, &s, reward2, done2);
     if (rc != APG_OK) return rc;
-    e->ring_head = (e->ring_head + 1) % (int)e->ring.size();
-    e->ring_count -= 1;
+    if (!e->hold) {
+      e->ring_head = (e->ring_head + 1) % (int)e->ring.size();
+      e->ring_count -= 1;
+    }
     return APG_OK;
   }
   return launch(e, 0, d_action, d_pred, nullptr, reward2, done2);
+}
+
+// advances the episode clock / payload ring by one step (what step_once does when `hold` is off)
+void commit_step(apg_image_env* e) {
+  if (e->needs_reset) {
+    e->ring_head = (e->ring_head + 1) % (int)e->ring.size();
+    e->ring_count -= 1;
+    e->t = 0;
+    e->needs_reset = false;
+  } else {
+    e->t += 1;
+    e->needs_reset = e->t >= e->cfg.step_limit;
+  }
+}
+
+// device-visible alias of a host pointer when the memory is page-locked (cudaHostAlloc / cudaHostRegister / torch pinned
+// memory): kernels can store results straight into it (posted writes over PCIe, no device-to-host copy afterwards)
+template <typename T>
+T* mapped_alias(T* h) {
+  if (!h) return nullptr;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<T*>(a.devicePointer) : nullptr;
 }
 
 }  // namespace
@@ -1055,6 +1094,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   APG_CHECK(cfg->device >= 0 && cfg->device < ndev, APG_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
   APG_CUDA(cudaSetDevice(cfg->device));
 
+  apg::apply_device_tuning();
   apg_image_env* e = new apg_image_env();
   e->cfg = *cfg;
   const size_t N = cfg->num_envs;
@@ -1143,6 +1183,8 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     A(cudaMalloc(&e->d_gctr, 2 * N * sizeof(EnvCtr)));
   }
   A(apg::dev_alloc(&e->d_in_action, N * 2));
+  A(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : e->ev_in) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   A(apg::dev_alloc(&e->d_in_pred, N * e->pred_width));
   int depth = cfg->payload_ring <= 0 ? APG_PAYLOAD_RING_DEFAULT : cfg->payload_ring;
   if (depth > APG_PAYLOAD_RING_MAX) depth = APG_PAYLOAD_RING_MAX;
@@ -1178,7 +1220,6 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   if (err == cudaSuccess && !generic_only && !e->thread_blend) {
     cudaError_t terr = cudaSuccess;
     if (apg_img::tma_plan(e->tma, *cfg, e->bank_pitch, e->words, &terr)) {
-      A(cudaMalloc(&e->d_thdr, apg_img::tma_header_bytes((long long)N)));
       A(apg_img::tma_preload(e->tma));
     }
     A(terr);
@@ -1212,7 +1253,9 @@ void apg_image_destroy(apg_image_env* e) {
   if (e->d_rej) cudaFree(e->d_rej);
   if (e->d_ghdr) cudaFree(e->d_ghdr);
   if (e->d_gctr) cudaFree(e->d_gctr);
-  if (e->d_thdr) cudaFree(e->d_thdr);
+  apg_img::tma_release(e->tma);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (auto& ev : e->ev_in) if (ev) cudaEventDestroy(ev);
   if (e->own_bank) cudaFree(e->d_bank);
   if (e->own_bank) cudaFree(e->d_bank_labels);
   apg::dev_free(e->b.d_glimpse); apg::dev_free(e->b.d_target_glimpse); apg::dev_free(e->b.d_glimpse_pos);
@@ -1398,15 +1441,53 @@ int apg_image_step_host(apg_image_env* e, const float* h_action, const float* h_
   APG_CHECK(e && h_action && h_pred, APG_ERR_INVALID, "apg_image_step_host: null argument");
   APG_CHECK(e->has_reset, APG_ERR_STATE, "step before reset");
   APG_CUDA(cudaSetDevice(e->cfg.device));
-  const size_t N = e->cfg.num_envs;
-  APG_CUDA(cudaMemcpyAsync(e->d_in_action, h_action, N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  APG_CUDA(cudaMemcpyAsync(e->d_in_pred, h_pred, N * e->pred_width * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  int rc = step_once(e, e->d_in_action, e->d_in_pred, nullptr, nullptr);
-  if (rc != APG_OK) return rc;
-  if (h_reward) APG_CUDA(cudaMemcpyAsync(h_reward, e->b.d_reward, N * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (h_terminated) APG_CUDA(cudaMemcpyAsync(h_terminated, e->b.d_terminated, N, cudaMemcpyDeviceToHost, e->stream));
-  if (h_truncated) APG_CUDA(cudaMemcpyAsync(h_truncated, e->b.d_truncated, N, cudaMemcpyDeviceToHost, e->stream));
-  if (h_glimpse) APG_CUDA(cudaMemcpyAsync(h_glimpse, e->b.d_glimpse, N * e->P * 4, cudaMemcpyDeviceToHost, e->stream));
+  const size_t N = e->cfg.num_envs, K = e->pred_width;
+  // Results go straight into page-locked caller buffers (the kernels store to their device aliases); pageable ones get
+  // device-to-host copies after the last kernel.  With h_glimpse page-locked the observation of this step is written
+  // to the caller's buffer INSTEAD of the engine's device buffer.
+  float* m_reward = mapped_alias(h_reward);
+  uint8_t* m_term = mapped_alias(h_terminated);
+  float* m_glimpse = mapped_alias(h_glimpse);
+  // The batch is cut into chunks: the host-to-device copy of chunk c+1 (copy stream) runs while chunk c is stepped
+  // (the special-purpose kernels take an environment range; the generic staged kernels step the whole batch at once)
+  const bool ranged = e->small.spec || (e->tma.spec && e->tma.have_map);
+  int chunks = 1;
+  if (ranged) chunks = N >= 32768 ? 4 : (N >= 8192 ? 2 : 1);
+  const size_t per = ((N + chunks - 1) / chunks + 1023) & ~(size_t)1023;  // chunk boundaries: multiples of 1024 envs
+  float* const glimpse_dev = e->b.d_glimpse;
+  if (m_glimpse) e->b.d_glimpse = m_glimpse;
+  e->hold = true;
+  int rc = APG_OK;
+  for (int c = 0; c < chunks && rc == APG_OK; ++c) {
+    const size_t lo = (size_t)c * per, hi = lo + per < N ? lo + per : N;
+    if (lo >= hi) break;
+    cudaError_t ce = cudaMemcpyAsync(e->d_in_action + lo * 2, h_action + lo * 2, (hi - lo) * 2 * sizeof(float),
+                                     cudaMemcpyHostToDevice, e->copy_stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(e->d_in_pred + lo * K, h_pred + lo * K, (hi - lo) * K * sizeof(float), cudaMemcpyHostToDevice,
+                           e->copy_stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_in[c], e->copy_stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->stream, e->ev_in[c], 0);
+    if (ce != cudaSuccess) {
+      rc = apg::fail(APG_ERR_CUDA, "apg_image_step_host: %s", cudaGetErrorString(ce));
+      break;
+    }
+    e->r0 = (int)lo; e->r1 = (int)hi;
+    rc = step_once(e, e->d_in_action, e->d_in_pred, m_reward, m_term);
+  }
+  e->hold = false;
+  e->r0 = 0; e->r1 = -1;
+  e->b.d_glimpse = glimpse_dev;
+  if (rc != APG_OK) {
+    cudaStreamSynchronize(e->copy_stream);
+    cudaStreamSynchronize(e->stream);
+    return rc;
+  }
+  commit_step(e);
+  if (h_reward && !m_reward) APG_CUDA(cudaMemcpyAsync(h_reward, e->b.d_reward, N * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (h_terminated && !m_term) APG_CUDA(cudaMemcpyAsync(h_terminated, e->b.d_terminated, N, cudaMemcpyDeviceToHost, e->stream));
+  if (h_glimpse && !m_glimpse) APG_CUDA(cudaMemcpyAsync(h_glimpse, e->b.d_glimpse, N * e->P * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (h_truncated) memset(h_truncated, 0, N);  // image environments never truncate (image_perception_module.py:212)
   APG_CUDA(cudaStreamSynchronize(e->stream));
   return APG_OK;
 }

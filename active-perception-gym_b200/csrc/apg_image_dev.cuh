@@ -26,7 +26,7 @@ struct ImgParams {
   int thread_blend;  // 1: thread-per-environment blend (small glimpses), 0: warp-per-environment
   EnvHdr* g_hdr;     // split == 2: tile headers / centres written by image_head_kernel, (n_sets, N)
   EnvCtr* g_ctr;
-  void* t_hdr;       // TMA path: tile headers written by tma_head_kernel, (n_sets, N) x 32 bytes
+  int n0, n1;        // environments [n0, n1) of the shard are stepped by this launch (special-purpose kernels)
   int force_slow;    // TMA path (tests): send every environment through the general per-output path
   int pdl;           // launched with programmatic stream serialization: wait for the previous grid explicitly
   int tb_consec;     // thread-blend path: use the consecutive-row variants

@@ -21,6 +21,10 @@
 // The payloads of the autoresets inside the window are drawn (in-stream, csrc/apg_payload.cu) before the launch.
 #include "apg_image_small.h"
 
+#include <cuda_pipeline.h>
+
+#include <cstdint>
+
 namespace apg_img {
 namespace {
 
@@ -57,7 +61,7 @@ __device__ __forceinline__ bool taps_consecutive(double cc, double half, double 
 template <int S0, int S1>
 __device__ __noinline__ void blend_general(const unsigned char* img, int H, int W, int pitch, double ccx, double ccy,
                                            double half0, double half1, double scale, double offy, double offx, float* out,
-                                           unsigned* vis_rows /* thread-private, stride kSmallThreads */) {
+                                           unsigned* vis_rows /* thread-private words, one per image row */) {
   unsigned colbits = 0u;
   int kc[S1];
   double wc[S1];
@@ -72,8 +76,8 @@ __device__ __noinline__ void blend_general(const unsigned char* img, int H, int 
     double wr;
     tap(ccy + ((double)i - half0) * scale, offy, H, kr, wr);
     if (vis_rows) {
-      vis_rows[kr * kSmallThreads] |= colbits;
-      vis_rows[(kr + 1) * kSmallThreads] |= colbits;
+      vis_rows[kr] |= colbits;
+      vis_rows[kr + 1] |= colbits;
     }
     const unsigned char* a = img + (size_t)kr * pitch;
     const unsigned char* b = a + pitch;
@@ -91,43 +95,100 @@ __device__ __noinline__ void blend_general(const unsigned char* img, int H, int 
   }
 }
 
-template <int S0, int S1>
+// asynchronous warp-cooperative copy global -> shared (cp.async, SASS LDGSTS): 16-byte pieces where both sides are
+// aligned, 4-byte pieces otherwise / for the tail.  `bytes` is a multiple of 4.
+__device__ __forceinline__ void warp_copy_async(unsigned char* dst, const unsigned char* src, int bytes, int lane) {
+  int done = 0;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int n16 = bytes >> 4;
+    for (int q = lane; q < n16; q += 32) __pipeline_memcpy_async(dst + q * 16, src + q * 16, 16);
+    done = n16 << 4;
+  }
+  for (int q = done + lane * 4; q < bytes; q += 128) __pipeline_memcpy_async(dst + q, src + q, 4);
+}
+
+struct SmallSmem {  // per-block layout of the dynamic shared memory
+  int fp_stride;    // bytes per environment footprint slot: (S0+1) rows of the bank pitch + 16 (bank-conflict padding)
+  int fp_bytes;     // per warp: 32 slots; the output staging (32 x P floats) aliases this area
+  int lg_bytes;     // per warp and stage: 32 x K floats
+  int warp_bytes;   // fp_bytes + 2 * lg_bytes
+  int vis_stride;   // words per environment of the visited mask: H | 1 (odd: conflict-free thread-private access)
+};
+
+__host__ __device__ inline SmallSmem small_smem(int S0, int P, int K, int H, int pitch) {
+  SmallSmem m;
+  m.fp_stride = (S0 + 1) * pitch + 16;
+  m.fp_bytes = 32 * m.fp_stride;
+  if (m.fp_bytes < 32 * P * 4) m.fp_bytes = 32 * P * 4;
+  m.lg_bytes = (32 * K * 4 + 15) & ~15;
+  m.warp_bytes = m.fp_bytes + 2 * m.lg_bytes;
+  m.vis_stride = H | 1;
+  return m;
+}
+
+template <int S0, int S1, int PITCH>  // PITCH = bytes per bank row (a multiple of 16)
 __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const ImgParams p, const SmallRollout ro) {
   constexpr int P = S0 * S1;
+  constexpr int kWarpsPerBlock = kSmallThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_out = reinterpret_cast<float*>(smem_raw);                           // (warps, 32, P) staging
-  unsigned* s_vis = reinterpret_cast<unsigned*>(smem_raw + (kSmallThreads / 32) * 32 * P * 4);  // (H, kSmallThreads)
+  const SmallSmem sm = small_smem(S0, P, p.K, p.H, PITCH);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = blockIdx.x * kSmallThreads + tid;
-  const bool live = n < p.N;
-  const int warp_env0 = blockIdx.x * kSmallThreads + warp * 32;
-  float* my_out = s_out + (warp * 32 + lane) * P;
-  unsigned* my_vis = s_vis + tid;
+  const int n = p.n0 + blockIdx.x * kSmallThreads + tid;  // [n0, n1): the environments this launch steps (n0 % 32 == 0)
+  const bool live = n < p.n1;
+  const int warp_env0 = p.n0 + blockIdx.x * kSmallThreads + warp * 32;
+  const int n_env = max(0, min(32, p.n1 - warp_env0));  // environments of this warp
+  unsigned char* wbase = smem_raw + warp * sm.warp_bytes;
+  unsigned char* s_fp = wbase;                                   // footprint slots of the warp's environments
+  float* s_out = reinterpret_cast<float*>(wbase);                // ... reused as the output staging (32 x P floats)
+  float* s_lg = reinterpret_cast<float*>(wbase + sm.fp_bytes);   // two stages of the warp's logits
+  unsigned* s_vis = reinterpret_cast<unsigned*>(smem_raw + kWarpsPerBlock * sm.warp_bytes);
+  float* my_out = s_out + lane * P;
+  unsigned* my_vis = s_vis + tid * sm.vis_stride;
   const unsigned char* bank = static_cast<const unsigned char*>(p.bank);
   const unsigned wmask = (p.W >= 32) ? 0xffffffffu : ((1u << p.W) - 1u);
+  const int lg_words = sm.lg_bytes >> 2;
+  constexpr int ch_per_env = (S0 + 1) * (PITCH >> 4);            // 16-byte pieces of one footprint (divisions by it fold)
 
   grid_dependency_wait(p.pdl);
 
-  // ---- state -> registers
+  // ---- state -> registers; the visited masks of the warp's environments are one contiguous run
   double px = 0.0, py = 0.0;
   int idx = 0, label = 0, fc = -1, lic = -1;
   float acc1 = 0.0f, acc2 = 0.0f, accr = 0.0f;
   unsigned char inv = 0;
   unsigned err = 0;
-  if (live && ro.first_mode != 2) {
-    const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
-    px = pp.x; py = pp.y;
-    idx = p.st_idx[n]; label = p.st_label[n];
-    acc1 = p.acc1[n]; acc2 = p.acc2[n]; accr = p.acc_ret[n];
-    fc = p.first_correct[n]; lic = p.last_incorrect[n];
-    if (p.invert) inv = p.st_inv[n];
-    if (p.track)
-      for (int r = 0; r < p.H; ++r) my_vis[r * kSmallThreads] = p.visited[(size_t)n * p.H + r];
+  if (ro.first_mode != 2) {
+    if (live) {
+      const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
+      px = pp.x; py = pp.y;
+      idx = p.st_idx[n]; label = p.st_label[n];
+      acc1 = p.acc1[n]; acc2 = p.acc2[n]; accr = p.acc_ret[n];
+      fc = p.first_correct[n]; lic = p.last_incorrect[n];
+      if (p.invert) inv = p.st_inv[n];
+    }
+    if (p.track) {
+      const unsigned* gv = p.visited + (size_t)warp_env0 * p.H;
+      unsigned* wv = s_vis + warp * 32 * sm.vis_stride;
+      for (int q = lane; q < n_env * p.H; q += 32) {
+        const int e = q / p.H;
+        wv[e * sm.vis_stride + (q - e * p.H)] = gv[q];
+      }
+    }
   }
+  // logits of the first step on their way (stage 0)
+  const unsigned char* pred_w = reinterpret_cast<const unsigned char*>(p.pred + (size_t)warp_env0 * p.K);
+  const size_t pred_step = (size_t)p.N * p.K * 4;
+  if (ro.first_mode != 2 && n_env > 0) warp_copy_async(reinterpret_cast<unsigned char*>(s_lg), pred_w, n_env * p.K * 4, lane);
+  __pipeline_commit();
+  __syncwarp();
   double st1 = 0.0, st2 = 0.0, st3 = 0.0, st4 = 0.0, st5 = 0.0, st0 = 0.0;  // this thread's share of the shard statistics
 
   int t = ro.t0;
   bool need_reset = ro.need_reset0 != 0;
+  const float2* act = reinterpret_cast<const float2*>(p.action) + n;
+  float* rew2 = p.reward2 ? p.reward2 + n : nullptr;
+  unsigned char* don2 = p.done2 ? p.done2 + n : nullptr;
+  float* gout = p.glimpse + (size_t)warp_env0 * P;
 #pragma unroll 1
   for (int k = 0; k < ro.n_steps; ++k) {
     const int mode = (k == 0 && ro.first_mode == 2) ? 2 : (need_reset ? 1 : 0);
@@ -135,82 +196,84 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     const int t_after = (mode == 0) ? t + 1 : 0;
     const bool terminated = (mode == 0) && (t_after >= p.T);
     const float time_obs = (float)(((double)t_after / (double)p.T) * 2.0 - 1.0);
-    const size_t koff = (size_t)k * p.N;
-    const float* x = p.pred + (koff + n) * p.K;
-    float* gout = p.glimpse + (size_t)warp_env0 * P;
+    const float* x = s_lg + (k & 1) * lg_words + lane * p.K;
 
+    // ---- inputs of the step
+    float a0 = 0.0f, a1 = 0.0f;
     if (live) {
-      // ---- inputs of the step, requested back to back
-      float a0 = 0.0f, a1 = 0.0f;
-      int slot = 0;
       if (mode == 0) {
-        const float2 aa = reinterpret_cast<const float2*>(p.action)[koff + n];
+        const float2 aa = act[(size_t)k * p.N];
         a0 = aa.x; a1 = aa.y;
       } else {
-        slot = (mode == 2) ? 0 : ro.reset_slot[k];
+        const int slot = (mode == 2) ? 0 : ro.reset_slot[k];
         const long long ni = ro.slot_idx[slot][n];
         const double2 pp = reinterpret_cast<const double2*>(ro.slot_pos[slot])[n];
         idx = (int)ni;
         p.index[n] = ni;
         if (p.invert) inv = ro.slot_inv[slot][n];
-        // ---- overlay / visited state of the new episode
         px = pp.x; py = pp.y;
       }
-      if (k + 1 < ro.n_steps) {  // next step's inputs -> L2 while this step computes (one 128-byte line per lane)
-        const char* nx = reinterpret_cast<const char*>(p.pred + ((koff + p.N) + warp_env0) * p.K);
-        const int bytes = 32 * p.K * 4;
-        if (warp_env0 + 32 <= p.N && lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + lane * 128));
-        if (warp_env0 + 32 <= p.N && lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.action + ((koff + p.N) + warp_env0) * 2) + lane * 128));
+    }
+    // ---- move (util.py:94-97, image_perception_module.py:206-209), overlay stamp of the PRE-move position
+    float base = 0.0f;
+    if (live && mode == 0) {
+      if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
+      if (p.track) {
+        p.stamp_xy[(size_t)(t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
+        p.stamp_xy[(size_t)(t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
       }
-
-      // ---- move (util.py:94-97, image_perception_module.py:206-209), overlay stamp of the PRE-move position
-      float base = 0.0f;
-      if (mode == 0) {
-        if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
-        if (p.track) {
-          p.stamp_xy[(size_t)(t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-          p.stamp_xy[(size_t)(t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
-        }
-        const float m = norm2f(a0, a1);
-        float q0 = a0, q1 = a1;
-        if (m > 1.0f) {
-          const float den = fmaxf(m, 1.0f);
-          q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
-          q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
-        }
-        px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
-        py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
-        base = __fmul_rn(-m, 1e-3f);
+      const float m = norm2f(a0, a1);
+      float q0 = a0, q1 = a1;
+      if (m > 1.0f) {
+        const float den = fmaxf(m, 1.0f);
+        q0 = __fmul_rn(__fdiv_rn(a0, den), 1.0f);
+        q1 = __fmul_rn(__fdiv_rn(a1, den), 1.0f);
       }
-      reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
+      px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
+      py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
+      base = __fmul_rn(-m, 1e-3f);
+    }
+    if (live) reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
 
-      // ---- taps, then the footprint words are requested: they land while the loss is computed
-      const double ccx = px * p.lim_x, ccy = py * p.lim_y;
-      int rmin, cmin;
-      double wr[S0], wc[S1];
-      bool consec = taps_consecutive<S0>(ccy, p.half0, p.scale, p.offy, p.H, rmin, wr, err);
+    // ---- taps; then the warp copies its 32 footprints cooperatively (consecutive lanes -> consecutive 16-byte pieces of
+    // one environment's (S0+1) contiguous bank rows): every request covers whole lines instead of 32 scattered sectors
+    const double ccx = px * p.lim_x, ccy = py * p.lim_y;
+    int rmin = 0, cmin = 0;
+    double wr[S0], wc[S1];
+    bool consec = true;
+    if (live) {
+      consec = taps_consecutive<S0>(ccy, p.half0, p.scale, p.offy, p.H, rmin, wr, err);
       consec = taps_consecutive<S1>(ccx, p.half1, p.scale, p.offx, p.W, cmin, wc, err) && consec;
-      const unsigned char* img = bank + (size_t)idx * p.H * p.bank_pitch;
-      unsigned fw[S0 + 1][3];
-      if (consec) {
-        const unsigned* src = reinterpret_cast<const unsigned*>(img + (size_t)rmin * p.bank_pitch + (cmin & ~3));
-        const int pitch_w = p.bank_pitch >> 2;
-#pragma unroll
-        for (int r = 0; r <= S0; ++r) {
-          fw[r][0] = __ldg(src + r * pitch_w);
-          fw[r][1] = __ldg(src + r * pitch_w + 1);
-          fw[r][2] = __ldg(src + r * pitch_w + 2);
-        }
+    }
+    {
+      const int my_row = idx * p.H + rmin;  // first bank row of this thread's footprint
+      const int total = n_env * ch_per_env;
+      for (int q = lane; q < ((total + 31) & ~31); q += 32) {
+        const int e = q / ch_per_env, c = q - e * ch_per_env;
+        const int row_e = __shfl_sync(0xffffffffu, my_row, e & 31);
+        if (q < total)
+          __pipeline_memcpy_async(s_fp + e * sm.fp_stride + c * 16, bank + (size_t)row_e * PITCH + c * 16, 16);
       }
+      __pipeline_commit();
+    }
+    // ---- next step's logits -> the other stage (they have the rest of the step to arrive); committed AFTER the
+    // footprints so that waiting for the footprints does not wait for them
+    if (k + 1 < ro.n_steps && n_env > 0)
+      warp_copy_async(reinterpret_cast<unsigned char*>(s_lg + ((k + 1) & 1) * lg_words), pred_w + (size_t)(k + 1) * pred_step,
+                      n_env * p.K * 4, lane);
+    __pipeline_commit();
 
-      // ---- label, cross-entropy, reward, flags (image_classification.py:113-127, loss_fn.py:100-110,212-220)
+    // ---- label, cross-entropy, reward, flags (image_classification.py:113-127, loss_fn.py:100-110,212-220); the
+    // logits of this step were requested one step ago
+    __pipeline_wait_prior(2);  // everything but the two newest groups (footprints, next logits) has landed
+    __syncwarp();
+    if (live) {
       if (mode != 0) {
         label = p.bank_labels[idx];
         if (p.invert && inv) label = p.K - label - 1;
       }
       if (p.invert) p.inverted_label[n] = (mode == 0) ? 2 : (int)inv;
       p.target_label[n] = label;
-      float pq = 0.0f, loss_f = 0.0f, m1 = 0.0f, m2 = 0.0f;
       if (mode != 2) {
         float mx = x[0];
         bool has_nan = isnan(mx);
@@ -225,19 +288,18 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
         for (int c = 0; c < p.K; ++c) s = __fadd_rn(s, expf(__fsub_rn(x[c], mx)));
         const float tl = __fsub_rn(x[label], mx);
         const float ce = -__fsub_rn(tl, logf(s));  // -log_softmax(x)[label], float32 like scipy
-        pq = __fdiv_rn(expf(tl), s);               // softmax(x)[label], overlay colour only
+        const float pq = __fdiv_rn(expf(tl), s);   // softmax(x)[label], overlay colour only
         const double loss_d = (double)ce * p.ce_scale + p.ce_offset;  // np.float64 scale -> float64 loss
-        loss_f = (float)loss_d;
-        m1 = pq;                            // correct_label_prob (active_classification_env.py:157-161)
-        m2 = (pq > p.inv_k) ? 1.0f : 0.0f;  // accuracy (:166-168)
+        const float m1 = pq;                            // correct_label_prob (active_classification_env.py:157-161)
+        const float m2 = (pq > p.inv_k) ? 1.0f : 0.0f;  // accuracy (:166-168)
         const float reward_f = (float)((double)base + (-loss_d));
         float reward_out = reward_f;
         if (p.sparse) reward_out = (float)((double)base - loss_d * (terminated ? 1.0 : 0.0));
         p.reward[n] = reward_out;
         p.base_reward[n] = base;
-        p.loss[n] = loss_f;
-        if (p.reward2) p.reward2[koff + n] = reward_out;
-        if (p.done2) p.done2[koff + n] = terminated ? 1 : 0;
+        p.loss[n] = (float)loss_d;
+        if (rew2) rew2[(size_t)k * p.N] = reward_out;
+        if (don2) don2[(size_t)k * p.N] = terminated ? 1 : 0;
         if (mode == 0) {  // overlay colour + episode statistics: real steps only
           if (p.track) p.stamp_q[(size_t)t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
           if (t_stamp == 0) { acc1 = 0.0f; acc2 = 0.0f; accr = 0.0f; fc = -1; lic = -1; }
@@ -257,17 +319,35 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
       p.terminated_out[n] = terminated ? 1 : 0;
       p.truncated_out[n] = 0;
       p.time_step[n] = time_obs;
-
-      // ---- visited bitmask (thread-private shared-memory words) + blend
+      // visited bitmask (thread-private shared-memory words)
       if (p.track && mode != 0)
-        for (int r = 0; r < p.H; ++r) my_vis[r * kSmallThreads] = 0u;
-      if (consec) {
-        if (p.track) {
-          const unsigned colbits = (((1u << (S1 + 1)) - 1u) << cmin) & wmask;
+        for (int r = 0; r < p.H; ++r) my_vis[r] = 0u;
+      if (p.track && consec) {
+        const unsigned colbits = (((1u << (S1 + 1)) - 1u) << cmin) & wmask;
 #pragma unroll
-          for (int r = 0; r <= S0; ++r)
-            if (rmin + r < p.H) my_vis[(rmin + r) * kSmallThreads] |= colbits;
-        }
+        for (int r = 0; r <= S0; ++r)
+          if (rmin + r < p.H) my_vis[rmin + r] |= colbits;
+      }
+    }
+
+    // ---- the footprints have landed: 3 aligned words per row -> registers, then the slots are free (the output staging
+    // aliases them)
+    __pipeline_wait_prior(1);
+    __syncwarp();
+    unsigned fw[S0 + 1][3];
+    if (live && consec) {
+      const unsigned* src = reinterpret_cast<const unsigned*>(s_fp + lane * sm.fp_stride + (cmin & ~3));
+      constexpr int pitch_w = PITCH >> 2;
+#pragma unroll
+      for (int r = 0; r <= S0; ++r) {
+        fw[r][0] = src[r * pitch_w];
+        fw[r][1] = src[r * pitch_w + 1];
+        fw[r][2] = src[r * pitch_w + 2];
+      }
+    }
+    __syncwarp();
+    if (live) {
+      if (consec) {
         // every footprint pixel is converted once; row r + 1 of the window is the bottom row of sensor row r
         const int sh = (cmin & 3) * 8;
         double top[S1 + 1], bot[S1 + 1];
@@ -295,27 +375,25 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
           for (int j = 0; j <= S1; ++j) top[j] = bot[j];
         }
       } else {
-        blend_general<S0, S1>(img, p.H, p.W, p.bank_pitch, ccx, ccy, p.half0, p.half1, p.scale, p.offy, p.offx, my_out,
-                              p.track ? my_vis : nullptr);
+        blend_general<S0, S1>(bank + (size_t)idx * p.H * PITCH, p.H, p.W, PITCH, ccx, ccy, p.half0, p.half1,
+                              p.scale, p.offy, p.offx, my_out, p.track ? my_vis : nullptr);
       }
     }
     // ---- the warp's 32 glimpses leave as one contiguous run of 128-bit stores
     __syncwarp();
-    {
-      const int n_env = min(32, p.N - warp_env0);
-      if (n_env > 0) {
-        const int total = n_env * P;  // floats; the run starts 16-byte aligned (warp_env0 is a multiple of 32)
-        const float4* s4 = reinterpret_cast<const float4*>(s_out + warp * 32 * P);
-        float4* g4 = reinterpret_cast<float4*>(gout);
-        const int n4 = total >> 2;
-        for (int q = lane; q < n4; q += 32) g4[q] = s4[q];
-        for (int q = (n4 << 2) + lane; q < total; q += 32) gout[q] = s_out[warp * 32 * P + q];
-      }
+    if (n_env > 0) {
+      const int total = n_env * P;  // floats; the run starts 16-byte aligned (warp_env0 is a multiple of 32)
+      const float4* s4 = reinterpret_cast<const float4*>(s_out);
+      float4* g4 = reinterpret_cast<float4*>(gout);
+      const int n4 = total >> 2;
+      for (int q = lane; q < n4; q += 32) g4[q] = s4[q];
+      for (int q = (n4 << 2) + lane; q < total; q += 32) gout[q] = s_out[q];
     }
     __syncwarp();
     t = t_after;
     need_reset = terminated;
   }
+  __pipeline_wait_prior(0);
 
   // ---- registers -> state
   if (live) {
@@ -324,9 +402,15 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     p.acc1[n] = acc1; p.acc2[n] = acc2; p.acc_ret[n] = accr;
     p.first_correct[n] = fc; p.last_incorrect[n] = lic;
     if (p.invert) p.st_inv[n] = inv;
-    if (p.track)
-      for (int r = 0; r < p.H; ++r) p.visited[(size_t)n * p.H + r] = my_vis[r * kSmallThreads];
     if (err) atomicOr(p.err, err);
+  }
+  if (p.track) {
+    unsigned* gv = p.visited + (size_t)warp_env0 * p.H;
+    const unsigned* wv = s_vis + warp * 32 * sm.vis_stride;
+    for (int q = lane; q < n_env * p.H; q += 32) {
+      const int e = q / p.H;
+      gv[q] = wv[e * sm.vis_stride + (q - e * p.H)];
+    }
   }
   // shard-wide episode statistics: warp sums, one atomic per warp and statistic
   if (__any_sync(0xffffffffu, st0 != 0.0)) {
@@ -347,17 +431,20 @@ bool small_plan(SmallPlan& plan, const apg_image_cfg& cfg, int words) {
   if (cfg.bank_dtype != APG_BANK_U8 || cfg.sensor_scale != 1.0 || cfg.blend_f32) return false;
   if (cfg.task != APG_TASK_CLASSIFICATION) return false;
   if (!(cfg.sensor_h == 5 && cfg.sensor_w == 5 && cfg.channels == 1)) return false;
-  if (words != 1 || cfg.height > 32 || cfg.height < 6 || cfg.width < 6) return false;
-  plan.spec = 1;
+  if (words != 1 || cfg.height > 32 || cfg.height < 6 || cfg.width < 17) return false;  // bank rows of 32 bytes
   plan.threads = kSmallThreads;
-  plan.smem = (size_t)(kSmallThreads / 32) * 32 * 25 * 4 + (size_t)cfg.height * kSmallThreads * 4;
+  const int pitch = (cfg.width * cfg.channels + 15) & ~15;
+  const SmallSmem sm = small_smem(5, 25, cfg.num_classes, cfg.height, pitch);
+  plan.smem = (size_t)(kSmallThreads / 32) * sm.warp_bytes + (size_t)kSmallThreads * sm.vis_stride * 4;
+  if (plan.smem > 30 * 1024) return false;  // 7 blocks per SM must fit (one wave at 65536 envs)
+  plan.spec = 1;
   return true;
 }
 
 cudaError_t small_preload(const SmallPlan& plan) {
   if (!plan.spec) return cudaSuccess;
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5>);
+  return cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32>);
 }
 
 int small_launch(const SmallPlan& plan, const ImgParams& p, const SmallRollout& ro, cudaStream_t stream) {
@@ -368,10 +455,10 @@ int small_launch(const SmallPlan& plan, const ImgParams& p, const SmallRollout& 
   cfg.stream = stream;
   cfg.attrs = at;
   cfg.numAttrs = p.pdl ? 1 : 0;
-  cfg.gridDim = dim3((unsigned)((p.N + kSmallThreads - 1) / kSmallThreads));
+  cfg.gridDim = dim3((unsigned)((p.n1 - p.n0 + kSmallThreads - 1) / kSmallThreads));
   cfg.blockDim = dim3(kSmallThreads);
   cfg.dynamicSmemBytes = plan.smem;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5>, p, ro);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32>, p, ro);
   if (e != cudaSuccess) return -(int)e;
   return 1;
 }

@@ -3,37 +3,51 @@
 //   ImagePerceptionModule.step / get_glimpse      ap_gym/envs/image/image_perception_module.py:191-217,294-331
 //   ImageLocalizationVectorEnv._step              ap_gym/envs/image_localization.py:151-181
 //
-// Two launches per vector step:
-//   tma_head_kernel   thread = environment: the two scalar chains of apg_image_dev.cuh (move / loss / reward / flags /
-//                     statistics) and a 32-byte tile header per glimpse (sensor centre in pixels, TMA box coordinates);
-//   tma_blend_kernel  PERSISTENT warps, warp = environment, lane = (sensor column, channel).  Each warp walks its
-//                     environments with a two-stage ring of shared-memory tiles: one elected lane issues ONE tensor-map
-//                     copy (cp.async.bulk.tensor.2d, SASS UTMALDG) per glimpse -- box = (S0+1) rows x 48 bytes of the
-//                     bank image, start aligned down to 16 bytes so that every row is exactly two 32-byte sectors -- for
-//                     environment k+1 while the warp blends environment k; completion is an mbarrier transaction count,
-//                     nothing in the block waits for anything but its own tile (no __syncthreads in the loop).
+// ONE launch per vector step, PERSISTENT warps.  A warp owns a group of <= 32 consecutive environments:
+//   phase H  lane = environment: the two scalar chains of apg_image_dev.cuh (move / loss / reward / flags / statistics)
+//            and a 32-byte tile header per environment in the warp's shared memory (sensor centre in pixels, first tap
+//            row / column, tensor-map box coordinates);
+//   phase B  warp = environment, lane = (sensor column, channel): the warp walks its environments with a two-stage ring
+//            of shared-memory tiles.  One elected lane issues ONE tensor-map copy (cp.async.bulk.tensor.2d, SASS
+//            UTMALDG) per glimpse -- box = (S0+1) rows x 48 bytes of the bank image, start aligned down to 16 bytes --
+//            for environment k+1 while the warp blends environment k; completion is an mbarrier transaction count.
+//            Nothing in the loop synchronises more than one warp.
 // Blend: the reference's 4-term float64 sum in scipy's order (bit-exact pixels).  The exact uint8 -> float64 pixel
-// value float64(float32(u8) / 255) comes from a 256-entry table in shared memory, replicated 16x so that the 64-bit
-// lookups of a half-warp never collide (one LDS.64 instead of the five-instruction conversion); with consecutive tap
-// rows every tile row is fetched and converted once.  Environments whose taps are not consecutive (a float64 rounding
-// accident at a grid line, probability ~1e-15 per tap) take a general per-output path from global memory.
+// value float64(float32(u8) / 255) comes from a 256-entry table, replicated 16x so that the 64-bit lookups of a
+// half-warp never collide (one LDS.64 instead of the five-instruction conversion); the 32 KB table is computed once on
+// the host and lands in every block's shared memory with one bulk copy (cp.async.bulk, SASS UBLKCP).  Taps: the first
+// tap of each axis is scipy's find_indices in full (phase H), the others are assumed consecutive and VERIFIED -- their
+// weight w = coord - grid[k0 + t], computed exactly like the reference's, must lie in [0, 1), which is precisely the
+// condition under which find_indices returns that index.  With consecutive tap rows every tile row is fetched and
+// converted once.  Environments that break the pattern (a float64 rounding accident at a grid line, probability
+// ~1e-15 per tap) take a general per-output path from global memory.
 #include "apg_image_tma.h"
 
 #include <cstdint>
+#include <vector>
 
 namespace apg_img {
 namespace {
 
+#ifndef APG_TMA_MINB
+#define APG_TMA_MINB 4
+#endif
+#ifndef APG_TMA_REPLICAS
+#define APG_TMA_REPLICAS 16
+#endif
+#ifndef APG_TMA_ARITH
+#define APG_TMA_ARITH 0  // 1: convert pixels arithmetically (px_to_f64) instead of the table lookup (experiment)
+#endif
 constexpr int kWarps = 8;
-constexpr int kReplicas = 16;                       // table copies: lane & 15 picks its own -> conflict-free LDS.64
+constexpr int kReplicas = APG_TMA_REPLICAS;         // table copies: lane & 15 picks its own -> conflict-free LDS.64
 constexpr int kTableBytes = 256 * kReplicas * 8;    // 32 KB
 
-struct __align__(16) TileHdr {  // 32 bytes per glimpse, head kernel -> blend kernel (through L2)
+struct __align__(16) TileHdr {  // 32 bytes per glimpse, phase H -> phase B (warp-private shared memory)
   double ccx, ccy;  // sensor centre in image-centred pixel coordinates (float64, like the reference)
   int y0;           // tensor-map row of the box: bank index * H + first tap row
   int x0;           // tensor-map byte column of the box: first tap column * C, aligned down to 16
   int idx;          // bank index (general path)
-  int pad;
+  int rc;           // first tap row | first tap column << 16
 };
 
 template <int S0, int S1, int C>
@@ -45,8 +59,8 @@ struct Geom {
   static constexpr int TILE_BYTES = BOX_W * BOX_H;
   static constexpr int TILE_STRIDE = (TILE_BYTES + 127) & ~127;  // tensor-map copies land on 128-byte boundaries
   static constexpr int TAPS = S0 + S1;
-  static constexpr int WARP_BYTES = (2 * TILE_STRIDE + TAPS * 16 + 16 + 127) & ~127;
-  static constexpr int SMEM = kTableBytes + kWarps * WARP_BYTES;
+  static constexpr int WARP_BYTES = (2 * TILE_STRIDE + TAPS * 16 + 32 * 32 + 16 + 127) & ~127;
+  static constexpr int SMEM = kTableBytes + kWarps * WARP_BYTES + 128;
   static_assert(G <= 32 && TAPS <= 32, "one lane per (column, channel) and one lane per tap");
 };
 
@@ -68,6 +82,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// the same on shared-window addresses computed once (the generic -> shared conversion is not free)
+__device__ __forceinline__ void mbar_expect_tx_u(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// exactly one lane of the (converged) warp gets true
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // one glimpse footprint: box (BOX_W bytes x BOX_H rows) of the bank tensor at (x, y) -> shared memory, completion
 // counted on `bar`
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) {
@@ -77,13 +111,22 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_u(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+// contiguous global -> shared bulk copy (bytes a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
-__device__ __forceinline__ TileHdr load_hdr(const TileHdr* g) {
-  const int4 a = reinterpret_cast<const int4*>(g)[0], b = reinterpret_cast<const int4*>(g)[1];
-  TileHdr h;
-  h.ccx = __hiloint2double(a.y, a.x); h.ccy = __hiloint2double(a.w, a.z);
-  h.y0 = b.x; h.x0 = b.y; h.idx = b.z; h.pad = b.w;
-  return h;
+// (double)k for 0 <= k < 2^31 without the conversion unit: 2^52 + k is exact in float64
+__device__ __forceinline__ double int_to_double(int k) {
+  return __hiloint2double(0x43300000, k) - 4503599627370496.0;
 }
 
 // tile header of one glimpse centred at (ccx, ccy): the tap coordinates are monotone in the tap number, so the first and
@@ -98,199 +141,194 @@ __device__ __forceinline__ void write_hdr(const ImgParams& p, TileHdr* out, doub
   int rmin, cmin;
   double w;
   tap_row(y0, p.offy, p.H, true, rmin, w);
-  tap(x0, p.offx, p.W, cmin, w);
+  tap_row(x0, p.offx, p.W, true, cmin, w);
   int4 a, b;
   a.x = __double2loint(ccx); a.y = __double2hiint(ccx); a.z = __double2loint(ccy); a.w = __double2hiint(ccy);
-  b.x = idx * p.H + rmin; b.y = (cmin * C) & ~15; b.z = idx; b.w = 0;
+  b.x = idx * p.H + rmin; b.y = (cmin * C) & ~15; b.z = idx; b.w = rmin | (cmin << 16);
   reinterpret_cast<int4*>(out)[0] = a;
   reinterpret_cast<int4*>(out)[1] = b;
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) tma_head_kernel(const ImgParams p) {
-  grid_dependency_wait(p.pdl);
-  __shared__ double s_stats[6];
-  const bool ep_end = (p.mode == 0) && p.terminated;
-  if (ep_end && threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
-  if (ep_end) __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < p.N) {
-    double px = 0.0, py = 0.0, tcx = 0.0, tcy = 0.0;
-    int idx = 0;
-    unsigned err = 0;
-    env_move(p, n, px, py, tcx, tcy, idx, err);
-    TileHdr* hdr = static_cast<TileHdr*>(p.t_hdr);
-    write_hdr<C>(p, hdr + n, px * p.lim_x, py * p.lim_y, idx, err);
-    if ((p.task == APG_TASK_LOCALIZATION) && (p.mode != 0)) write_hdr<C>(p, hdr + p.N + n, tcx, tcy, idx, err);
-    env_loss(p, n, s_stats, ep_end, err);
-    if (err) atomicOr(p.err, err);
-  }
-  if (ep_end) {
-    __syncthreads();
-    if (threadIdx.x < 6) atomicAdd(p.stats + threadIdx.x, s_stats[threadIdx.x]);
-  }
-}
-
-// General path of one environment (any tap pattern): every lane evaluates outputs o = lane, lane + 32, ... from global
-// memory with the reference's per-point taps; rows past the image (weight exactly 0, see tap_row) are read from the row
-// above.  Rare by construction -- kept out of line.
+// General path of one environment (any tap pattern): scipy's per-point taps, pixels straight from the bank; rows /
+// columns past the image (weight exactly 0) are read from the line before.  Also updates the visited mask.  Rare by
+// construction -- kept out of line.
 template <int S0, int S1, int C>
-__device__ __noinline__ void blend_env_general(const unsigned char* bank, int H, int bank_pitch, const Tap* taps, int idx,
-                                               int lane, float* out) {
+__device__ __noinline__ void blend_env_general(const unsigned char* bank, int H, int W, int words, int bank_pitch, double ccx,
+                                               double ccy, double half0, double half1, double scale, double offy,
+                                               double offx, int idx, int lane, float* out, unsigned* vm) {
   using Gm = Geom<S0, S1, C>;
   const unsigned char* img = bank + (size_t)idx * H * bank_pitch;
   for (int o = lane; o < Gm::P; o += 32) {
     const int i = o / Gm::G, jc = o - i * Gm::G, j = jc / C, c = jc - j * C;
-    const Tap rt = taps[i], ct = taps[S0 + j];
-    const int r0 = rt.k, r1 = min(rt.k + 1, H - 1);
-    const unsigned char* a = img + (size_t)r0 * bank_pitch + ct.k * C + c;
-    const unsigned char* b = img + (size_t)r1 * bank_pitch + ct.k * C + c;
+    int kr, kc;
+    double wy, wx;
+    tap(ccy + ((double)i - half0) * scale, offy, H, kr, wy);
+    tap(ccx + ((double)j - half1) * scale, offx, W, kc, wx);
+    const unsigned char* a = img + (size_t)kr * bank_pitch + kc * C + c;
+    const unsigned char* b = a + bank_pitch;
     const double p00 = px_to_f64(a[0]), p01 = px_to_f64(a[C]), p10 = px_to_f64(b[0]), p11 = px_to_f64(b[C]);
-    const double wy = rt.w, omy = 1.0 - rt.w, wx = ct.w, omx = 1.0 - ct.w;
+    const double omy = 1.0 - wy, omx = 1.0 - wx;
     double acc = p00 * (omy * omx);
     acc = acc + p01 * (omy * wx);
     acc = acc + p10 * (wy * omx);
     acc = acc + p11 * (wy * wx);
     out[o] = (float)acc;
+    if (vm && c == 0) {  // rows {kr, kr+1} x columns {kc, kc+1}
+      for (int dr = 0; dr < 2; ++dr)
+        for (int dc = 0; dc < 2; ++dc) atomicOr(vm + (kr + dr) * words + ((kc + dc) >> 5), 1u << ((kc + dc) & 31));
+    }
   }
 }
 
 template <int S0, int S1, int C>
-__global__ void __launch_bounds__(kWarps * 32, 4) tma_blend_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kWarps * 32, APG_TMA_MINB)
+tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, const double* __restrict__ g_table,
+                const int group_size, const int n_groups) {
   using Gm = Geom<S0, S1, C>;
   extern __shared__ __align__(128) unsigned char smem[];
   double* table = reinterpret_cast<double*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* wbase = smem + kTableBytes + warp * Gm::WARP_BYTES;
   unsigned char* tiles = wbase;
-  Tap* taps = reinterpret_cast<Tap*>(wbase + 2 * Gm::TILE_STRIDE);
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16);
+  TileHdr* hdrs = reinterpret_cast<TileHdr*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16 + 32 * 32);
+  unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + kTableBytes + kWarps * Gm::WARP_BYTES);
+  __shared__ double s_stats[6];
 
   // block prologue (independent of the previous grid, so it overlaps its tail under programmatic dependent launch):
-  // the conversion table and this warp's two barriers
-  for (int q = tid; q < 256 * kReplicas; q += kWarps * 32) table[q] = px_to_f64((unsigned char)(q >> 4));
+  // barriers, then the conversion table arrives with one bulk copy
+  if (tid == 0) mbar_init(tbar, 1);
   if (lane == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 6) s_stats[tid] = 0.0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(tbar, kTableBytes);
+    bulk_load(table, g_table, kTableBytes, tbar);
+  }
   grid_dependency_wait(p.pdl);
 
+  const bool ep_end = (p.mode == 0) && p.terminated;
   const int n_sets = ((p.task == APG_TASK_LOCALIZATION) && (p.mode != 0)) ? 2 : 1;
-  const int n_work = n_sets * p.N;
-  const int stride = gridDim.x * kWarps;
-  const TileHdr* hdrs = static_cast<const TileHdr*>(p.t_hdr);
-
-  // lane = (column j, channel c) of the sensor row; lanes past the row run column G-1 and skip the store
+  // lane = (column j, channel c) of the sensor row; lanes past the row run element G-1 and skip the store
   const bool lane_ok = lane < Gm::G;
   const int jc = lane_ok ? lane : Gm::G - 1;
-  const int j = jc / C, c = jc - j * C;
+  const int j = jc / C;
   const double* tab = table + (lane & (kReplicas - 1));
+  // sensor_scale == 1 on this path (tma_plan): tap coordinate t of an axis = centre + (t - (S-1)/2), the offsets are
+  // compile-time constants for the rows and one register per lane for its column
+  constexpr double kHalf0 = (S0 - 1) / 2.0, kHalf1 = (S1 - 1) / 2.0;
+  const double col_off = (double)j - kHalf1, col_j = (double)j;
+  const double row_off_lane = (double)min(lane, S0 - 1) - kHalf0, row_lane = (double)min(lane, S0 - 1);
+  const unsigned long long wmask = (p.W >= 64) ? ~0ull : ((1ull << p.W) - 1ull);
+  const int vis_r = (p.words == 2) ? (lane >> 1) : lane, vis_w = (p.words == 2) ? (lane & 1) : 0;
+  const unsigned tiles_u = smem_u32(tiles), mbar_u = smem_u32(mbar);  // shared-window addresses of the ring
+  const int vis_words = p.H * p.words;
+  bool table_ready = false;
+  int it = 0;  // tiles consumed so far by this warp: stage = it & 1, barrier parity = (it >> 1) & 1
 
-  int q = blockIdx.x * kWarps + warp;
-  TileHdr h0, h1;
-  h0.ccx = h0.ccy = 0.0; h0.y0 = h0.x0 = h0.idx = h0.pad = 0;
-  h1 = h0;
-  if (q < n_work) {
-    h0 = load_hdr(hdrs + q);
-    if (lane == 0) {
-      mbar_expect_tx(&mbar[0], Gm::TILE_BYTES);
-      tma_load_2d(tiles, &tmap, h0.x0, h0.y0, &mbar[0]);
+  for (int g = blockIdx.x * kWarps + warp; g < n_groups; g += gridDim.x * kWarps) {
+    const int env_base = p.n0 + g * group_size;
+    const int cnt = min(group_size, p.n1 - env_base);
+    double tcx = 0.0, tcy = 0.0;
+    int idx = 0;
+    for (int set = 0; set < n_sets; ++set) {
+      // ---------------------------------------------------------------- phase H: lane = environment
+      if (lane < cnt) {
+        unsigned err = 0;
+        const int n = env_base + lane;
+        if (set == 0) {
+          double px = 0.0, py = 0.0;
+          env_move(p, n, px, py, tcx, tcy, idx, err);
+          write_hdr<C>(p, hdrs + lane, px * p.lim_x, py * p.lim_y, idx, err);
+          env_loss(p, n, s_stats, ep_end, err);
+        } else {
+          write_hdr<C>(p, hdrs + lane, tcx, tcy, idx, err);
+        }
+        if (err) atomicOr(p.err, err);
+      }
+      __syncwarp();
+      if (!table_ready) {
+        mbar_wait(tbar, 0);
+        table_ready = true;
+      }
+      // ---------------------------------------------------------------- phase B: warp = environment
+      float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P + jc;
+      unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
+      if (elect_one()) {
+        const int2 xy = reinterpret_cast<const int2*>(hdrs)[2];  // (y0, x0) of environment 0
+        mbar_expect_tx_u(mbar_u + 8 * (it & 1), Gm::TILE_BYTES);
+        tma_load_2d_u(tiles_u + (it & 1) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (it & 1));
+      }
+      for (int e = 0; e < cnt; ++e, ++it, out += Gm::P) {
+        const int s = it & 1;
+        // stage s^1 was last read in the previous iteration (program order + the __syncwarp that ends it): refill it
+        if (e + 1 < cnt && elect_one()) {
+          const int2 xy = reinterpret_cast<const int2*>(hdrs + e + 1)[2];
+          mbar_expect_tx_u(mbar_u + 8 * (s ^ 1), Gm::TILE_BYTES);
+          tma_load_2d_u(tiles_u + (s ^ 1) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (s ^ 1));
+        }
+        const double2 cc = reinterpret_cast<const double2*>(hdrs + e)[0];  // sensor centre (x, y), broadcast
+        const int2 hi = reinterpret_cast<const int2*>(hdrs + e)[3];        // (bank index, first taps)
+        const int rmin = hi.y & 0xffff, cmin = hi.y >> 16;
+        // ---- taps under the consecutive-index assumption (see the file header): the weight of tap t of an axis is
+        // coord_t - grid[k0 + t] with grid[k] = k - off; this lane's column weight lives in registers, the row
+        // weights are recomputed inside the row loop (three float64 adds per row, no shared-memory round trip)
+        const double gy0 = int_to_double(rmin) - p.offy, gx0 = int_to_double(cmin) - p.offx;
+        const double wx = (cc.x + col_off) - (gx0 + col_j), omx = 1.0 - wx;
+        const double wyl = (cc.y + row_off_lane) - (gy0 + row_lane);  // lane t < S0 verifies tap row t
+        const bool bad = !(wx >= 0.0) || !(wx < 1.0) || (cmin + j > p.W - 1) || !(wyl >= 0.0) || !(wyl < 1.0) ||
+                         (rmin + min(lane, S0 - 1) > p.H - 1);
+        const bool slow = __any_sync(0xffffffffu, bad) || p.force_slow;
+        if (vm && p.mode != 0) {
+          for (int w = lane; w < vis_words; w += 32) vm[w] = 0u;
+          __syncwarp();
+        }
+        mbar_wait_u(mbar_u + 8 * s, (unsigned)((it >> 1) & 1));  // this environment's tile has landed
+        if (!slow) {
+          const unsigned char* colp = tiles + s * Gm::TILE_STRIDE + ((cmin * C) & 15) + jc;
+#if APG_TMA_ARITH
+#define APG_PX(b) px_to_f64((unsigned char)(b))
+#else
+#define APG_PX(b) tab[(int)(b) * kReplicas]
+#endif
+          double p00 = APG_PX(colp[0]), p01 = APG_PX(colp[C]);
+#pragma unroll
+          for (int i = 0; i < S0; ++i) {
+            colp += Gm::BOX_W;
+            const double p10 = APG_PX(colp[0]), p11 = APG_PX(colp[C]);
+            const double wy = (cc.y + ((double)i - kHalf0)) - (gy0 + (double)i), omy = 1.0 - wy;
+            double acc = p00 * (omy * omx);  // the reference's leading `0.0 +` is an exact no-op for products >= +0
+            acc = acc + p01 * (omy * wx);
+            acc = acc + p10 * (wy * omx);
+            acc = acc + p11 * (wy * wx);
+            // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
+            if (lane_ok) out[i * Gm::G] = (float)acc;
+            p00 = p10;
+            p01 = p11;
+          }
+          // visited bitmask: rows rmin .. rmin + S0 x columns cmin .. cmin + S1; lane = (row, word), one RED per lane
+          if (vm) {
+            const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cmin) & wmask);
+            const unsigned bits = vis_w == 0 ? (unsigned)cb : (unsigned)(cb >> 32);
+            if (vis_r <= S0 && rmin + vis_r < p.H && bits) atomicOr(vm + (rmin + vis_r) * p.words + vis_w, bits);
+          }
+        } else {
+          blend_env_general<S0, S1, C>(static_cast<const unsigned char*>(p.bank), p.H, p.W, p.words, p.bank_pitch, cc.x,
+                                       cc.y, p.half0, p.half1, p.scale, p.offy, p.offx, hi.x, lane, out - jc, vm);
+        }
+        if (vm) vm += vis_words;
+        __syncwarp();  // every lane is done with stage s before it is refilled
+      }
     }
   }
-  if (q + stride < n_work) h1 = load_hdr(hdrs + q + stride);
-
-  for (int it = 0; q < n_work; q += stride, ++it) {
-    const int s = it & 1;
-    const int qn = q + stride;
-    // stage s^1 was last read in the previous iteration (program order + the __syncwarp that ends it): refill it
-    if (qn < n_work && lane == 0) {
-      mbar_expect_tx(&mbar[s ^ 1], Gm::TILE_BYTES);
-      tma_load_2d(tiles + (s ^ 1) * Gm::TILE_STRIDE, &tmap, h1.x0, h1.y0, &mbar[s ^ 1]);
-    }
-    TileHdr h2 = h1;
-    if (qn + stride < n_work) h2 = load_hdr(hdrs + qn + stride);  // lands while this environment is blended
-
-    const int set = (q >= p.N) ? 1 : 0;
-    const int n = q - set * p.N;
-    float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)n * Gm::P;
-
-    // ---- taps: lane i < S0 -> sensor row i, lane S0 + j -> sensor column j (scipy find_indices, float64)
-    int k = 0;
-    if (lane < Gm::TAPS) {
-      const bool is_row = lane < S0;
-      const int t = is_row ? lane : lane - S0;
-      const double coord = (is_row ? h0.ccy : h0.ccx) + ((double)t - (is_row ? p.half0 : p.half1)) * p.scale;
-      double w;
-      tap_row(coord, is_row ? p.offy : p.offx, is_row ? p.H : p.W, is_row, k, w);
-      Tap tp;
-      tp.w = w; tp.k = k; tp.pad = 0;
-      taps[lane] = tp;
-    }
-    const int rmin = __shfl_sync(0xffffffffu, k, 0), cmin = __shfl_sync(0xffffffffu, k, S0);
-    // fast path needs consecutive tap rows (vertical reuse) and columns inside the staged box
-    const bool mine_bad = (lane < S0) ? (k - rmin != lane)
-                                      : ((lane < Gm::TAPS) ? ((k - cmin) < 0 || (k - cmin) > lane - S0) : false);
-    const bool slow = __any_sync(0xffffffffu, mine_bad) || p.force_slow;
-    unsigned cb0 = 0u, cb1 = 0u;  // visited-mask column bits of this glimpse (columns {j0, j0+1} of every tap)
-    if (lane >= S0 && lane < Gm::TAPS) {
-      if (k < 32) cb0 |= 1u << k; else if (k < 64) cb1 |= 1u << (k - 32);
-      if (k + 1 < 32) cb0 |= 1u << (k + 1); else if (k + 1 < 64) cb1 |= 1u << (k - 31);
-    }
-    cb0 = __reduce_or_sync(0xffffffffu, cb0);
-    cb1 = __reduce_or_sync(0xffffffffu, cb1);
-    __syncwarp();
-
-    mbar_wait(&mbar[s], (unsigned)((it >> 1) & 1));  // this environment's tile has landed
-    if (!slow) {
-      const Tap ct = taps[S0 + j];
-      const double wx = ct.w, omx = 1.0 - ct.w;
-      const unsigned char* colp = tiles + s * Gm::TILE_STRIDE + ((cmin * C) & 15) + (ct.k - cmin) * C + c;
-      double p00 = tab[(int)colp[0] * kReplicas], p01 = tab[(int)colp[C] * kReplicas];
-#pragma unroll
-      for (int i = 0; i < S0; ++i) {
-        colp += Gm::BOX_W;
-        const double p10 = tab[(int)colp[0] * kReplicas], p11 = tab[(int)colp[C] * kReplicas];
-        const double wy = taps[i].w, omy = 1.0 - wy;
-        double acc = p00 * (omy * omx);  // the reference's leading `0.0 +` is an exact no-op for products >= +0
-        acc = acc + p01 * (omy * wx);
-        acc = acc + p10 * (wy * omx);
-        acc = acc + p11 * (wy * wx);
-        // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
-        if (lane_ok) out[i * Gm::G + jc] = (float)acc;
-        p00 = p10;
-        p01 = p11;
-      }
-    } else {
-      blend_env_general<S0, S1, C>(static_cast<const unsigned char*>(p.bank), p.H, p.bank_pitch, taps, h0.idx, lane, out);
-    }
-
-    // ---- visited bitmask of the observation glimpse: rows {i0, i0+1} x columns {j0, j0+1}
-    if (p.track && set == 0) {
-      unsigned* vm = p.visited + (size_t)n * p.H * p.words;
-      if (p.mode != 0) {
-        for (int w = lane; w < p.H * p.words; w += 32) vm[w] = 0u;
-        __syncwarp();
-      }
-      if (!slow) {  // rows rmin .. rmin + S0; lane = (row, word), one RED per lane (words <= 2 on this path)
-        const int r = (p.words == 2) ? (lane >> 1) : lane, w = (p.words == 2) ? (lane & 1) : 0;
-        const unsigned bits = w == 0 ? cb0 : cb1;
-        if (r <= S0 && rmin + r < p.H && bits) atomicOr(vm + (rmin + r) * p.words + w, bits);
-      } else {
-        for (int w = 0; w < p.words; ++w) {
-          const unsigned bits = w == 0 ? cb0 : cb1;
-          if (!bits) continue;
-          for (int rr = lane; rr < 2 * S0; rr += 32) {
-            const int row = (rr < S0) ? taps[rr].k : taps[rr - S0].k + 1;
-            if (row < p.H) atomicOr(vm + row * p.words + w, bits);
-          }
-        }
-      }
-    }
-    __syncwarp();  // every lane is done with stage s and the taps before they are rewritten
-    h0 = h1;
-    h1 = h2;
+  if (!table_ready) mbar_wait(tbar, 0);  // a warp without work: the bulk copy must not outlive the block
+  if (ep_end) {
+    __syncthreads();
+    if (tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);
   }
 }
 
@@ -326,7 +364,7 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
   plan.smem = Gm::SMEM;
   plan.box_w = Gm::BOX_W;
   plan.box_h = Gm::BOX_H;
-  auto kernel = tma_blend_kernel<10, 10, 3>;
+  auto kernel = tma_step_kernel<10, 10, 3>;
   *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
   if (*err != cudaSuccess) return false;
   int sms = 0, per_sm = 0;
@@ -334,7 +372,20 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
   if (*err == cudaSuccess) *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32, plan.smem);
   if (*err != cudaSuccess || sms <= 0 || per_sm <= 0) return false;
   plan.grid = sms * per_sm;
+  plan.warps = plan.grid * kWarps;
+  // the conversion table float64(float32(u) / 255), 16 copies interleaved (entry u of copy r at u * 16 + r)
+  std::vector<double> t((size_t)256 * kReplicas);
+  for (int u = 0; u < 256; ++u)
+    for (int r = 0; r < kReplicas; ++r) t[(size_t)u * kReplicas + r] = (double)((float)u / 255.0f);
+  *err = cudaMalloc(reinterpret_cast<void**>(&plan.d_table), kTableBytes);
+  if (*err == cudaSuccess) *err = cudaMemcpy(plan.d_table, t.data(), kTableBytes, cudaMemcpyHostToDevice);
+  if (*err != cudaSuccess) return false;
   return true;
+}
+
+void tma_release(TmaPlan& plan) {
+  if (plan.d_table) cudaFree(plan.d_table);
+  plan.d_table = nullptr;
 }
 
 bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_items, int height) {
@@ -354,14 +405,10 @@ bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_i
   return plan.have_map;
 }
 
-size_t tma_header_bytes(long long n_envs) { return (size_t)2 * (size_t)n_envs * sizeof(TileHdr); }
-
 cudaError_t tma_preload(const TmaPlan& plan) {
   if (!plan.spec) return cudaSuccess;
   cudaFuncAttributes a;
-  cudaError_t e = cudaFuncGetAttributes(&a, tma_head_kernel<3>);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, tma_blend_kernel<10, 10, 3>);
-  return e;
+  return cudaFuncGetAttributes(&a, tma_step_kernel<10, 10, 3>);
 }
 
 int tma_launch_step(const TmaPlan& plan, const ImgParams& p, cudaStream_t stream) {
@@ -372,19 +419,20 @@ int tma_launch_step(const TmaPlan& plan, const ImgParams& p, cudaStream_t stream
   cfg.stream = stream;
   cfg.attrs = at;
   cfg.numAttrs = p.pdl ? 1 : 0;
-  cfg.gridDim = dim3((unsigned)((p.N + 255) / 256));
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tma_head_kernel<3>, p);
-  if (e != cudaSuccess) return -(int)e;
-  const int n_sets = ((p.task == APG_TASK_LOCALIZATION) && (p.mode != 0)) ? 2 : 1;
-  const int want = (n_sets * p.N + kWarps - 1) / kWarps;
+  // groups of <= 32 consecutive environments, one (or a few) per persistent warp
+  const int n_range = p.n1 - p.n0;
+  int gs = (n_range + plan.warps - 1) / plan.warps;
+  if (gs > 32) gs = 32;
+  if (gs < 1) gs = 1;
+  const int n_groups = (n_range + gs - 1) / gs;
+  const int want = (n_groups + kWarps - 1) / kWarps;
   cfg.gridDim = dim3((unsigned)(want < plan.grid ? want : plan.grid));
   cfg.blockDim = dim3(kWarps * 32);
   cfg.dynamicSmemBytes = plan.smem;
-  e = cudaLaunchKernelEx(&cfg, tma_blend_kernel<10, 10, 3>, p, plan.tmap);
+  const double* table = plan.d_table;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tma_step_kernel<10, 10, 3>, p, plan.tmap, table, gs, n_groups);
   if (e != cudaSuccess) return -(int)e;
-  return 2;
+  return 1;
 }
 
 }  // namespace apg_img

@@ -11,7 +11,9 @@ namespace apg_img {
 
 struct TmaPlan {
   int spec = 0;        // 1: S0 = S1 = 10, C = 3 (the TinyImageNet shape); 0 = geometry not covered by this path
-  int grid = 0;        // persistent grid of the blend kernel (blocks)
+  int grid = 0;        // persistent grid of the step kernel (blocks)
+  int warps = 0;       // grid * warps per block
+  double* d_table = nullptr;  // uint8 -> float64 pixel table (16 interleaved copies), device
   size_t smem = 0;     // dynamic shared memory of the blend kernel
   int box_w = 0, box_h = 0;
   CUtensorMap tmap;    // the bank as a (rows, row bytes) uint8 tensor, box = one glimpse footprint
@@ -22,9 +24,9 @@ struct TmaPlan {
 bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words, cudaError_t* err);
 // (re-)encodes the tensor map of the bank; false when the driver entry point is unavailable or the bank is too large
 bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_items, int height);
-// head + blend launches of one vector step; returns the number of launches or a negative cudaError
+void tma_release(TmaPlan& plan);
+// the launch of one vector step; returns the number of launches or a negative cudaError
 int tma_launch_step(const TmaPlan& plan, const ImgParams& p, cudaStream_t stream);
-size_t tma_header_bytes(long long n_envs);
 // loads the kernels (first-use module load off the step path)
 cudaError_t tma_preload(const TmaPlan& plan);
 

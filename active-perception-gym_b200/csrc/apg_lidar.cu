@@ -100,8 +100,8 @@ struct WalkState {
 // The grid walk of scan_one from the start cell to the end of the segment (cell coordinates are padded ones).  NB = the
 // ray runs along a grid line, so the cells on its other side touch it too (general, rare); NB = false drops those
 // lookups from the loop.  An ordinary iteration is: next crossing, step the cell, one bit test, the crossing parameter
-// of the next grid line -- the interval bookkeeping of oracle/lidar_oracle.c runs only when the wall state changes or
-// a lattice corner is touched (about twice per ray).
+// of the next grid line; the interval bookkeeping of oracle/lidar_oracle.c applies only when the wall state changes or
+// a lattice corner is touched (about twice per ray; ptxas predicates it, a warp-vote guard measured slower).
 template <bool NB>
 __device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px, double py, double dx, double dy, int sx,
                                      int sy, double inv_dx, double inv_dy, bool nbx, bool nby) {
@@ -305,18 +305,23 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
 
   // ---------------------------------------------------------------- phase 2: stage the maps
   // padded word j of padded row yp holds the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad (pad <= 31)
-  for (int q = tid; q < nE * pmw; q += kThreads) {
-    const int e = q / pmw, r = q - e * pmw;
-    const int yp = r / p.pw, j = r - yp * p.pw;
+  // (item = (environment, padded row): a warp stages 32 rows at a time, each lane walks the few words of its row --
+  //  no integer divisions in the inner loop)
+  for (int q = tid; q < nE * p.prows; q += kThreads) {
+    const int e = q / p.prows, yp = q - e * p.prows;
     const int y = yp - p.pad;
-    unsigned v = 0u;
+    unsigned* dst = smem_maps + e * pmw + yp * p.pw;
     if (y >= 0 && y < p.H) {
       const unsigned* row = p.bank + (size_t)s_midx[e] * mw + (size_t)y * p.words;
-      const unsigned lo = (j >= 1 && j - 1 < p.words) ? row[j - 1] : 0u;
-      const unsigned hi = (j < p.words) ? row[j] : 0u;
-      v = __funnelshift_l(lo, hi, p.pad);  // (hi << pad) | (lo >> (32 - pad))
+      unsigned lo = 0u;
+      for (int j = 0; j < p.pw; ++j) {
+        const unsigned hi = (j < p.words) ? row[j] : 0u;
+        dst[j] = __funnelshift_l(lo, hi, p.pad);  // (hi << pad) | (lo >> (32 - pad))
+        lo = hi;
+      }
+    } else {
+      for (int j = 0; j < p.pw; ++j) dst[j] = 0u;
     }
-    smem_maps[q] = v;
   }
   __syncthreads();
 
@@ -562,6 +567,7 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
                      cudaGetErrorString(de));
   APG_CHECK(cfg->device >= 0 && cfg->device < ndev, APG_ERR_INVALID, "device %d out of range", cfg->device);
   APG_CUDA(cudaSetDevice(cfg->device));
+  apg::apply_device_tuning();
   apg_lidar_env* e = new apg_lidar_env();
   e->cfg = *cfg;
   e->words = (cfg->width + 31) / 32;
