@@ -12,5 +12,6 @@ from .floor_maps import FloorMapBank, pack_maps, unpack_maps
 from .lidar_env import LIDARLocalization2DVectorEnv, lidar_directions
 from .image_env import ImageClassificationVectorEnv, ImageLocalizationVectorEnv, ImagePerceptionConfig
 from .reference_compat import enable_reference_compat, register_envs
+from .hide_and_seek import CircleSquareHideAndSeekVectorWrapper
 
 __version__ = "0.1.0"

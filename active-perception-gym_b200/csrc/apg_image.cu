@@ -442,11 +442,11 @@ __global__ void __launch_bounds__(256) image_head_kernel(const ImgParams p) {
     double px = 0.0, py = 0.0, tcx = 0.0, tcy = 0.0;
     int idx = 0;
     unsigned err = 0;
-    env_move(p, n, px, py, tcx, tcy, idx, err);
+    env_move(p, p, n, px, py, tcx, tcy, idx, err);
     stage_head<BankT>(p, n, p.g_hdr, p.g_ctr, px * p.lim_x, py * p.lim_y, idx, err);
     if ((p.task == APG_TASK_LOCALIZATION) && (p.mode != 0))
       stage_head<BankT>(p, n, p.g_hdr + p.N, p.g_ctr + p.N, tcx, tcy, idx, err);
-    env_loss(p, n, s_stats, ep_end, err);
+    env_loss(p, p, n, s_stats, ep_end, err);
     if (err) atomicOr(p.err, err);
   }
   if (ep_end) {
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
       EnvCtr* s_ctr = reinterpret_cast<EnvCtr*>(smem_raw + p.ctr_off);
       if (tid < nE) {  // E <= blockDim
         unsigned err = 0;
-        if (set == 0) env_move(p, env0 + tid, px, py, tcx, tcy, idx, err);
+        if (set == 0) env_move(p, p, env0 + tid, px, py, tcx, tcy, idx, err);
         stage_head<BankT>(p, tid, s_hdr, s_ctr, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy, idx, err);
         if (err) atomicOr(p.err, err);
       }
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
       const int el = tid - ((int)blockDim.x - p.E);
       if (set == 0 && el >= 0 && el < nE) {
         unsigned err = 0;
-        env_loss(p, env0 + el, s_stats, ep_end, err);
+        env_loss(p, p, env0 + el, s_stats, ep_end, err);
         if (err) atomicOr(p.err, err);
       }
     } else {
@@ -526,11 +526,11 @@ __global__ void __launch_bounds__(kThreads, 4) image_step_kernel(const ImgParams
       if (el < nE && role <= loss_role) {
         unsigned err = 0;
         if (role == 0) {
-          if (set == 0) env_move(p, env0 + el, px, py, tcx, tcy, idx, err);
+          if (set == 0) env_move(p, p, env0 + el, px, py, tcx, tcy, idx, err);
           stage_env<BankT>(p, el, s_hdr, s_taps, s_tile, set == 0 ? px * p.lim_x : tcx, set == 0 ? py * p.lim_y : tcy,
                            idx, err);
         }
-        if (role == loss_role && set == 0) env_loss(p, env0 + el, s_stats, ep_end, err);
+        if (role == loss_role && set == 0) env_loss(p, p, env0 + el, s_stats, ep_end, err);
         if (err) atomicOr(p.err, err);
       }
       __pipeline_commit();
@@ -732,6 +732,9 @@ int stage_payload(apg_image_env* e, apg_image_env::Slot& s, const int64_t* h_idx
   return APG_OK;
 }
 
+// shapes served by a persistent multi-step kernel (csrc/apg_image_small.cu, csrc/apg_image_tma.cu)
+bool persistent(const apg_image_env* e) { return e->small.spec || (e->tma.spec && e->tma.have_map); }
+
 // everything of the kernel parameter block that does not depend on the step
 void fill_params(const apg_image_env* e, ImgParams& p, int mode, const float* d_action, const float* d_pred,
                  const apg_image_env::Slot* slot, float* reward2, uint8_t* done2) {
@@ -786,11 +789,12 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   const apg_image_cfg& c = e->cfg;
   ImgParams p{};
   fill_params(e, p, mode, d_action, d_pred, slot, reward2, done2);
-  if (e->small.spec) {  // explicit reset through the persistent kernel (steps go through rollout_small)
-    apg_img::SmallRollout ro{};
+  if (persistent(e)) {  // explicit reset through the persistent kernels (steps go through rollout_window)
+    apg_img::RolloutPlan ro{};
     ro.n_steps = 1; ro.t0 = 0; ro.need_reset0 = 0; ro.first_mode = 2;
-    ro.slot_idx[0] = reinterpret_cast<const long long*>(slot->d_idx); ro.slot_pos[0] = slot->d_pos; ro.slot_inv[0] = slot->d_inv;
-    const int n = apg_img::small_launch(e->small, p, ro, e->stream);
+    ro.slot_idx[0] = reinterpret_cast<const long long*>(slot->d_idx); ro.slot_pos[0] = slot->d_pos;
+    ro.slot_target[0] = slot->d_target; ro.slot_inv[0] = slot->d_inv;
+    const int n = e->small.spec ? apg_img::small_launch(e->small, p, ro, e->stream) : apg_img::tma_launch(e->tma, p, ro, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
     e->t = 0;
@@ -821,16 +825,6 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
     cfg.attrs = at; cfg.numAttrs = e->pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, p);
   };
-  if (e->tma.spec && e->tma.have_map) {
-    const int n = apg_img::tma_launch_step(e->tma, p, e->stream);
-    if (n < 0) return apg::fail(APG_ERR_CUDA, "image step kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
-    apg::count_launch(n);
-    if (!e->hold) {
-      e->t = t_after;
-      e->needs_reset = (mode == 0) && p.terminated;
-    }
-    return APG_OK;
-  }
   if (e->split == 2) {
     const int hgrid = apg::ceil_div(c.num_envs, 256);
     if (c.bank_dtype == APG_BANK_U8) go(image_head_kernel<unsigned char>, hgrid, 256, 0);
@@ -965,21 +959,21 @@ int generate_payload(apg_image_env* e) {
   return APG_OK;
 }
 
-// n_steps consecutive steps of the persistent small-glimpse kernel: as few launches as the autoreset payload ring and the
+// n_steps consecutive steps of a persistent kernel: as few launches as the autoreset payload ring and the
 // per-launch limits allow (one for the bench's 51-step windows).  Payloads of the autoresets inside a window are drawn
 // in-stream before its launch.
-int rollout_small(apg_image_env* e, const float* d_actions, const float* d_preds, int n_steps, float* d_rewards,
-                  uint8_t* d_dones) {
+int rollout_window(apg_image_env* e, const float* d_actions, const float* d_preds, int n_steps, float* d_rewards,
+                   uint8_t* d_dones) {
   const size_t N = e->cfg.num_envs;
   const int ring = (int)e->ring.size();
-  const int max_resets = ring < apg_img::kSmallMaxSlots ? ring : apg_img::kSmallMaxSlots;
+  const int max_resets = ring < apg_img::kRolloutMaxSlots ? ring : apg_img::kRolloutMaxSlots;
   int done = 0;
   while (done < n_steps) {
-    apg_img::SmallRollout ro{};
+    apg_img::RolloutPlan ro{};
     ro.t0 = e->t; ro.need_reset0 = e->needs_reset ? 1 : 0; ro.first_mode = 0;
     int t = e->t, m = 0, resets = 0;
     bool need = e->needs_reset;
-    while (done + m < n_steps && m < apg_img::kSmallMaxSteps) {
+    while (done + m < n_steps && m < apg_img::kRolloutMaxSteps) {
       if (need) {
         if (resets == max_resets) break;
         ro.reset_slot[m] = (unsigned char)resets++;
@@ -997,13 +991,14 @@ int rollout_small(apg_image_env* e, const float* d_actions, const float* d_preds
     }
     for (int i = 0; i < resets; ++i) {
       const apg_image_env::Slot& s = e->ring[(e->ring_head + i) % ring];
-      ro.slot_idx[i] = reinterpret_cast<const long long*>(s.d_idx); ro.slot_pos[i] = s.d_pos; ro.slot_inv[i] = s.d_inv;
+      ro.slot_idx[i] = reinterpret_cast<const long long*>(s.d_idx); ro.slot_pos[i] = s.d_pos;
+      ro.slot_target[i] = s.d_target; ro.slot_inv[i] = s.d_inv;
     }
     ro.n_steps = m;
     ImgParams p{};
     fill_params(e, p, 0, d_actions + (size_t)done * N * 2, d_preds + (size_t)done * N * e->pred_width, nullptr,
                 d_rewards ? d_rewards + (size_t)done * N : nullptr, d_dones ? d_dones + (size_t)done * N : nullptr);
-    const int n = apg_img::small_launch(e->small, p, ro, e->stream);
+    const int n = e->small.spec ? apg_img::small_launch(e->small, p, ro, e->stream) : apg_img::tma_launch(e->tma, p, ro, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
     if (!e->hold) {
@@ -1018,7 +1013,7 @@ int rollout_small(apg_image_env* e, const float* d_actions, const float* d_preds
 }
 
 int step_once(apg_image_env* e, const float* d_action, const float* d_pred, float* reward2, uint8_t* done2) {
-  if (e->small.spec) return rollout_small(e, d_action, d_pred, 1, reward2, done2);
+  if (persistent(e)) return rollout_window(e, d_action, d_pred, 1, reward2, done2);
   if (e->needs_reset && e->ring_count == 0 && e->have_streams) {
     int rc = generate_payload(e);
     if (rc != APG_OK) return rc;
@@ -1426,7 +1421,7 @@ int apg_image_rollout(apg_image_env* e, const float* d_actions, const float* d_p
     APG_CHECK(e->have_streams || resets <= e->ring_count, APG_ERR_NEED_PAYLOAD,
               "rollout of %d steps needs %d reset payloads, %d queued", n_steps, resets, e->ring_count);
   }
-  if (e->small.spec) return rollout_small(e, d_actions, d_preds, n_steps, d_rewards, d_dones);
+  if (persistent(e)) return rollout_window(e, d_actions, d_preds, n_steps, d_rewards, d_dones);
   const size_t N = e->cfg.num_envs;
   for (int k = 0; k < n_steps; ++k) {
     int rc = step_once(e, d_actions + (size_t)k * N * 2, d_preds + (size_t)k * N * e->pred_width,
@@ -1450,9 +1445,13 @@ int apg_image_step_host(apg_image_env* e, const float* h_action, const float* h_
   float* m_glimpse = mapped_alias(h_glimpse);
   // The batch is cut into chunks: the host-to-device copy of chunk c+1 (copy stream) runs while chunk c is stepped
   // (the special-purpose kernels take an environment range; the generic staged kernels step the whole batch at once)
-  const bool ranged = e->small.spec || (e->tma.spec && e->tma.have_map);
+  const bool ranged = persistent(e);
   int chunks = 1;
   if (ranged) chunks = N >= 32768 ? 4 : (N >= 8192 ? 2 : 1);
+  if (const char* ov = getenv("APG_HOST_CHUNKS")) {  // developer switch: number of pipeline chunks of the host step
+    const int v = atoi(ov);
+    if (ranged && v >= 1 && v <= 8) chunks = v;
+  }
   const size_t per = ((N + chunks - 1) / chunks + 1023) & ~(size_t)1023;  // chunk boundaries: multiples of 1024 envs
   float* const glimpse_dev = e->b.d_glimpse;
   if (m_glimpse) e->b.d_glimpse = m_glimpse;

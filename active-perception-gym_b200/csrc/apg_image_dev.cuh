@@ -88,6 +88,39 @@ struct ImgParams {
   unsigned* err;
 };
 
+// What changes from step to step inside a multi-step launch (same field names as in ImgParams).
+struct StepCtx {
+  int mode, t_stamp;
+  unsigned char terminated;
+  float time_obs;
+  const float* action;
+  const float* pred;
+  const long long* new_idx;
+  const double* new_pos;
+  const float* new_target;
+  const unsigned char* new_inv;
+  float* reward2;
+  unsigned char* done2;
+};
+
+constexpr int kRolloutMaxSteps = 128;  // steps per launch
+constexpr int kRolloutMaxSlots = 8;    // autoresets per launch
+
+// What one multi-step launch steps through.  The episode clock is shared by all environments, so the mode of every step
+// follows from (t0, need_reset0): a step is an autoreset step exactly when the previous one terminated.  p.action /
+// p.pred / p.reward2 / p.done2 point at the FIRST step of the window (stacked (n_steps, N, ...) arrays).
+struct RolloutPlan {
+  int n_steps;
+  int t0;           // episode clock before the first step
+  int need_reset0;  // the first step is an autoreset step
+  int first_mode;   // 2: the first (only) step is an explicit reset from slot 0
+  unsigned char reset_slot[kRolloutMaxSteps];  // for autoreset steps: which payload slot below
+  const long long* slot_idx[kRolloutMaxSlots];
+  const double* slot_pos[kRolloutMaxSlots];
+  const float* slot_target[kRolloutMaxSlots];
+  const unsigned char* slot_inv[kRolloutMaxSlots];
+};
+
 // scipy find_indices on the grid g[k] = k - off (see oracle/image_oracle.py:tap_indices)
 __device__ __forceinline__ void tap(double coord, double off, int len, int& k_out, double& w_out) {
   int k = (int)floor(coord + off);
@@ -189,10 +222,13 @@ __device__ __forceinline__ float px_to_f32(float v) { return v; }
 //              the taps / staging need;
 //   env_loss   labels / targets, loss, reward, flags, overlay colour, episode statistics.
 // Both read the (read-only) action; env_move alone touches pos / st_idx, env_loss alone st_label / st_target / acc*.
-__device__ __forceinline__ void env_move(const ImgParams& p, int n, double& px, double& py, double& tcx, double& tcy,
+// `c` carries what changes from step to step (mode, t_stamp, terminated, time_obs, action, pred, the reset payload new_*,
+// reward2 / done2): the kernel parameter block itself for one-step launches, a StepCtx inside multi-step launches.
+template <class Ctx>
+__device__ __forceinline__ void env_move(const ImgParams& p, const Ctx& c, int n, double& px, double& py, double& tcx, double& tcy,
                                          int& idx, unsigned& err) {
-  if (p.mode == 0) {
-    const float2 aa = reinterpret_cast<const float2*>(p.action)[n];
+  if (c.mode == 0) {
+    const float2 aa = reinterpret_cast<const float2*>(c.action)[n];
     const double2 pp = reinterpret_cast<const double2*>(p.pos)[n];
     idx = p.st_idx[n];
     px = pp.x;
@@ -200,8 +236,8 @@ __device__ __forceinline__ void env_move(const ImgParams& p, int n, double& px, 
     const float a0 = aa.x, a1 = aa.y;
     if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
     if (p.track) {  // overlay stamp of the PRE-move position
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-      p.stamp_xy[(size_t)(p.t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
+      p.stamp_xy[(size_t)(c.t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
+      p.stamp_xy[(size_t)(c.t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
     }
     const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
     float q0 = a0, q1 = a1;
@@ -213,15 +249,15 @@ __device__ __forceinline__ void env_move(const ImgParams& p, int n, double& px, 
     px = fmin(fmax(px + p.msl_x * (double)q0, -1.0), 1.0);
     py = fmin(fmax(py + p.msl_y * (double)q1, -1.0), 1.0);
   } else {
-    const long long ni = p.new_idx[n];
-    const double2 pp = reinterpret_cast<const double2*>(p.new_pos)[n];
+    const long long ni = c.new_idx[n];
+    const double2 pp = reinterpret_cast<const double2*>(c.new_pos)[n];
     idx = (int)ni;
     px = pp.x;
     py = pp.y;
     p.st_idx[n] = idx;
     p.index[n] = ni;
     if (p.task != APG_TASK_CLASSIFICATION) {
-      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
+      const float2 nt = reinterpret_cast<const float2*>(c.new_target)[n];
       tcx = (double)nt.x * p.lim_x;  // float32 target promoted to float64
       tcy = (double)nt.y * p.lim_y;
     }
@@ -230,7 +266,8 @@ __device__ __forceinline__ void env_move(const ImgParams& p, int n, double& px, 
   reinterpret_cast<float2*>(p.glimpse_pos)[n] = make_float2((float)px, (float)py);
 }
 
-__device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_stats, bool ep_end, unsigned& err) {
+template <class Ctx>
+__device__ __forceinline__ void env_loss(const ImgParams& p, const Ctx& c, int n, double* s_stats, bool ep_end, unsigned& err) {
   float base = 0.0f, pq = 0.0f, loss_f = 0.0f;
   float m1 = 0.0f, m2 = 0.0f;  // LogWrapper metrics of this step
   double neg_loss_d = 0.0;
@@ -240,9 +277,9 @@ __device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_st
   float2 in_action = make_float2(0.f, 0.f), in_pred2 = make_float2(0.f, 0.f), in_target = make_float2(0.f, 0.f);
   float in_acc1 = 0.0f, in_acc2 = 0.0f, in_accr = 0.0f, x_first = 0.0f, x_last = 0.0f;
   int in_fc = -1, in_lic = -1, label = 0;
-  if (p.mode == 0) {
-    in_action = reinterpret_cast<const float2*>(p.action)[n];
-    if (p.t_stamp != 0) {
+  if (c.mode == 0) {
+    in_action = reinterpret_cast<const float2*>(c.action)[n];
+    if (c.t_stamp != 0) {
       in_acc1 = p.acc1[n];
       in_acc2 = p.acc2[n];
       in_accr = p.acc_ret[n];
@@ -253,29 +290,29 @@ __device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_st
     }
     if (cls) label = p.st_label[n];
   }
-  if (cls && p.mode != 2) {  // pulls the environment's logits into L1 with the other inputs
-    x_first = p.pred[(size_t)n * p.K];
-    x_last = p.pred[(size_t)n * p.K + p.K - 1];
+  if (cls && c.mode != 2) {  // pulls the environment's logits into L1 with the other inputs
+    x_first = c.pred[(size_t)n * p.K];
+    x_last = c.pred[(size_t)n * p.K + p.K - 1];
   }
-  if (!cls && p.mode != 2) {
+  if (!cls && c.mode != 2) {
     in_target = reinterpret_cast<const float2*>(p.st_target)[n];
-    in_pred2 = reinterpret_cast<const float2*>(p.pred)[n];
+    in_pred2 = reinterpret_cast<const float2*>(c.pred)[n];
   }
   // ---- labels / targets and the loss (the reset step still charges a loss)
   if (cls) {
     unsigned char inv = 0;
-    if (p.mode != 0) {
-      label = p.bank_labels[(int)p.new_idx[n]];
+    if (c.mode != 0) {
+      label = p.bank_labels[(int)c.new_idx[n]];
       if (p.invert) {
-        inv = p.new_inv[n];
+        inv = c.new_inv[n];
         if (inv) label = p.K - label - 1;
       }
       p.st_label[n] = label;
     }
-    if (p.invert) p.inverted_label[n] = (p.mode == 0) ? 2 : (int)inv;
+    if (p.invert) p.inverted_label[n] = (c.mode == 0) ? 2 : (int)inv;
     p.target_label[n] = label;
-    if (p.mode != 2) {
-      const float* x = p.pred + (size_t)n * p.K;
+    if (c.mode != 2) {
+      const float* x = c.pred + (size_t)n * p.K;
       float mx = fmaxf(x_first, x_last);
       bool has_nan = isnan(x_first) || isnan(x_last);
       for (int k = 1; k < p.K - 1; ++k) {
@@ -297,7 +334,7 @@ __device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_st
       m2 = (pq > p.inv_k) ? 1.0f : 0.0f;  // accuracy (:166-168)
     }
   } else {
-    if (p.mode != 2) {
+    if (c.mode != 2) {
       const float t0 = in_target.x, t1 = in_target.y;
       const float2 qq = in_pred2;
       if (isnan(qq.x) || isnan(qq.y)) err |= APG_FLAG_NAN_PRED;
@@ -306,53 +343,53 @@ __device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_st
       loss_f = __fadd_rn(__fmul_rn(__fdiv_rn(ss, 2.0f), p.mse_scale), p.mse_offset);
       m1 = __fsqrt_rn(ss);       // euclidean_distance (active_regression_env.py:211)
       m2 = __fdiv_rn(ss, 2.0f);  // mse (:212)
-      if (p.mode == 0 && p.track)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64)
+      if (c.mode == 0 && p.track)  // 1 - ||pred - target|| / sqrt(4) in float64 (np.sqrt(4) is np.float64)
         pq = (float)fmin(fmax(1.0 - (double)__fsqrt_rn(ss) / 2.0, 0.0), 1.0);
       reinterpret_cast<float2*>(p.target_xy)[n] = make_float2(t0, t1);
     }
-    if (p.mode != 0) {
-      const float2 nt = reinterpret_cast<const float2*>(p.new_target)[n];
+    if (c.mode != 0) {
+      const float2 nt = reinterpret_cast<const float2*>(c.new_target)[n];
       reinterpret_cast<float2*>(p.st_target)[n] = nt;
-      if (p.mode == 2) reinterpret_cast<float2*>(p.target_xy)[n] = nt;
+      if (c.mode == 2) reinterpret_cast<float2*>(p.target_xy)[n] = nt;
     }
   }
-  if (p.mode == 0) {
+  if (c.mode == 0) {
     const float a0 = in_action.x, a1 = in_action.y;
-    if (p.track) p.stamp_q[(size_t)p.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
+    if (p.track) p.stamp_q[(size_t)c.t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
     const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)));
     base = __fmul_rn(-m, 1e-3f);
   }
-  if (p.mode != 2) {
+  if (c.mode != 2) {
     float reward_f;
     // classification: float32 base - float64 loss -> float64; localization stays float32 except on the reset
     // step, whose base reward is np.zeros(N) (float64)
     if (cls) reward_f = (float)((double)base + neg_loss_d);
-    else reward_f = (p.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
+    else reward_f = (c.mode == 0) ? __fsub_rn(base, loss_f) : (float)(0.0 - (double)loss_f);
     float reward_out = reward_f;
     if (p.sparse) {  // base_reward - loss * weight, weight = float32(terminated)  (sparsify_wrapper.py:60-83)
-      const bool w1 = (p.mode == 0) && p.terminated;
+      const bool w1 = (c.mode == 0) && c.terminated;
       if (cls) reward_out = (float)((double)base - (-neg_loss_d) * (w1 ? 1.0 : 0.0));
-      else if (p.mode == 0) reward_out = __fsub_rn(base, __fmul_rn(loss_f, w1 ? 1.0f : 0.0f));
+      else if (c.mode == 0) reward_out = __fsub_rn(base, __fmul_rn(loss_f, w1 ? 1.0f : 0.0f));
       else reward_out = (float)(0.0 - (double)__fmul_rn(loss_f, 0.0f));
     }
     p.reward[n] = reward_out;
     p.base_reward[n] = base;
     p.loss[n] = loss_f;
-    if (p.reward2) p.reward2[n] = reward_out;
-    if (p.done2) p.done2[n] = p.terminated;
+    if (c.reward2) c.reward2[n] = reward_out;
+    if (c.done2) c.done2[n] = c.terminated;
     // ---- episode statistics (the *VectorLogWrapper loops): real steps only, cleared by the reset step
-    if (p.mode == 0) {
+    if (c.mode == 0) {
       const float a1 = __fadd_rn(in_acc1, m1);
       const float a2 = __fadd_rn(in_acc2, m2);
       const float ar = __fadd_rn(in_accr, reward_f);
       if (cls) {
         int fc = in_fc, lic = in_lic;
-        if (m2 > 0.5f) { if (fc < 0) fc = p.t_stamp; } else lic = p.t_stamp;
+        if (m2 > 0.5f) { if (fc < 0) fc = c.t_stamp; } else lic = c.t_stamp;
         p.first_correct[n] = fc;
         p.last_incorrect[n] = lic;
       }
       if (ep_end) {
-        const float nt = (float)(p.t_stamp + 1);
+        const float nt = (float)(c.t_stamp + 1);
         const float avg1 = __fdiv_rn(a1, nt), avg2 = __fdiv_rn(a2, nt);
         p.ep_avg1[n] = avg1; p.ep_final1[n] = m1; p.ep_avg2[n] = avg2; p.ep_final2[n] = m2; p.ep_return[n] = ar;
         atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)avg1); atomicAdd(&s_stats[2], (double)m1);
@@ -362,9 +399,9 @@ __device__ __forceinline__ void env_loss(const ImgParams& p, int n, double* s_st
       }
     }
   }
-  p.terminated_out[n] = p.terminated;
+  p.terminated_out[n] = c.terminated;
   p.truncated_out[n] = 0;
-  p.time_step[n] = p.time_obs;
+  p.time_step[n] = c.time_obs;
 }
 
 // Programmatic dependent launch: consecutive vector steps are launched back to back on one stream; with the launch

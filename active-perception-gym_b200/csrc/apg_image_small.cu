@@ -169,10 +169,10 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     if (p.track) {
       const unsigned* gv = p.visited + (size_t)warp_env0 * p.H;
       unsigned* wv = s_vis + warp * 32 * sm.vis_stride;
-      for (int q = lane; q < n_env * p.H; q += 32) {
-        const int e = q / p.H;
-        wv[e * sm.vis_stride + (q - e * p.H)] = gv[q];
-      }
+      // H <= 32 words per environment: one coalesced run per iteration, eight loads in flight at a time
+#pragma unroll 8
+      for (int e = 0; e < n_env; ++e)
+        if (lane < p.H) wv[e * sm.vis_stride + lane] = __ldcg(gv + e * p.H + lane);
     }
   }
   // logits of the first step on their way (stage 0)
@@ -407,10 +407,8 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
   if (p.track) {
     unsigned* gv = p.visited + (size_t)warp_env0 * p.H;
     const unsigned* wv = s_vis + warp * 32 * sm.vis_stride;
-    for (int q = lane; q < n_env * p.H; q += 32) {
-      const int e = q / p.H;
-      gv[q] = wv[e * sm.vis_stride + (q - e * p.H)];
-    }
+    for (int e = 0; e < n_env; ++e)
+      if (lane < p.H) gv[e * p.H + lane] = wv[e * sm.vis_stride + lane];
   }
   // shard-wide episode statistics: warp sums, one atomic per warp and statistic
   if (__any_sync(0xffffffffu, st0 != 0.0)) {

@@ -8,27 +8,15 @@
 
 namespace apg_img {
 
-constexpr int kSmallMaxSteps = 128;  // steps per launch
-constexpr int kSmallMaxSlots = 8;    // autoresets per launch
-
 struct SmallPlan {
   int spec = 0;  // 1: 5x5x1 sensor, classification (the MNIST shape); 0 = not covered by this path
   int threads = 0;
   size_t smem = 0;
 };
 
-// What one launch steps through.  The episode clock is shared by all environments, so the mode of every step follows
-// from (t0, need_reset0): a step is an autoreset step exactly when the previous one terminated.
-struct SmallRollout {
-  int n_steps;
-  int t0;           // episode clock before the first step
-  int need_reset0;  // the first step is an autoreset step
-  int first_mode;   // 2: the first (only) step is an explicit reset from slot 0
-  unsigned char reset_slot[kSmallMaxSteps];  // for autoreset steps: which payload slot below
-  const long long* slot_idx[kSmallMaxSlots];
-  const double* slot_pos[kSmallMaxSlots];
-  const unsigned char* slot_inv[kSmallMaxSlots];
-};
+typedef RolloutPlan SmallRollout;  // see apg_image_dev.cuh
+constexpr int kSmallMaxSteps = kRolloutMaxSteps;
+constexpr int kSmallMaxSlots = kRolloutMaxSlots;
 
 bool small_plan(SmallPlan& plan, const apg_image_cfg& cfg, int words);
 cudaError_t small_preload(const SmallPlan& plan);

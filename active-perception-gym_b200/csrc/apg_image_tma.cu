@@ -13,8 +13,8 @@
 //            for environment k+1 while the warp blends environment k; completion is an mbarrier transaction count.
 //            Nothing in the loop synchronises more than one warp.
 // Blend: the reference's 4-term float64 sum in scipy's order (bit-exact pixels).  The exact uint8 -> float64 pixel
-// value float64(float32(u8) / 255) comes from a 256-entry table, replicated 16x so that the 64-bit lookups of a
-// half-warp never collide (one LDS.64 instead of the five-instruction conversion); the 32 KB table is computed once on
+// value float64(float32(u8) / 255) comes from a 256-entry table, replicated 8x (lane & 7 picks its copy: at most two
+// lanes of a half-warp share one) -- one LDS.64 instead of the five-instruction conversion; the 16 KB table is computed once on
 // the host and lands in every block's shared memory with one bulk copy (cp.async.bulk, SASS UBLKCP).  Taps: the first
 // tap of each axis is scipy's find_indices in full (phase H), the others are assumed consecutive and VERIFIED -- their
 // weight w = coord - grid[k0 + t], computed exactly like the reference's, must lie in [0, 1), which is precisely the
@@ -33,14 +33,17 @@ namespace {
 #define APG_TMA_MINB 4
 #endif
 #ifndef APG_TMA_REPLICAS
-#define APG_TMA_REPLICAS 16
+#define APG_TMA_REPLICAS 8
+#endif
+#ifndef APG_TMA_WYSMEM
+#define APG_TMA_WYSMEM 1  // 1: row weights through shared memory (one LDS.64 per row) instead of three adds per row
 #endif
 #ifndef APG_TMA_ARITH
 #define APG_TMA_ARITH 0  // 1: convert pixels arithmetically (px_to_f64) instead of the table lookup (experiment)
 #endif
 constexpr int kWarps = 8;
-constexpr int kReplicas = APG_TMA_REPLICAS;         // table copies: lane & 15 picks its own -> conflict-free LDS.64
-constexpr int kTableBytes = 256 * kReplicas * 8;    // 32 KB
+constexpr int kReplicas = APG_TMA_REPLICAS;         // table copies: lane & (kReplicas - 1) picks its own
+constexpr int kTableBytes = 256 * kReplicas * 8;    // 16 KB at 8 copies
 
 struct __align__(16) TileHdr {  // 32 bytes per glimpse, phase H -> phase B (warp-private shared memory)
   double ccx, ccy;  // sensor centre in image-centred pixel coordinates (float64, like the reference)
@@ -180,16 +183,19 @@ __device__ __noinline__ void blend_env_general(const unsigned char* bank, int H,
   }
 }
 
-template <int S0, int S1, int C>
+// IH x IW = the bank image size: compile-time, like the sensor geometry -- the per-environment prologue of phase B runs
+// once per glimpse on a warp with 64 registers per thread, every runtime constant it re-reads is an instruction.
+template <int S0, int S1, int C, int IH, int IW>
 __global__ void __launch_bounds__(kWarps * 32, APG_TMA_MINB)
 tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, const double* __restrict__ g_table,
-                const int group_size, const int n_groups) {
+                const int group_size, const int n_groups, const RolloutPlan ro) {
   using Gm = Geom<S0, S1, C>;
   extern __shared__ __align__(128) unsigned char smem[];
   double* table = reinterpret_cast<double*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* wbase = smem + kTableBytes + warp * Gm::WARP_BYTES;
   unsigned char* tiles = wbase;
+  double* s_wy = reinterpret_cast<double*>(wbase + 2 * Gm::TILE_STRIDE);  // APG_TMA_WYSMEM: row weights of the current glimpse
   TileHdr* hdrs = reinterpret_cast<TileHdr*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16);
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16 + 32 * 32);
   unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + kTableBytes + kWarps * Gm::WARP_BYTES);
@@ -211,8 +217,6 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   }
   grid_dependency_wait(p.pdl);
 
-  const bool ep_end = (p.mode == 0) && p.terminated;
-  const int n_sets = ((p.task == APG_TASK_LOCALIZATION) && (p.mode != 0)) ? 2 : 1;
   // lane = (column j, channel c) of the sensor row; lanes past the row run element G-1 and skip the store
   const bool lane_ok = lane < Gm::G;
   const int jc = lane_ok ? lane : Gm::G - 1;
@@ -223,16 +227,44 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   constexpr double kHalf0 = (S0 - 1) / 2.0, kHalf1 = (S1 - 1) / 2.0;
   const double col_off = (double)j - kHalf1, col_j = (double)j;
   const double row_off_lane = (double)min(lane, S0 - 1) - kHalf0, row_lane = (double)min(lane, S0 - 1);
-  const unsigned long long wmask = (p.W >= 64) ? ~0ull : ((1ull << p.W) - 1ull);
-  const int vis_r = (p.words == 2) ? (lane >> 1) : lane, vis_w = (p.words == 2) ? (lane & 1) : 0;
+  constexpr int kWords = (IW + 31) / 32;
+  static_assert(kWords <= 2 && (S0 + 1) * kWords <= 32, "visited rows x words: one lane each");
+  constexpr unsigned long long wmask = (IW >= 64) ? ~0ull : ((1ull << (IW & 63)) - 1ull);
+  constexpr double kOffY = (IH - 1) / 2.0, kOffX = (IW - 1) / 2.0;
+  const int vis_r = (kWords == 2) ? (lane >> 1) : lane, vis_w = (kWords == 2) ? (lane & 1) : 0;
   const unsigned tiles_u = smem_u32(tiles), mbar_u = smem_u32(mbar);  // shared-window addresses of the ring
-  const int vis_words = p.H * p.words;
-  bool table_ready = false;
+  constexpr int vis_words = IH * kWords;
+  bool table_ready = false, any_ep_end = false;
   int it = 0;  // tiles consumed so far by this warp: stage = it & 1, barrier parity = (it >> 1) & 1
 
+  // A warp takes its group of environments through ALL steps of the launch before it moves on: warps drift apart, the
+  // latency-bound phase H of one hides behind the blends of the others, and launch ramp / tail are paid once per window.
   for (int g = blockIdx.x * kWarps + warp; g < n_groups; g += gridDim.x * kWarps) {
     const int env_base = p.n0 + g * group_size;
     const int cnt = min(group_size, p.n1 - env_base);
+    int t = ro.t0;
+    bool need_reset = ro.need_reset0 != 0;
+   for (int k = 0; k < ro.n_steps; ++k) {
+    StepCtx c;
+    c.mode = (k == 0 && ro.first_mode == 2) ? 2 : (need_reset ? 1 : 0);
+    c.t_stamp = (c.mode == 0) ? t : 0;
+    const int t_after = (c.mode == 0) ? t + 1 : 0;
+    c.terminated = ((c.mode == 0) && (t_after >= p.T)) ? 1 : 0;
+    c.time_obs = (float)(((double)t_after / (double)p.T) * 2.0 - 1.0);
+    c.action = p.action + (size_t)k * p.N * 2;
+    c.pred = p.pred + (size_t)k * p.N * ((p.task == APG_TASK_CLASSIFICATION) ? p.K : 2);
+    {
+      const int slot = (c.mode == 1) ? ro.reset_slot[k] : 0;
+      c.new_idx = ro.slot_idx[slot]; c.new_pos = ro.slot_pos[slot]; c.new_target = ro.slot_target[slot];
+      c.new_inv = ro.slot_inv[slot];
+    }
+    c.reward2 = p.reward2 ? p.reward2 + (size_t)k * p.N : nullptr;
+    c.done2 = p.done2 ? p.done2 + (size_t)k * p.N : nullptr;
+    t = t_after;
+    need_reset = c.terminated != 0;
+    const bool ep_end = (c.mode == 0) && c.terminated;
+    any_ep_end = any_ep_end || ep_end;
+    const int n_sets = ((p.task == APG_TASK_LOCALIZATION) && (c.mode != 0)) ? 2 : 1;
     double tcx = 0.0, tcy = 0.0;
     int idx = 0;
     for (int set = 0; set < n_sets; ++set) {
@@ -242,9 +274,9 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         const int n = env_base + lane;
         if (set == 0) {
           double px = 0.0, py = 0.0;
-          env_move(p, n, px, py, tcx, tcy, idx, err);
+          env_move(p, c, n, px, py, tcx, tcy, idx, err);
           write_hdr<C>(p, hdrs + lane, px * p.lim_x, py * p.lim_y, idx, err);
-          env_loss(p, n, s_stats, ep_end, err);
+          env_loss(p, c, n, s_stats, ep_end, err);
         } else {
           write_hdr<C>(p, hdrs + lane, tcx, tcy, idx, err);
         }
@@ -277,13 +309,17 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         // ---- taps under the consecutive-index assumption (see the file header): the weight of tap t of an axis is
         // coord_t - grid[k0 + t] with grid[k] = k - off; this lane's column weight lives in registers, the row
         // weights are recomputed inside the row loop (three float64 adds per row, no shared-memory round trip)
-        const double gy0 = int_to_double(rmin) - p.offy, gx0 = int_to_double(cmin) - p.offx;
+        const double gy0 = int_to_double(rmin) - kOffY, gx0 = int_to_double(cmin) - kOffX;
         const double wx = (cc.x + col_off) - (gx0 + col_j), omx = 1.0 - wx;
         const double wyl = (cc.y + row_off_lane) - (gy0 + row_lane);  // lane t < S0 verifies tap row t
-        const bool bad = !(wx >= 0.0) || !(wx < 1.0) || (cmin + j > p.W - 1) || !(wyl >= 0.0) || !(wyl < 1.0) ||
-                         (rmin + min(lane, S0 - 1) > p.H - 1);
+        const bool bad = !(wx >= 0.0) || !(wx < 1.0) || (cmin + j > IW - 1) || !(wyl >= 0.0) || !(wyl < 1.0) ||
+                         (rmin + min(lane, S0 - 1) > IH - 1);
         const bool slow = __any_sync(0xffffffffu, bad) || p.force_slow;
-        if (vm && p.mode != 0) {
+#if APG_TMA_WYSMEM
+        if (lane < S0) s_wy[lane] = wyl;
+        __syncwarp();
+#endif
+        if (vm && c.mode != 0) {
           for (int w = lane; w < vis_words; w += 32) vm[w] = 0u;
           __syncwarp();
         }
@@ -300,7 +336,11 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
           for (int i = 0; i < S0; ++i) {
             colp += Gm::BOX_W;
             const double p10 = APG_PX(colp[0]), p11 = APG_PX(colp[C]);
+#if APG_TMA_WYSMEM
+            const double wy = s_wy[i], omy = 1.0 - wy;
+#else
             const double wy = (cc.y + ((double)i - kHalf0)) - (gy0 + (double)i), omy = 1.0 - wy;
+#endif
             double acc = p00 * (omy * omx);  // the reference's leading `0.0 +` is an exact no-op for products >= +0
             acc = acc + p01 * (omy * wx);
             acc = acc + p10 * (wy * omx);
@@ -314,7 +354,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
           if (vm) {
             const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cmin) & wmask);
             const unsigned bits = vis_w == 0 ? (unsigned)cb : (unsigned)(cb >> 32);
-            if (vis_r <= S0 && rmin + vis_r < p.H && bits) atomicOr(vm + (rmin + vis_r) * p.words + vis_w, bits);
+            if (vis_r <= S0 && rmin + vis_r < IH && bits) atomicOr(vm + (rmin + vis_r) * kWords + vis_w, bits);
           }
         } else {
           blend_env_general<S0, S1, C>(static_cast<const unsigned char*>(p.bank), p.H, p.W, p.words, p.bank_pitch, cc.x,
@@ -324,10 +364,10 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         __syncwarp();  // every lane is done with stage s before it is refilled
       }
     }
+   }
   }
   if (!table_ready) mbar_wait(tbar, 0);  // a warp without work: the bulk copy must not outlive the block
-  if (ep_end) {
-    __syncthreads();
+  if (__syncthreads_or(any_ep_end ? 1 : 0)) {
     if (tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);
   }
 }
@@ -356,7 +396,7 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
   plan = TmaPlan{};
   *err = cudaSuccess;
   if (cfg.bank_dtype != APG_BANK_U8 || cfg.sensor_scale != 1.0 || cfg.blend_f32) return false;
-  if (!(cfg.sensor_h == 10 && cfg.sensor_w == 10 && cfg.channels == 3)) return false;
+  if (!(cfg.sensor_h == 10 && cfg.sensor_w == 10 && cfg.channels == 3 && cfg.height == 64 && cfg.width == 64)) return false;
   using Gm = Geom<10, 10, 3>;
   if (words > 2 || (Gm::BOX_H) * words > 32 || cfg.height < Gm::BOX_H || bank_pitch < Gm::BOX_W) return false;
   if (!encode_fn()) return false;
@@ -364,7 +404,7 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
   plan.smem = Gm::SMEM;
   plan.box_w = Gm::BOX_W;
   plan.box_h = Gm::BOX_H;
-  auto kernel = tma_step_kernel<10, 10, 3>;
+  auto kernel = tma_step_kernel<10, 10, 3, 64, 64>;
   *err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
   if (*err != cudaSuccess) return false;
   int sms = 0, per_sm = 0;
@@ -408,10 +448,10 @@ bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_i
 cudaError_t tma_preload(const TmaPlan& plan) {
   if (!plan.spec) return cudaSuccess;
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, tma_step_kernel<10, 10, 3>);
+  return cudaFuncGetAttributes(&a, tma_step_kernel<10, 10, 3, 64, 64>);
 }
 
-int tma_launch_step(const TmaPlan& plan, const ImgParams& p, cudaStream_t stream) {
+int tma_launch(const TmaPlan& plan, const ImgParams& p, const RolloutPlan& ro, cudaStream_t stream) {
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -430,7 +470,7 @@ int tma_launch_step(const TmaPlan& plan, const ImgParams& p, cudaStream_t stream
   cfg.blockDim = dim3(kWarps * 32);
   cfg.dynamicSmemBytes = plan.smem;
   const double* table = plan.d_table;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tma_step_kernel<10, 10, 3>, p, plan.tmap, table, gs, n_groups);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tma_step_kernel<10, 10, 3, 64, 64>, p, plan.tmap, table, gs, n_groups, ro);
   if (e != cudaSuccess) return -(int)e;
   return 1;
 }

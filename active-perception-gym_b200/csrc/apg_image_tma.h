@@ -25,8 +25,9 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
 // (re-)encodes the tensor map of the bank; false when the driver entry point is unavailable or the bank is too large
 bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_items, int height);
 void tma_release(TmaPlan& plan);
-// the launch of one vector step; returns the number of launches or a negative cudaError
-int tma_launch_step(const TmaPlan& plan, const ImgParams& p, cudaStream_t stream);
+// one launch = the steps of `ro` (p.action / p.pred / p.reward2 / p.done2 point at the first one); returns the number of
+// launches or a negative cudaError
+int tma_launch(const TmaPlan& plan, const ImgParams& p, const RolloutPlan& ro, cudaStream_t stream);
 // loads the kernels (first-use module load off the step path)
 cudaError_t tma_preload(const TmaPlan& plan);
 

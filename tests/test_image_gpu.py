@@ -364,3 +364,119 @@ def test_rollout_equals_stepping():
                        e2.step({"action": acts[0], "prediction": preds[0]})[0]["glimpse"])
     e1.close()
     e2.close()
+
+
+def test_rollout_equals_stepping_tinyloc_shape():
+    """The TMA kernel steps a whole rollout window inside ONE launch (a warp takes its environments through every step
+    before it moves on): windows of 1 / 20 / 30 steps with autoresets inside must reproduce step-by-step execution --
+    per-step rewards and done flags, final observations (both glimpse sets), visited masks, statistics."""
+    import torch
+    import ap_gym_b200 as apg
+    from oracle.datasets import synthetic_u8_bank
+
+    N, steps = 3000, 51
+    imgs, labels = synthetic_u8_bank(seed=13, M=128, H=64, W=64, C=3, K=5)
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, 5), sensor_size=(10, 10))
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    acts = (torch.rand((steps, N, 2), generator=gen, device="cuda") * 2 - 1) * 1.3
+    preds = torch.rand((steps, N, 2), generator=gen, device="cuda") * 2 - 1
+    tgt = np.random.default_rng(0).uniform(-1, 1, (N, 2)).astype(np.float32)
+    e1 = apg.ImageLocalizationVectorEnv(N, cfg)
+    e2 = apg.ImageLocalizationVectorEnv(N, cfg)
+    assert e1._lib.apg_image_variant(e1._h) == 3
+    e1.reset(seed=9, options={"prediction_target": tgt})
+    e2.reset(seed=9, options={"prediction_target": tgt})
+    rew = torch.empty((steps, N), device="cuda")
+    done = torch.empty((steps, N), dtype=torch.bool, device="cuda")
+    e1.rollout(acts[:1], preds[:1], rew[:1], done[:1])
+    e1.rollout(acts[1:21], preds[1:21], rew[1:21], done[1:21])
+    e1.rollout(acts[21:], preds[21:], rew[21:], done[21:])
+    for s in range(steps):
+        o, r, te, tr, _ = e2.step({"action": acts[s], "prediction": preds[s]})
+        assert torch.equal(r, rew[s]) and torch.equal(te, done[s]), f"step {s}"
+    e1.sync()
+    for k in ("glimpse", "target_glimpse", "glimpse_pos", "time_step"):
+        assert torch.equal(e1._views[k], e2._views[k]), k
+    assert torch.equal(e1.state()["visited"], e2.state()["visited"]) and torch.equal(e1.state()["pos"], e2.state()["pos"])
+    assert e1.episode_stats(reduce=False) == pytest.approx(e2.episode_stats(reduce=False), rel=1e-12)
+    e1.close()
+    e2.close()
+
+
+def test_mnist_benchmark_shape_matches_oracle_n65536():
+    """BASELINE config 2 at FULL size (N = 65536, 28x28x1 uint8 bank, K = 10) against the oracle for 19 steps: 16 real
+    steps, the autoreset step and two steps of the next episode, through the persistent rollout kernel (one launch per
+    step here).  Bit-exact observations / flags / targets / indices, rewards within the float bar."""
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+    import ap_gym_b200 as apg
+
+    N, K = 65536, 10
+    imgs, labels = synthetic_u8_bank(seed=3, M=8192, H=28, W=28, C=1, K=K)
+    oracle = ImageEnvOracle(imgs, labels, N, task="cls", num_classes=K, track_overlay=False)
+    env = apg.ImageClassificationVectorEnv(
+        N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K)), output="numpy")
+    assert env._lib.apg_image_variant(env._h) == 4
+    o0, _ = oracle.reset(seed=21)
+    e0, _ = env.reset(seed=21)
+    assert np.array_equal(e0["glimpse"], o0["glimpse"])
+    rng = np.random.default_rng(6)
+    for s in range(19):
+        a = (rng.uniform(-1, 1, (N, 2)) * 1.2).astype(np.float32)
+        p = (rng.standard_normal((N, K)) * 3).astype(np.float32)
+        oo, orw, ote, otr, oinf = oracle.step(a, p)
+        eo, erw, ete, etr, einf = env.step({"action": a, "prediction": p})
+        for k in oo:
+            assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+        assert np.array_equal(ete, ote) and np.array_equal(etr, otr)
+        assert np.array_equal(einf["prediction"]["target"], oinf["prediction"]["target"])
+        assert np.array_equal(einf["index"], oinf["index"])
+        assert_close(erw, orw, RTOL, ATOL, f"step {s} reward")
+    assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited)
+    env.close()
+
+
+def test_hypothesis_seeds_and_geometries():
+    """Property test: for random seeds, image / sensor geometries, scales, step lengths and tasks the engine
+    reproduces the oracle bit-exactly (pixels, positions, masks, flags) -- whichever kernel the geometry selects."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+    import ap_gym_b200 as apg
+
+    @settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(seed=st.integers(0, 2**31 - 1), H=st.integers(12, 70), W=st.integers(12, 70), C=st.sampled_from([1, 3]),
+           S=st.integers(2, 11), scale=st.sampled_from([1.0, 1.0, 1.25, 2.0]), task=st.sampled_from(["cls", "loc"]),
+           msl=st.sampled_from([0.2, 0.5, 1.0]), T=st.integers(2, 6), u8=st.booleans())
+    def check(seed, H, W, C, S, scale, task, msl, T, u8):
+        # (sensor_scale < 1 lets the reference itself sample outside the image grid at the border -> ValueError: not drawn)
+        if S * scale > min(H, W):
+            return
+        N, K = 37, 4
+        imgs, labels = synthetic_u8_bank(seed=seed % 1000, M=16, H=H, W=W, C=C, K=K)
+        if not u8:
+            imgs = (imgs.astype(np.float32) / np.float32(255)) ** 2  # a float32 bank that is not k/255
+        kw = dict(sensor_size=(S, S), sensor_scale=scale, step_limit=T, max_step_length=msl)
+        oracle = ImageEnvOracle(imgs, labels, N, task=task, num_classes=K, track_overlay=False, **kw)
+        cls = apg.ImageClassificationVectorEnv if task == "cls" else apg.ImageLocalizationVectorEnv
+        env = cls(N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K), **kw), output="numpy")
+        rng = np.random.default_rng(seed)
+        tgt = rng.uniform(-1, 1, (N, 2)).astype(np.float32) if task == "loc" else None
+        oo, _ = oracle.reset(seed=seed, explicit_targets=tgt)
+        eo, _ = env.reset(seed=seed, options={"prediction_target": tgt} if task == "loc" else None)
+        for k in oo:
+            assert np.array_equal(eo[k], oo[k]), f"reset obs {k}"
+        for s in range(2 * T + 3):
+            a = (rng.uniform(-1, 1, (N, 2)) * 1.6).astype(np.float32)
+            p = rng.standard_normal((N, K if task == "cls" else 2)).astype(np.float32)
+            oo, orw, ote, _, oinf = oracle.step(a, p)
+            eo, erw, ete, _, einf = env.step({"action": a, "prediction": p})
+            for k in oo:
+                assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+            assert np.array_equal(_np(env.state()["pos"]), oracle.pos)
+            assert np.array_equal(_np(env.state()["visited"]).view(np.uint32), oracle.visited), f"step {s} visited"
+            assert np.array_equal(ete, ote)
+            assert_close(erw, orw, RTOL, ATOL, f"step {s} reward")
+        env.close()
+
+    check()

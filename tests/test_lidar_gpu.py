@@ -62,9 +62,33 @@ def test_engine_matches_reference_golden(name, mode):
     env.close()
 
 
-@pytest.mark.parametrize("bank,B,N,steps", [("rooms32", 64, 2048, 230), ("maze21", 8, 1024, 120), ("maze63", 256, 256, 110)])
+# GEOS-DEPENDENT RAYS.  The reference's result for a ray that grazes a lattice corner (zero-length intersection pieces:
+# Point / MultiPoint / GeometryCollection, lidar_localization2d.py:512-528) is whatever shapely's GEOS returns; engine and
+# oracle follow the reference's type dispatch under EXACT geometry, which no real GEOS has confirmed here
+# ("GEOS unpinned").  Such rays only occur on the four exact-diagonal beams of the scan right after a reset.  Setting
+# APG_TEST_MASK_GEOS_RAYS=1 removes those beams of reset observations from the bit-exact assertions below, should a
+# real shapely ever disagree; by default they are compared like every other ray.
+import os
+
+MASK_GEOS_RAYS = os.environ.get("APG_TEST_MASK_GEOS_RAYS", "0") == "1"
+
+
+def _beam_mask(B, reset_rows):
+    """(N, B) bool: beams that take part in the comparison (all, unless the GEOS switch masks the exact diagonals of
+    freshly reset environments)."""
+    keep = np.ones((len(reset_rows), B), bool)
+    if MASK_GEOS_RAYS and B % 8 == 0:
+        diag = np.array([B // 8 * k for k in (1, 3, 5, 7)])
+        keep[np.ix_(np.flatnonzero(reset_rows), diag)] = False
+    return keep
+
+
+@pytest.mark.parametrize("bank,B,N,steps", [("rooms32", 64, 2048, 230), ("maze21", 8, 1024, 120), ("maze63", 256, 256, 110),
+                                            ("maze63", 256, 2304, 104)])
 def test_engine_matches_oracle_seeded(bank, B, N, steps):
-    """Larger seeded runs (thousands of envs, >2 episodes incl. the device-side RNG resets) vs the C oracle."""
+    """Larger seeded runs (thousands of envs, >2 episodes incl. the device-side RNG resets) vs the C oracle; the last
+    case is the LIDARLocMaze benchmark shape (63x63 mazes, 256 beams) at N = 2304 across one autoreset.  GEOS unpinned:
+    see MASK_GEOS_RAYS above."""
     import ap_gym_b200 as apg
     from oracle.lidar_oracle import LidarVecOracle
 
@@ -86,8 +110,9 @@ def test_engine_matches_oracle_seeded(bank, B, N, steps):
         oo, orw, ote, otr, oinf = oracle.step(a, p)
         eo, erw, ete, etr, einf = env.step({"action": a, "prediction": p})
         assert np.array_equal(_np(env.state()["pos"]), oracle.pos), f"step {s} pos"
-        assert np.array_equal(_np(env.state()["cells"]), oinf["cells"]), f"step {s} cells"
-        assert np.array_equal(eo["lidar"], oo["lidar"]), f"step {s} lidar"
+        keep = _beam_mask(B, ~einf["_base_reward"])  # rows that were reset by this step
+        assert np.array_equal(_np(env.state()["cells"])[keep], oinf["cells"][keep]), f"step {s} cells"
+        assert np.array_equal(eo["lidar"][keep], oo["lidar"][keep]), f"step {s} lidar"
         assert np.array_equal(eo["odometry"], oo["odometry"])
         assert np.array_equal(eo["time_step"], oo["time_step"])
         assert np.array_equal(ete, ote) and np.array_equal(etr, otr)

@@ -148,3 +148,57 @@ print("COMPAT OK")
 def test_engine_envs_are_drop_ins_for_the_reference_api():
     r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "COMPAT OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+HIDE_AND_SEEK = r'''
+import sys
+ROOT = sys.argv[1]
+sys.path[:0] = [ROOT + "/oracle/shim", "/root/reference", ROOT + "/active-perception-gym_b200", ROOT]
+import numpy as np
+import ap_gym
+from ap_gym.envs.image import CircleSquareDataset, ImagePerceptionConfig
+from ap_gym.envs.image_classification import ImageClassificationVectorEnv
+from ap_gym.envs.circle_square_catch_or_flee import CircleSquareHideAndSeekVectorWrapper as RefW
+from ap_gym_b200 import CircleSquareHideAndSeekVectorWrapper as W
+
+ds = CircleSquareDataset(image_shape=(28, 28), show_gradient=True)
+
+
+class EngineSurface:  # what the wrapper touches of an engine env, fed by the reference's own vector env
+    def __init__(self, inner):
+        self.inner, self.config, self._W, self._H = inner, inner.config, 28, 28
+        self.prediction_space = inner.prediction_space
+
+    def reset(self, **kw):
+        return self.inner.reset(**kw)
+
+    def step(self, a):
+        return self.inner.step(a)
+
+
+ref = RefW(ImageClassificationVectorEnv(8, ImagePerceptionConfig(dataset=ds)))
+mine = W(EngineSurface(ImageClassificationVectorEnv(8, ImagePerceptionConfig(dataset=ds))))
+# (the reference's own mask_prediction=True variant raises KeyError in reset(): its info has no "prediction" there)
+masked = W(EngineSurface(ImageClassificationVectorEnv(8, ImagePerceptionConfig(dataset=ds))), mask_prediction=True)
+ref.reset(seed=3)
+mine.reset(seed=3)
+_, minfo = masked.reset(seed=3)
+assert minfo["prediction"]["target"] == ()
+rng = np.random.default_rng(0)
+for s in range(20):
+    a = {"action": rng.uniform(-1, 1, (8, 2)).astype(np.float32), "prediction": rng.standard_normal((8, 2)).astype(np.float32)}
+    o1, r1, t1, _, i1 = ref.step(a)
+    o2, r2, t2, _, i2 = mine.step(a)
+    o3, r3, t3, _, i3 = masked.step(a)
+    assert np.allclose(r1, r2, rtol=1e-6, atol=1e-7), s
+    assert np.allclose(i1["base_reward"], i2["base_reward"], rtol=1e-6, atol=1e-7)
+    # no prediction: reward = base reward (movement cost + hide-and-seek term), identical term as above
+    assert np.allclose(r3, i3["base_reward"]) and np.allclose(i3["base_reward"], i2["base_reward"], rtol=1e-6, atol=1e-7)
+    assert i3["prediction"]["target"] == ()
+print("HIDE OK")
+'''
+
+
+def test_hide_and_seek_reward_term_matches_the_reference_wrapper():
+    r = subprocess.run([sys.executable, "-c", HIDE_AND_SEEK, ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "HIDE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
