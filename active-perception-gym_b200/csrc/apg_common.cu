@@ -22,17 +22,6 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-// Device-wide hint: the granularity at which L2 fills from DRAM.  The engine's bank reads are random gathers of 32-64
-// bytes, so anything above one 32-byte sector is over-fetch.  APG_L2_FETCH=<32|64|128> overrides, 0 leaves the driver
-// default.
-int apply_device_tuning() {
-  int want = 32;
-  if (const char* ov = getenv("APG_L2_FETCH")) want = atoi(ov);
-  if (want == 32 || want == 64 || want == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want);
-  cudaGetLastError();  // a hint: failure to set it is not an error
-  return want;
-}
-
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

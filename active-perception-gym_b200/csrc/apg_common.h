@@ -16,7 +16,6 @@ namespace apg {
 std::string& last_error();
 int fail(int code, const char* fmt, ...);
 void count_launch(int64_t n = 1);
-int apply_device_tuning();  // L2 fetch granularity hint (see apg_common.cu)
 
 #define APG_CUDA(expr)                                                                              \
   do {                                                                                              \

@@ -1089,7 +1089,6 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   APG_CHECK(cfg->device >= 0 && cfg->device < ndev, APG_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
   APG_CUDA(cudaSetDevice(cfg->device));
 
-  apg::apply_device_tuning();
   apg_image_env* e = new apg_image_env();
   e->cfg = *cfg;
   const size_t N = cfg->num_envs;
@@ -1447,7 +1446,9 @@ int apg_image_step_host(apg_image_env* e, const float* h_action, const float* h_
   // (the special-purpose kernels take an environment range; the generic staged kernels step the whole batch at once)
   const bool ranged = persistent(e);
   int chunks = 1;
-  if (ranged) chunks = N >= 32768 ? 4 : (N >= 8192 ? 2 : 1);
+  // (measured on B200: two chunks for the TMA kernel; the thread-per-environment kernel has a launch cost that a
+  //  second chunk would pay twice, its single-step launch is shorter than the copy it would hide)
+  if (ranged && !e->small.spec) chunks = N >= 16384 ? 2 : 1;
   if (const char* ov = getenv("APG_HOST_CHUNKS")) {  // developer switch: number of pipeline chunks of the host step
     const int v = atoi(ov);
     if (ranged && v >= 1 && v <= 8) chunks = v;

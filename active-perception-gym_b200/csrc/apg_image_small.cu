@@ -28,6 +28,9 @@
 namespace apg_img {
 namespace {
 
+#ifndef APG_SMALL_COOP
+#define APG_SMALL_COOP 1  // 1: footprints copied warp-cooperatively through shared memory, 0: per-thread gathers (__ldg)
+#endif
 constexpr int kSmallThreads = 64;  // 2 warps per block: 65536 envs = 1024 blocks = 6.9 per SM, all resident (one wave)
 
 __device__ __forceinline__ float norm2f(float a, float b) {
@@ -169,10 +172,9 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     if (p.track) {
       const unsigned* gv = p.visited + (size_t)warp_env0 * p.H;
       unsigned* wv = s_vis + warp * 32 * sm.vis_stride;
-      // H <= 32 words per environment: one coalesced run per iteration, eight loads in flight at a time
-#pragma unroll 8
+      // H <= 32 words per environment: one coalesced run per iteration, all of them in flight at once (cp.async)
       for (int e = 0; e < n_env; ++e)
-        if (lane < p.H) wv[e * sm.vis_stride + lane] = __ldcg(gv + e * p.H + lane);
+        if (lane < p.H) __pipeline_memcpy_async(wv + e * sm.vis_stride + lane, gv + e * p.H + lane, 4);
     }
   }
   // logits of the first step on their way (stage 0)
@@ -245,6 +247,8 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
       consec = taps_consecutive<S0>(ccy, p.half0, p.scale, p.offy, p.H, rmin, wr, err);
       consec = taps_consecutive<S1>(ccx, p.half1, p.scale, p.offx, p.W, cmin, wc, err) && consec;
     }
+    unsigned fw[S0 + 1][3];
+#if APG_SMALL_COOP
     {
       const int my_row = idx * p.H + rmin;  // first bank row of this thread's footprint
       const int total = n_env * ch_per_env;
@@ -256,6 +260,19 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
       }
       __pipeline_commit();
     }
+#else
+    if (live && consec) {  // three aligned words per footprint row straight into registers
+      const unsigned* src = reinterpret_cast<const unsigned*>(bank + ((size_t)idx * p.H + rmin) * PITCH + (cmin & ~3));
+      constexpr int pitch_w = PITCH >> 2;
+#pragma unroll
+      for (int r = 0; r <= S0; ++r) {
+        fw[r][0] = __ldg(src + r * pitch_w);
+        fw[r][1] = __ldg(src + r * pitch_w + 1);
+        fw[r][2] = __ldg(src + r * pitch_w + 2);
+      }
+    }
+    __pipeline_commit();  // (keeps the group count of the cooperative variant)
+#endif
     // ---- next step's logits -> the other stage (they have the rest of the step to arrive); committed AFTER the
     // footprints so that waiting for the footprints does not wait for them
     if (k + 1 < ro.n_steps && n_env > 0)
@@ -332,9 +349,9 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
 
     // ---- the footprints have landed: 3 aligned words per row -> registers, then the slots are free (the output staging
     // aliases them)
+#if APG_SMALL_COOP
     __pipeline_wait_prior(1);
     __syncwarp();
-    unsigned fw[S0 + 1][3];
     if (live && consec) {
       const unsigned* src = reinterpret_cast<const unsigned*>(s_fp + lane * sm.fp_stride + (cmin & ~3));
       constexpr int pitch_w = PITCH >> 2;
@@ -346,6 +363,7 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
       }
     }
     __syncwarp();
+#endif
     if (live) {
       if (consec) {
         // every footprint pixel is converted once; row r + 1 of the window is the bottom row of sensor row r

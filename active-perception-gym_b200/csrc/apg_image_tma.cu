@@ -106,14 +106,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 // one glimpse footprint: box (BOX_W bytes x BOX_H rows) of the bank tensor at (x, y) -> shared memory, completion
-// counted on `bar`
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
+// counted on `bar` (shared-window addresses)
 __device__ __forceinline__ void tma_load_2d_u(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),

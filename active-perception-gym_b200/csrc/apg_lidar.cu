@@ -31,6 +31,7 @@ constexpr int kEnvsPerBlock = 32;
 
 struct LidarParams {
   int N, W, H, words, B, G, T, M;
+  int n0, n1;          // environments [n0, n1) of the shard are stepped by this launch (n0 a multiple of 32)
   int pad, pw, prows;  // shared-memory maps carry a free border of `pad` cells: (H + 2 pad) rows of pw words
   int static_map, static_idx, emit_cells, sparse;
   int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams), 3 = explicit reset (keep streams)
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int env0 = blockIdx.x * kEnvsPerBlock;
-  const int nE = min(kEnvsPerBlock, p.N - env0);
+  const int env0 = p.n0 + blockIdx.x * kEnvsPerBlock;
+  const int nE = min(kEnvsPerBlock, p.n1 - env0);
   const int mw = p.H * p.words;    // words of one bank map
   const int pmw = p.prows * p.pw;  // words of one padded shared-memory map
   const float Wf = (float)p.W, Hf = (float)p.H;
@@ -519,6 +520,11 @@ struct apg_lidar_env {
   float* d_acc1 = nullptr; float* d_acc2 = nullptr; float* d_acc_ret = nullptr;
   double* d_stats = nullptr;
   bool has_reset = false;
+  // *_host pipelining: sub-range launches, a copy stream and its events (see apg_lidar_step_host)
+  int r0 = 0, r1 = -1;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[8] = {};
+  float* lidar_out = nullptr;  // where this step's lidar observation goes (default: the engine's device buffer)
 };
 
 namespace {
@@ -529,23 +535,36 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   LidarParams p{};
   p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
   p.pad = e->pad; p.pw = e->pw; p.prows = e->prows;
+  p.n0 = e->r0; p.n1 = e->r1 < 0 ? c.num_envs : e->r1;
   p.T = c.step_limit; p.M = (int)e->n_maps; p.static_map = c.static_map; p.static_idx = c.static_map_index;
   p.emit_cells = c.emit_cells; p.sparse = c.sparse_reward ? 1 : 0; p.mode = mode; p.range = c.lidar_range; p.seed = seed; p.env_offset = c.env_offset;
   p.bank = e->d_bank; p.dirs = e->d_dirs; p.action = d_action; p.pred = d_pred;
   p.pos = e->b.d_pos; p.init = e->b.d_initial_pos; p.aliased = e->d_aliased; p.elapsed = e->d_elapsed;
   p.map_idx = e->d_map_idx; p.prev_done = e->d_prev_done; p.g0 = e->d_g0; p.g2 = e->d_g2;
-  p.lidar = e->b.d_lidar; p.odometry = e->b.d_odometry; p.time_step = e->b.d_time_step; p.map_obs = e->b.d_map;
+  p.lidar = e->lidar_out ? e->lidar_out : e->b.d_lidar; p.odometry = e->b.d_odometry; p.time_step = e->b.d_time_step; p.map_obs = e->b.d_map;
   p.reward = e->b.d_reward; p.base_reward = e->b.d_base_reward; p.loss = e->b.d_loss; p.target = e->b.d_target;
   p.terminated = e->b.d_terminated; p.truncated = e->b.d_truncated; p.stepped = e->b.d_stepped;
   p.map_idx_out = reinterpret_cast<long long*>(e->b.d_map_idx); p.cells = e->b.d_cells; p.dists = e->b.d_dists;
   p.reward2 = reward2; p.done2 = done2; p.err = e->d_err;
   p.acc1 = e->d_acc1; p.acc2 = e->d_acc2; p.acc_ret = e->d_acc_ret; p.ep_avg1 = e->b.d_ep_avg1; p.ep_final1 = e->b.d_ep_final1;
   p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return; p.stats = e->d_stats;
-  const int grid = apg::ceil_div(c.num_envs, kEnvsPerBlock);
+  const int grid = apg::ceil_div(p.n1 - p.n0, kEnvsPerBlock);
   lidar_step_kernel<<<grid, kThreads, e->smem, e->stream>>>(p);
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
   return APG_OK;
+}
+
+// device-visible alias of a page-locked host pointer (see apg_image_step_host)
+template <typename T>
+T* lidar_mapped_alias(T* h) {
+  if (!h) return nullptr;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<T*>(a.devicePointer) : nullptr;
 }
 
 }  // namespace
@@ -567,7 +586,6 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
                      cudaGetErrorString(de));
   APG_CHECK(cfg->device >= 0 && cfg->device < ndev, APG_ERR_INVALID, "device %d out of range", cfg->device);
   APG_CUDA(cudaSetDevice(cfg->device));
-  apg::apply_device_tuning();
   apg_lidar_env* e = new apg_lidar_env();
   e->cfg = *cfg;
   e->words = (cfg->width + 31) / 32;
@@ -623,6 +641,8 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
   A(apg::dev_alloc(&e->d_err, 1));
   A(apg::dev_alloc(&e->d_in_action, N * 2));
   A(apg::dev_alloc(&e->d_in_pred, N * 2));
+  A(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : e->ev_in) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   A(apg::dev_alloc(&e->d_dirs, B * 2));
   if (err == cudaSuccess && e->smem > 48 * 1024)
     A(cudaFuncSetAttribute(lidar_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -650,6 +670,8 @@ void apg_lidar_destroy(apg_lidar_env* e) {
   apg::dev_free(e->d_aliased); apg::dev_free(e->d_elapsed); apg::dev_free(e->d_map_idx); apg::dev_free(e->d_prev_done);
   apg::dev_free(e->d_g0); apg::dev_free(e->d_g2); apg::dev_free(e->d_err);
   apg::dev_free(e->d_in_action); apg::dev_free(e->d_in_pred);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (auto& ev : e->ev_in) if (ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -739,16 +761,44 @@ int apg_lidar_step_host(apg_lidar_env* e, const float* h_action, const float* h_
   APG_CHECK(e && h_action && h_pred, APG_ERR_INVALID, "apg_lidar_step_host: null argument");
   APG_CHECK(e->has_reset, APG_ERR_STATE, "step before reset");
   APG_CUDA(cudaSetDevice(e->cfg.device));
-  const size_t N = e->cfg.num_envs;
-  APG_CUDA(cudaMemcpyAsync(e->d_in_action, h_action, N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  APG_CUDA(cudaMemcpyAsync(e->d_in_pred, h_pred, N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  int rc = lidar_launch(e, 0, 0, e->d_in_action, e->d_in_pred, nullptr, nullptr);
-  if (rc != APG_OK) return rc;
-  if (h_reward) APG_CUDA(cudaMemcpyAsync(h_reward, e->b.d_reward, N * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (h_terminated) APG_CUDA(cudaMemcpyAsync(h_terminated, e->b.d_terminated, N, cudaMemcpyDeviceToHost, e->stream));
-  if (h_truncated) APG_CUDA(cudaMemcpyAsync(h_truncated, e->b.d_truncated, N, cudaMemcpyDeviceToHost, e->stream));
-  if (h_lidar)
-    APG_CUDA(cudaMemcpyAsync(h_lidar, e->b.d_lidar, N * e->cfg.beam_count * 4, cudaMemcpyDeviceToHost, e->stream));
+  const size_t N = e->cfg.num_envs, B = e->cfg.beam_count;
+  // same scheme as apg_image_step_host: chunks whose host-to-device copies (copy stream) overlap the kernels of the
+  // previous chunk; page-locked result buffers are written by the kernel directly
+  float* m_reward = lidar_mapped_alias(h_reward);
+  uint8_t* m_term = lidar_mapped_alias(h_terminated);
+  float* m_lidar = lidar_mapped_alias(h_lidar);
+  const int chunks = N >= 65536 ? 4 : (N >= 8192 ? 2 : 1);
+  const size_t per = ((N + chunks - 1) / chunks + 1023) & ~(size_t)1023;
+  e->lidar_out = m_lidar;
+  int rc = APG_OK;
+  for (int c = 0; c < chunks && rc == APG_OK; ++c) {
+    const size_t lo = (size_t)c * per, hi = lo + per < N ? lo + per : N;
+    if (lo >= hi) break;
+    cudaError_t ce = cudaMemcpyAsync(e->d_in_action + lo * 2, h_action + lo * 2, (hi - lo) * 2 * sizeof(float),
+                                     cudaMemcpyHostToDevice, e->copy_stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(e->d_in_pred + lo * 2, h_pred + lo * 2, (hi - lo) * 2 * sizeof(float), cudaMemcpyHostToDevice,
+                           e->copy_stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_in[c], e->copy_stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->stream, e->ev_in[c], 0);
+    if (ce != cudaSuccess) {
+      rc = apg::fail(APG_ERR_CUDA, "apg_lidar_step_host: %s", cudaGetErrorString(ce));
+      break;
+    }
+    e->r0 = (int)lo; e->r1 = (int)hi;
+    rc = lidar_launch(e, 0, 0, e->d_in_action, e->d_in_pred, m_reward, m_term);
+  }
+  e->r0 = 0; e->r1 = -1;
+  e->lidar_out = nullptr;
+  if (rc != APG_OK) {
+    cudaStreamSynchronize(e->copy_stream);
+    cudaStreamSynchronize(e->stream);
+    return rc;
+  }
+  if (h_reward && !m_reward) APG_CUDA(cudaMemcpyAsync(h_reward, e->b.d_reward, N * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (h_terminated && !m_term) APG_CUDA(cudaMemcpyAsync(h_terminated, e->b.d_terminated, N, cudaMemcpyDeviceToHost, e->stream));
+  if (h_lidar && !m_lidar) APG_CUDA(cudaMemcpyAsync(h_lidar, e->b.d_lidar, N * B * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (h_truncated) memset(h_truncated, 0, N);  // TimeLimit(issue_termination=True) never truncates
   APG_CUDA(cudaStreamSynchronize(e->stream));
   return APG_OK;
 }

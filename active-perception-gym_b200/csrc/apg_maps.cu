@@ -1,0 +1,126 @@
+// Procedural maze maps on the device, bit-identical to the reference's generator
+//   FloorMapDatasetMaze.get_data_point      ap_gym/envs/floor_map/floor_map_dataset_maze.py:24-55
+// (recursive depth-first `carve` with numpy draws).  One thread generates one maze: the recursion becomes an explicit
+// stack of packed frames (cell, direction order, next direction, first flag), the draws are the reference's --
+//   rng = default_rng(idx)                       SeedSequence -> PCG64                      (csrc/apg_rng.h)
+//   rng.permutation(directions), once per cell   shuffle of arange(4): random_interval(i), i = 3, 2, 1 = masked 32-bit
+//                                                draws with rejection (numpy's buffered next_uint32)
+//   rng.random() < branching_prob                once per eligible neighbour after the first carved one
+// -- in the same order, so that the bank index -> map function is the reference's and maps never have to be generated on
+// the host (the reference's dataset has len 2**32; 63x63 mazes take 79 ms each there).  Restated on the CPU in
+// oracle/floor_map_oracle.py; pinned against the reference-generated banks tests/golden/maps_maze{21,63}.npz.
+#include <vector>
+
+#include "apg_common.h"
+#include "apg_rng.h"
+
+namespace {
+
+__device__ __forceinline__ unsigned interval(apg::Pcg64& g, unsigned max, unsigned mask) {
+  unsigned v;
+  do { v = apg::pcg64_next32(g) & mask; } while (v > max);
+  return v;
+}
+
+// direction order of one cell: numpy's Generator.permutation on a 4-row array = shuffle(arange(4)); 2 bits per entry
+__device__ __forceinline__ unsigned draw_order(apg::Pcg64& g) {
+  unsigned o[4] = {0u, 1u, 2u, 3u};
+  {
+    const unsigned j = interval(g, 3u, 3u);
+    const unsigned t = o[3]; o[3] = o[j]; o[j] = t;
+  }
+  {
+    const unsigned j = interval(g, 2u, 3u);
+    const unsigned t = o[2]; o[2] = o[j]; o[j] = t;
+  }
+  {
+    const unsigned j = interval(g, 1u, 1u);
+    const unsigned t = o[1]; o[1] = o[j]; o[j] = t;
+  }
+  return o[0] | (o[1] << 2) | (o[2] << 4) | (o[3] << 6);
+}
+
+// frame: x (bits 0-7) | y (8-15) | order (16-23) | next direction slot k (24-26) | first (27)
+__global__ void maze_kernel(const unsigned long long* __restrict__ idx, int n, int W, int H, double branching_prob,
+                            unsigned* __restrict__ bits, unsigned* __restrict__ stack, int cells) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const int words = (W + 31) >> 5;
+  unsigned* b = bits + (size_t)m * H * words;
+  for (int y = 0; y < H; ++y)
+    for (int w = 0; w < words; ++w) {
+      const int nb = min(32, W - w * 32);
+      b[y * words + w] = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);  // all walls
+    }
+  apg::Pcg64 g;
+  apg::pcg64_seed(g, idx[m]);
+  unsigned* st = stack + (size_t)m * cells;
+  b[1 * words] &= ~(1u << 1);  // starting cell (1, 1)
+  int sp = 0;
+  st[0] = 1u | (1u << 8) | (draw_order(g) << 16) | (1u << 27);
+  const int dxs[4] = {2, -2, 0, 0}, dys[4] = {0, 0, 2, -2};
+  while (sp >= 0) {
+    unsigned fr = st[sp];
+    const unsigned k = (fr >> 24) & 7u;
+    if (k == 4u) {
+      --sp;
+      continue;
+    }
+    const int x = fr & 0xff, y = (fr >> 8) & 0xff;
+    const unsigned d = (fr >> (16 + 2 * k)) & 3u;
+    fr += 1u << 24;
+    const int nx = x + dxs[d], ny = y + dys[d];
+    bool push = false;
+    if (nx > 0 && nx < W - 1 && ny > 0 && ny < H - 1 && ((b[ny * words + (nx >> 5)] >> (nx & 31)) & 1u)) {
+      const bool first = (fr >> 27) & 1u;
+      // `first or rng.random() < branching_prob`: the draw only happens when `first` is False
+      if (first || ((double)(apg::pcg64_next64(g) >> 11) * (1.0 / 9007199254740992.0)) < branching_prob) {
+        const int ix = x + dxs[d] / 2, iy = y + dys[d] / 2;
+        b[iy * words + (ix >> 5)] &= ~(1u << (ix & 31));
+        b[ny * words + (nx >> 5)] &= ~(1u << (nx & 31));
+        fr &= ~(1u << 27);
+        push = true;
+      }
+    }
+    st[sp] = fr;
+    if (push) {
+      ++sp;
+      st[sp] = (unsigned)nx | ((unsigned)ny << 8) | (draw_order(g) << 16) | (1u << 27);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int apg_maps_generate_maze(int32_t device, const uint64_t* h_indices, int64_t n_maps, int32_t width,
+                                      int32_t height, double branching_prob, uint32_t* h_bits) {
+  APG_CHECK(h_indices && h_bits && n_maps > 0, APG_ERR_INVALID, "apg_maps_generate_maze: bad argument");
+  APG_CHECK(width >= 3 && height >= 3 && width <= 255 && height <= 255 && (width & 1) && (height & 1), APG_ERR_INVALID,
+            "Width and height must be odd (and at most 255).");
+  int ndev = 0;
+  cudaError_t de = cudaGetDeviceCount(&ndev);
+  if (de != cudaSuccess || ndev <= 0)
+    return apg::fail(APG_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(de));
+  APG_CHECK(device >= 0 && device < ndev, APG_ERR_INVALID, "device %d out of range", device);
+  APG_CUDA(cudaSetDevice(device));
+  const int words = (width + 31) / 32;
+  const int cells = ((width - 1) / 2) * ((height - 1) / 2) + 1;
+  const size_t nbits = (size_t)n_maps * height * words;
+  unsigned long long* d_idx = nullptr;
+  unsigned *d_bits = nullptr, *d_stack = nullptr;
+  cudaError_t err = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+  A(cudaMalloc(&d_idx, n_maps * 8));
+  A(cudaMalloc(&d_bits, nbits * 4));
+  A(cudaMalloc(&d_stack, (size_t)n_maps * cells * 4));
+  if (err == cudaSuccess) {
+    A(cudaMemcpy(d_idx, h_indices, n_maps * 8, cudaMemcpyHostToDevice));
+    maze_kernel<<<(unsigned)((n_maps + 63) / 64), 64>>>(d_idx, (int)n_maps, width, height, branching_prob, d_bits, d_stack, cells);
+    apg::count_launch();
+    A(cudaGetLastError());
+    A(cudaMemcpy(h_bits, d_bits, nbits * 4, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_idx); cudaFree(d_bits); cudaFree(d_stack);
+  if (err != cudaSuccess) return apg::fail(APG_ERR_CUDA, "apg_maps_generate_maze: %s", cudaGetErrorString(err));
+  return APG_OK;
+}

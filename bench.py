@@ -375,11 +375,22 @@ def run_workload(name, args, rank, world, local_rank, dist, sampler, peaks):
     barrier()
     t_wall0 = time.time()
     ev0.record()
+    t_host0 = time.perf_counter()
     run(K)
+    host_enqueue_us = (time.perf_counter() - t_host0) * 1e6
     ev1.record()
+    back_to_back_ms = None
+    if os.environ.get("APG_BENCH_DIAG"):  # a second window queued behind the first: device time without the idle-start gap
+        ev2 = ev()
+        run(K)
+        ev2.record()
     barrier()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
+    if os.environ.get("APG_BENCH_DIAG"):
+        back_to_back_ms = ev1.elapsed_time(ev2)
+        sys.stderr.write("diag %s rank %d: timed window %.1f us, host enqueue %.1f us, same window queued back to back %.1f us\n"
+                         % (name, rank, ms * 1e3, host_enqueue_us, back_to_back_ms * 1e3))
     launches = lib.apg_launch_count() - l0
     clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)

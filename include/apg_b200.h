@@ -149,11 +149,15 @@ int apg_image_queue_reset_payload(apg_image_env* env, const int64_t* h_idx, cons
 int apg_image_pending_payloads(apg_image_env* env);
 
 /* The reference's three reset-path Generators (g0 env-level, g1 module-level, g2 dataset iterator) as
- * numpy PCG64 states.  Once set, the engine draws the payload of every autoreset itself (host side, bit-identical to
- * numpy: image_perception_module.py:129-133,159-161, dataset_iterator.py:57, image_localization.py:153-156) whenever
- * no payload is queued -- for the GLOBAL batch of global_num_envs envs, of which this shard is
- * [env_offset, env_offset + num_envs).  apg_image_get_streams returns the advanced states (e.g. to continue them in
- * numpy for the next explicit reset). */
+ * numpy PCG64 states.  Once set, the engine draws the payload of every autoreset itself whenever no payload is queued --
+ * ON THE DEVICE, in-stream, bit-identical to numpy (csrc/apg_payload.cu; image_perception_module.py:129-133,159-161,
+ * dataset_iterator.py:57, image_localization.py:153-156) -- for the GLOBAL batch of global_num_envs envs, of which this
+ * shard is [env_offset, env_offset + num_envs).  The states are uploaded and every scratch buffer is allocated HERE (and
+ * in apg_image_set_bank), so that no step ever allocates, synchronises or loads a kernel for the first time; banks
+ * whose length would reject too many Lemire draws fall back to drawing on the host.
+ * apg_image_get_streams returns the current states (e.g. to continue them in numpy for the next explicit reset); payloads
+ * that were drawn ahead of time (apg_image_prefetch_payloads) are dropped and the streams rewound to the state before
+ * the oldest of them, so the caller always sees the reference's stream position. */
 typedef struct {
   uint64_t state_hi, state_lo; /* numpy bit_generator.state["state"]["state"] (128 bit) */
   uint64_t inc_hi, inc_lo;     /* ...["state"]["inc"] */
@@ -170,12 +174,19 @@ int apg_image_prefetch_payloads(apg_image_env* env, int32_t count);
 int apg_image_step(apg_image_env* env, const float* d_action, const float* d_pred);
 /* n_steps consecutive steps from stacked device inputs d_actions (n_steps, N, 2), d_preds (n_steps, N, K|2);
  * per-step reward / done flags are additionally written to d_rewards (n_steps, N) f32 and d_dones
- * (n_steps, N) u8 when these are non-NULL.  Autoreset steps consume queued payloads.  Asynchronous. */
+ * (n_steps, N) u8 when these are non-NULL.  Autoreset steps consume queued payloads (drawn in-stream when the reset
+ * streams are set).  Asynchronous.  Results are those of n_steps calls of apg_image_step; for the shapes served by a
+ * persistent kernel (apg_image_variant 3 and 4) a window of up to 128 steps is ONE launch in which every thread /
+ * warp keeps its environments' state on chip and walks them through all steps of the window. */
 int apg_image_rollout(apg_image_env* env, const float* d_actions, const float* d_preds, int32_t n_steps,
                       float* d_rewards, uint8_t* d_dones);
-/* One vector step with HOST inputs/outputs: copies h_action/h_pred to the device, steps, copies reward (N) f32,
- * terminated/truncated (N) u8 and, when non-NULL, glimpse (N*P) f32 back, then synchronises.  This is the
- * reference-facing call: same argument meaning as env.step({"action", "prediction"}). */
+/* One vector step with HOST inputs/outputs: copies h_action/h_pred to the device, steps, delivers reward (N) f32,
+ * terminated/truncated (N) u8 and, when non-NULL, glimpse (N*P) f32 in the caller's buffers, then synchronises.  This
+ * is the reference-facing call: same argument meaning as env.step({"action", "prediction"}).
+ * Pipelining: the batch is cut into chunks whose host-to-device copies (a second stream) overlap the stepping of the
+ * previous chunk.  PAGE-LOCKED result buffers (cudaHostAlloc / cudaHostRegister / torch pinned memory) are written by
+ * the kernels directly (posted writes over PCIe, no copy afterwards); a page-locked h_glimpse receives the observation
+ * INSTEAD of the engine's device buffer for that step.  Pageable buffers get ordinary device-to-host copies. */
 int apg_image_step_host(apg_image_env* env, const float* h_action, const float* h_pred, float* h_reward,
                         uint8_t* h_terminated, uint8_t* h_truncated, float* h_glimpse);
 
@@ -197,8 +208,13 @@ int apg_image_get_stats(apg_image_env* env, double* h_stats, int clear);
 /* Reads (and with clear!=0 resets) the sticky device error flags; synchronises the stream. */
 int apg_image_poll_error(apg_image_env* env, uint32_t* flags, int clear);
 int apg_image_sync(apg_image_env* env);
-/* Which step-kernel variant the handle selected for its sensor geometry: 0 = block-staged / warp-per-env blend,
- * 1 = block-staged / thread-per-env blend (small glimpses), 2 = persistent producer/consumer pipeline. */
+/* Which step-kernel variant the handle selected for its bank / sensor geometry:
+ *   0 = generic staged tiles, warp-per-env blend        (any geometry / scale / bank dtype, large glimpses)
+ *   1 = generic staged tiles, thread-per-env blend      (any geometry / scale / bank dtype, glimpses <= 96 floats)
+ *   3 = TMA-tile persistent kernel, whole rollout windows per launch   (uint8 64x64x3 bank, 10x10 sensor, scale 1:
+ *       TinyImageNetLoc / TinyImageNet)
+ *   4 = persistent thread-per-env rollout kernel        (uint8 single-channel bank up to 32x32, 5x5 sensor, scale 1,
+ *       classification: MNIST) */
 int apg_image_variant(apg_image_env* env);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -276,6 +292,14 @@ int apg_lidar_get_buffers(apg_lidar_env* env, apg_lidar_buffers* out);
 int apg_lidar_get_stats(apg_lidar_env* env, double* h_stats, int clear); /* same layout as apg_image_get_stats */
 int apg_lidar_poll_error(apg_lidar_env* env, uint32_t* flags, int clear);
 int apg_lidar_sync(apg_lidar_env* env);
+
+/* Procedural maze maps generated ON THE DEVICE, bit-identical to the reference's generator
+ * FloorMapDatasetMaze.get_data_point (ap_gym/envs/floor_map/floor_map_dataset_maze.py:24-55; the recursive carve as an
+ * explicit stack, the numpy draws of default_rng(index) in the same order): map i of the result is dataset[h_indices[i]],
+ * bit-packed like apg_lidar_set_map_bank expects ((n_maps, height, ceil(width/32)) uint32, bit = wall).  Odd sizes up
+ * to 255.  Synchronous.  The rooms generator (floor_map_dataset_rooms.py) is not provided. */
+int apg_maps_generate_maze(int32_t device, const uint64_t* h_indices, int64_t n_maps, int32_t width, int32_t height,
+                           double branching_prob, uint32_t* h_bits);
 
 /* Host-side test hook for the numpy-compatible random streams used on the device reset path (csrc/apg_rng.h):
  * a Generator(PCG64(SeedSequence(seed))) driven by n_ops operations --

@@ -480,3 +480,105 @@ def test_hypothesis_seeds_and_geometries():
         env.close()
 
     check()
+
+
+def test_sparse_env_exposes_weighted_loss_and_dict_target_spaces():
+    """`sparse=True` = SparsifyVectorWrapper (sparsify_wrapper.py:49-88): loss_fn is WeightedLossFn, the target spaces are
+    Dict{"target", "weight"} and the reward the kernel computes equals base_reward - loss_fn(prediction, info target)."""
+    import ap_gym_b200 as apg
+    from oracle.datasets import synthetic_u8_bank
+
+    imgs, labels = synthetic_u8_bank(seed=2, M=64, H=28, W=28, C=1, K=10)
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, 10))
+    for cls, pw in ((apg.ImageClassificationVectorEnv, 10), (apg.ImageLocalizationVectorEnv, 2)):
+        env = cls(64, cfg, sparse=True, output="numpy")
+        assert isinstance(env.loss_fn, apg.WeightedLossFn)
+        assert set(env.single_prediction_target_space.spaces) == {"target", "weight"}
+        assert set(env.prediction_target_space.spaces) == {"target", "weight"}
+        rng = np.random.default_rng(0)
+        env.reset(seed=1, options={"prediction_target": rng.uniform(-1, 1, (64, 2)).astype(np.float32)} if pw == 2 else None)
+        for s in range(18):
+            a = rng.uniform(-1, 1, (64, 2)).astype(np.float32)
+            p = rng.standard_normal((64, pw)).astype(np.float32)
+            o, r, te, tr, info = env.step({"action": a, "prediction": p})
+            tgt = info["prediction"]["target"]
+            assert np.array_equal(tgt["weight"], te.astype(np.float32))
+            want = info["base_reward"] - env.loss_fn(p, tgt, (64,))
+            assert_close(r, want, RTOL, ATOL, f"step {s} sparse reward")
+        env.close()
+
+
+def test_prefetched_payloads_do_not_move_the_reference_streams():
+    """Payloads drawn ahead of time advance the engine's copies of the Generators; reading them back (np_random, an
+    unseeded reset) drops the prefetched payloads and rewinds, so the env continues exactly like one that never
+    prefetched."""
+    import ap_gym_b200 as apg
+    from oracle.datasets import synthetic_u8_bank
+
+    imgs, labels = synthetic_u8_bank(seed=5, M=100, H=28, W=28, C=1, K=10)
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, 10))
+    a_env = apg.ImageClassificationVectorEnv(33, cfg, output="numpy", payload_ring=4)
+    b_env = apg.ImageClassificationVectorEnv(33, cfg, output="numpy", payload_ring=4)
+    a_env.reset(seed=7)
+    b_env.reset(seed=7)
+    rng = np.random.default_rng(0)
+    for s in range(5):
+        act = {"action": rng.uniform(-1, 1, (33, 2)).astype(np.float32), "prediction": rng.standard_normal((33, 10)).astype(np.float32)}
+        a_env.step(act)
+        b_env.step(act)
+    a_env.queue_autoreset_payloads(3)
+    st_a, st_b = a_env.np_random.bit_generator.state, b_env.np_random.bit_generator.state
+    assert st_a == st_b
+    oa, ia = a_env.reset()   # unseeded: the streams continue
+    ob, ib = b_env.reset()
+    assert np.array_equal(ia["index"], ib["index"]) and np.array_equal(oa["glimpse"], ob["glimpse"])
+    for s in range(20):      # crosses an autoreset drawn by the engine
+        act = {"action": rng.uniform(-1, 1, (33, 2)).astype(np.float32), "prediction": rng.standard_normal((33, 10)).astype(np.float32)}
+        xa, xb = a_env.step(act), b_env.step(act)
+        assert np.array_equal(xa[0]["glimpse"], xb[0]["glimpse"]) and np.array_equal(xa[4]["index"], xb[4]["index"])
+    a_env.close()
+    b_env.close()
+
+
+@pytest.mark.parametrize("shape", ["mnist", "tinyloc"])
+def test_host_step_chunks_and_mapped_outputs(shape, monkeypatch):
+    """apg_image_step_host: the chunked pipeline (1 vs 4 chunks) and page-locked vs pageable result buffers give
+    identical rewards / flags / observations."""
+    import ctypes as C
+    import torch
+    import ap_gym_b200 as apg
+    from ap_gym_b200 import _capi
+    from oracle.datasets import synthetic_u8_bank
+
+    N = 40000
+    if shape == "mnist":
+        imgs, labels = synthetic_u8_bank(seed=5, M=256, H=28, W=28, C=1, K=10)
+        mk = lambda: apg.ImageClassificationVectorEnv(N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, 10)))
+        pw, P = 10, 25
+    else:
+        imgs, labels = synthetic_u8_bank(seed=5, M=64, H=64, W=64, C=3, K=5)
+        mk = lambda: apg.ImageLocalizationVectorEnv(
+            N, apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, 5), sensor_size=(10, 10)),
+            target_sampling="uniform")
+        pw, P = 2, 300
+    lib = _capi.lib()
+    results = []
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-1, 1, (19, N, 2)).astype(np.float32)
+    preds = rng.standard_normal((19, N, pw)).astype(np.float32)
+    for chunks, pinned in (("1", False), ("4", True)):
+        monkeypatch.setenv("APG_HOST_CHUNKS", chunks)
+        env = mk()
+        env.reset(seed=2)
+        alloc = (lambda *sh, dt: torch.empty(sh, dtype=dt).pin_memory()) if pinned else (lambda *sh, dt: torch.empty(sh, dtype=dt))
+        r, te, tr, g = alloc(N, dt=torch.float32), alloc(N, dt=torch.uint8), alloc(N, dt=torch.uint8), alloc(N, P, dt=torch.float32)
+        out = []
+        for s in range(19):
+            _capi.check(lib.apg_image_step_host(env._h, acts[s].ctypes.data_as(C.c_void_p), preds[s].ctypes.data_as(C.c_void_p),
+                                                r.data_ptr(), te.data_ptr(), tr.data_ptr(), g.data_ptr()))
+            out.append((r.clone().numpy(), te.clone().numpy(), tr.clone().numpy(), g.clone().numpy()))
+        results.append(out)
+        env.close()
+    for s in range(19):
+        for x, y in zip(results[0][s], results[1][s]):
+            assert np.array_equal(x, y), f"step {s}"

@@ -211,3 +211,35 @@ def test_lidar_full_size_properties():
             assert float(r.abs().max()) == 0.0 and float(o["time_step"].max()) == -1.0
     env.close()
     shard.close()
+
+
+def test_host_step_chunks_and_mapped_outputs():
+    """apg_lidar_step_host with page-locked result buffers (written by the kernel, chunked pipeline) against the same
+    call with pageable buffers (device-to-host copies)."""
+    import ctypes as C
+    import torch
+    import ap_gym_b200 as apg
+    from ap_gym_b200 import _capi
+
+    maps = load_bank("rooms32", 64)
+    N, B = 70000, 16
+    lib = _capi.lib()
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-1, 1, (6, N, 2)).astype(np.float32)
+    preds = rng.uniform(-1, 1, (6, N, 2)).astype(np.float32)
+    results = []
+    for pinned in (False, True):
+        env = apg.LIDARLocalization2DVectorEnv(N, apg.FloorMapBank.from_maps(maps), lidar_beam_count=B)
+        env.reset(seed=3)
+        alloc = (lambda *sh, dt: torch.empty(sh, dtype=dt).pin_memory()) if pinned else (lambda *sh, dt: torch.empty(sh, dtype=dt))
+        r, te, tr, li = alloc(N, dt=torch.float32), alloc(N, dt=torch.uint8), alloc(N, dt=torch.uint8), alloc(N, B, dt=torch.float32)
+        out = []
+        for s in range(6):
+            _capi.check(lib.apg_lidar_step_host(env._h, acts[s].ctypes.data_as(C.c_void_p), preds[s].ctypes.data_as(C.c_void_p),
+                                                r.data_ptr(), te.data_ptr(), tr.data_ptr(), li.data_ptr()))
+            out.append((r.clone().numpy(), te.clone().numpy(), li.clone().numpy()))
+        results.append(out)
+        env.close()
+    for s in range(6):
+        for x, y in zip(results[0][s], results[1][s]):
+            assert np.array_equal(x, y), f"step {s}"
