@@ -645,6 +645,7 @@ struct apg_image_env {
   // keeps the episode clock / payload ring where they are until every chunk of the step has been launched
   int r0 = 0, r1 = -1;
   bool hold = false;
+  bool top_up = true;  // rollout windows replace the autoreset payloads they consume right behind their launch
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[8] = {};
   // bank
@@ -1002,10 +1003,20 @@ int rollout_window(apg_image_env* e, const float* d_actions, const float* d_pred
     if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
     if (!e->hold) {
+      int drawn = 0;
+      for (int i = 0; i < resets; ++i) drawn += e->ring[(e->ring_head + i) % ring].drawn ? 1 : 0;
       e->ring_head = (e->ring_head + resets) % ring;
       e->ring_count -= resets;
       e->t = t;
       e->needs_reset = need;
+      // Replace the payloads this launch consumed right behind it, in-stream: the draws of the NEXT autoresets then run
+      // while the host is idle anyway instead of sitting in front of the next window's launch.  The streams run ahead
+      // of the reference's position by the queued payloads; apg_image_get_streams / an explicit reset rewind them.
+      if (e->device_rng && e->have_streams && e->top_up)
+        for (int i = 0; i < drawn && e->ring_count < ring; ++i) {
+          int rc = generate_payload(e);
+          if (rc != APG_OK) return rc;
+        }
     }
     done += m;
   }
@@ -1209,6 +1220,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   if (const char* ov = getenv("APG_IMG_FORCE_SLOW")) e->force_slow = atoi(ov) != 0;
   if (const char* ov = getenv("APG_IMG_HOST_RNG")) e->host_rng = atoi(ov) != 0;
   if (const char* ov = getenv("APG_IMG_PDL")) e->pdl = atoi(ov) ? 1 : 0;
+  if (const char* ov = getenv("APG_IMG_TOP_UP")) e->top_up = atoi(ov) != 0;
   if (err == cudaSuccess && !generic_only && e->thread_blend && apg_img::small_plan(e->small, *cfg, e->words))
     A(apg_img::small_preload(e->small));
   if (err == cudaSuccess && !generic_only && !e->thread_blend) {
