@@ -1454,6 +1454,7 @@ int apg_image_step_host(apg_image_env* e, const float* h_action, const float* h_
   float* m_reward = mapped_alias(h_reward);
   uint8_t* m_term = mapped_alias(h_terminated);
   float* m_glimpse = mapped_alias(h_glimpse);
+  if (reinterpret_cast<uintptr_t>(m_glimpse) & 15) m_glimpse = nullptr;  // the special kernels store 128 bits at a time
   // The batch is cut into chunks: the host-to-device copy of chunk c+1 (copy stream) runs while chunk c is stepped
   // (the special-purpose kernels take an environment range; the generic staged kernels step the whole batch at once)
   const bool ranged = persistent(e);

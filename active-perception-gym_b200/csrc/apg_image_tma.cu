@@ -29,8 +29,11 @@
 namespace apg_img {
 namespace {
 
+#ifndef APG_TMA_TRIPLE
+#define APG_TMA_TRIPLE 1  // 1: phase B blends 32 / S1 environments per pass, lane = (environment, column); 0: one per pass
+#endif
 #ifndef APG_TMA_MINB
-#define APG_TMA_MINB 4
+#define APG_TMA_MINB (APG_TMA_TRIPLE ? 2 : 4)
 #endif
 #ifndef APG_TMA_REPLICAS
 #define APG_TMA_REPLICAS 8
@@ -41,7 +44,13 @@ namespace {
 #ifndef APG_TMA_ARITH
 #define APG_TMA_ARITH 0  // 1: convert pixels arithmetically (px_to_f64) instead of the table lookup (experiment)
 #endif
-constexpr int kWarps = 8;
+#ifndef APG_TMA_WARPS
+#define APG_TMA_WARPS (APG_TMA_TRIPLE ? 10 : 8)
+#endif
+#ifndef APG_TMA_STAGE_ROWS
+#define APG_TMA_STAGE_ROWS 10  // sensor rows staged in shared memory between two 128-bit copy-outs (triple mode)
+#endif
+constexpr int kWarps = APG_TMA_WARPS;
 constexpr int kReplicas = APG_TMA_REPLICAS;         // table copies: lane & (kReplicas - 1) picks its own
 constexpr int kTableBytes = 256 * kReplicas * 8;    // 16 KB at 8 copies
 
@@ -62,7 +71,27 @@ struct Geom {
   static constexpr int TILE_BYTES = BOX_W * BOX_H;
   static constexpr int TILE_STRIDE = (TILE_BYTES + 127) & ~127;  // tensor-map copies land on 128-byte boundaries
   static constexpr int TAPS = S0 + S1;
+#if APG_TMA_TRIPLE
+  // lane = (environment of the pass, sensor column): E environments per pass, every lane blends the C channels of its
+  // column; the float32 rows go through a shared-memory stage so that the global stores are 128-bit and contiguous
+  static constexpr int E = 32 / S1;
+  static constexpr int STAGE_ROWS = APG_TMA_STAGE_ROWS < S0 ? APG_TMA_STAGE_ROWS : S0;
+  static constexpr int STAGE_ENV = ((STAGE_ROWS * G + 31) & ~31) + 4;  // floats per environment: = 4 mod 32 (bank spread), 16-byte multiple
+  static constexpr int STAGE_BYTES = E * STAGE_ENV * 4;
+  static constexpr int WY_BYTES = E * S0 * 8;
+  static constexpr int OFF_WY = 2 * E * TILE_STRIDE;
+  static constexpr int OFF_HDR = OFF_WY + ((WY_BYTES + 15) & ~15);
+  static constexpr int OFF_STAGE = OFF_HDR + 32 * 32;
+  static constexpr int OFF_MBAR = OFF_STAGE + STAGE_BYTES;
+  static constexpr int WARP_BYTES = (OFF_MBAR + 16 + 127) & ~127;
+  static_assert(S0 <= S1, "lane (environment, column t) verifies tap row t");
+  static_assert((STAGE_ROWS * G) % 4 == 0 && (S0 * G) % 4 == 0, "128-bit copy-out");
+#else
+  static constexpr int OFF_WY = 2 * TILE_STRIDE;
+  static constexpr int OFF_HDR = OFF_WY + TAPS * 16;
+  static constexpr int OFF_MBAR = OFF_HDR + 32 * 32;
   static constexpr int WARP_BYTES = (2 * TILE_STRIDE + TAPS * 16 + 32 * 32 + 16 + 127) & ~127;
+#endif
   static constexpr int SMEM = kTableBytes + kWarps * WARP_BYTES + 128;
   static_assert(G <= 32 && TAPS <= 32, "one lane per (column, channel) and one lane per tap");
 };
@@ -176,6 +205,12 @@ __device__ __noinline__ void blend_env_general(const unsigned char* bank, int H,
   }
 }
 
+#if APG_TMA_ARITH
+#define APG_PX(b) px_to_f64((unsigned char)(b))
+#else
+#define APG_PX(b) tab[(int)(b) * kReplicas]
+#endif
+
 // IH x IW = the bank image size: compile-time, like the sensor geometry -- the per-environment prologue of phase B runs
 // once per glimpse on a warp with 64 registers per thread, every runtime constant it re-reads is an instruction.
 template <int S0, int S1, int C, int IH, int IW>
@@ -188,9 +223,9 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* wbase = smem + kTableBytes + warp * Gm::WARP_BYTES;
   unsigned char* tiles = wbase;
-  double* s_wy = reinterpret_cast<double*>(wbase + 2 * Gm::TILE_STRIDE);  // APG_TMA_WYSMEM: row weights of the current glimpse
-  TileHdr* hdrs = reinterpret_cast<TileHdr*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16);
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wbase + 2 * Gm::TILE_STRIDE + Gm::TAPS * 16 + 32 * 32);
+  double* s_wy = reinterpret_cast<double*>(wbase + Gm::OFF_WY);  // row weights of the glimpse(s) being blended
+  TileHdr* hdrs = reinterpret_cast<TileHdr*>(wbase + Gm::OFF_HDR);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wbase + Gm::OFF_MBAR);
   unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + kTableBytes + kWarps * Gm::WARP_BYTES);
   __shared__ double s_stats[6];
 
@@ -210,16 +245,26 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   }
   grid_dependency_wait(p.pdl);
 
+#if APG_TMA_TRIPLE
+  // lane = (environment es of the pass, column j); lanes past E * S1 shadow the last column of the last environment
+  const bool lane_ok = lane < Gm::E * S1;
+  const int es_lane = lane_ok ? lane / S1 : Gm::E - 1;
+  const int j = lane_ok ? lane - es_lane * S1 : S1 - 1;
+  const int trow = min(j, S0 - 1);  // the tap row this lane verifies
+  float* stage = reinterpret_cast<float*>(wbase + Gm::OFF_STAGE);
+#else
   // lane = (column j, channel c) of the sensor row; lanes past the row run element G-1 and skip the store
   const bool lane_ok = lane < Gm::G;
   const int jc = lane_ok ? lane : Gm::G - 1;
   const int j = jc / C;
+  const int trow = min(lane, S0 - 1);
+#endif
   const double* tab = table + (lane & (kReplicas - 1));
   // sensor_scale == 1 on this path (tma_plan): tap coordinate t of an axis = centre + (t - (S-1)/2), the offsets are
   // compile-time constants for the rows and one register per lane for its column
   constexpr double kHalf0 = (S0 - 1) / 2.0, kHalf1 = (S1 - 1) / 2.0;
   const double col_off = (double)j - kHalf1, col_j = (double)j;
-  const double row_off_lane = (double)min(lane, S0 - 1) - kHalf0, row_lane = (double)min(lane, S0 - 1);
+  const double row_off_lane = (double)trow - kHalf0, row_lane = (double)trow;
   constexpr int kWords = (IW + 31) / 32;
   static_assert(kWords <= 2 && (S0 + 1) * kWords <= 32, "visited rows x words: one lane each");
   constexpr unsigned long long wmask = (IW >= 64) ? ~0ull : ((1ull << (IW & 63)) - 1ull);
@@ -280,6 +325,118 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         mbar_wait(tbar, 0);
         table_ready = true;
       }
+#if APG_TMA_TRIPLE
+      // ---------------------------------------------------------------- phase B: warp = E environments per pass
+      // lane = (environment es of the pass, sensor column col): the weight products of a (row, column) are formed once
+      // and serve the C channels; one mbarrier stage holds the E tiles of a pass.
+      float* const out_base = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P;
+      unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
+      if (elect_one()) {
+        const int nn = min(Gm::E, cnt);
+        mbar_expect_tx_u(mbar_u + 8 * (it & 1), nn * Gm::TILE_BYTES);
+        for (int q = 0; q < nn; ++q) {
+          const int2 xy = reinterpret_cast<const int2*>(hdrs + q)[2];
+          tma_load_2d_u(tiles_u + ((it & 1) * Gm::E + q) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (it & 1));
+        }
+      }
+      for (int e0 = 0; e0 < cnt; e0 += Gm::E, ++it) {
+        const int s = it & 1;
+        const int nv = min(Gm::E, cnt - e0);
+        // stage s^1 was last read in the previous pass (program order + the __syncwarp that ends it): refill it
+        if (e0 + Gm::E < cnt && elect_one()) {
+          const int nn = min(Gm::E, cnt - e0 - Gm::E);
+          mbar_expect_tx_u(mbar_u + 8 * (s ^ 1), nn * Gm::TILE_BYTES);
+          for (int q = 0; q < nn; ++q) {
+            const int2 xy = reinterpret_cast<const int2*>(hdrs + e0 + Gm::E + q)[2];
+            tma_load_2d_u(tiles_u + ((s ^ 1) * Gm::E + q) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (s ^ 1));
+          }
+        }
+        const int es = min(es_lane, nv - 1);         // lanes past the pass recompute its last environment and store nothing
+        const bool st_ok = lane_ok && es_lane < nv;
+        const double2 cc = reinterpret_cast<const double2*>(hdrs + e0 + es)[0];  // sensor centre (x, y)
+        const int rc = reinterpret_cast<const int*>(hdrs + e0 + es)[7];          // first taps
+        const int rmin = rc & 0xffff, cmin = rc >> 16;
+        // ---- taps under the consecutive-index assumption (see the file header): the weight of tap t of an axis is
+        // coord_t - grid[k0 + t] with grid[k] = k - off; lane (es, col) owns column tap col and verifies row tap col
+        const double gy0 = int_to_double(rmin) - kOffY, gx0 = int_to_double(cmin) - kOffX;
+        const double wx = (cc.x + col_off) - (gx0 + col_j), omx = 1.0 - wx;
+        const double wyl = (cc.y + row_off_lane) - (gy0 + row_lane);
+        const bool bad = !(wx >= 0.0) || !(wx < 1.0) || (cmin + j > IW - 1) || !(wyl >= 0.0) || !(wyl < 1.0) ||
+                         (rmin + trow > IH - 1);
+        const bool slow = __any_sync(0xffffffffu, bad) || p.force_slow;
+        if (st_ok && j < S0) s_wy[es * S0 + j] = wyl;
+        if (vm && c.mode != 0) {
+          for (int w = lane; w < nv * vis_words; w += 32) vm[w] = 0u;
+        }
+        __syncwarp();
+        mbar_wait_u(mbar_u + 8 * s, (unsigned)((it >> 1) & 1));  // the tiles of this pass have landed
+        if (!slow) {
+          const unsigned char* colp = tiles + (s * Gm::E + es) * Gm::TILE_STRIDE + ((cmin * C) & 15) + j * C;
+          const double* wyp = s_wy + es * S0;
+          float* stg = stage + es * Gm::STAGE_ENV + j * C;
+          double pa[C], pb[C];
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) { pa[ch] = APG_PX(colp[ch]); pb[ch] = APG_PX(colp[C + ch]); }
+#pragma unroll
+          for (int r0 = 0; r0 < S0; r0 += Gm::STAGE_ROWS) {
+            constexpr int kR = Gm::STAGE_ROWS;
+#pragma unroll
+            for (int ii = 0; ii < kR; ++ii) {
+              const int i = r0 + ii;
+              if (i < S0) {
+                colp += Gm::BOX_W;
+                double qa[C], qb[C];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) { qa[ch] = APG_PX(colp[ch]); qb[ch] = APG_PX(colp[C + ch]); }
+                const double wy = wyp[i], omy = 1.0 - wy;
+                const double w00 = omy * omx, w01 = omy * wx, w10 = wy * omx, w11 = wy * wx;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                  double acc = pa[ch] * w00;  // the reference's leading `0.0 +` is an exact no-op for products >= +0
+                  acc = acc + pb[ch] * w01;
+                  acc = acc + qa[ch] * w10;
+                  acc = acc + qb[ch] * w11;
+                  // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
+                  if (st_ok) stg[ii * Gm::G + ch] = (float)acc;
+                  pa[ch] = qa[ch];
+                  pb[ch] = qb[ch];
+                }
+              }
+            }
+            __syncwarp();
+            // copy-out: rows r0 .. r0 + rows of every environment of the pass, 128 bits per lane and store
+            const int rows = (S0 - r0) < kR ? (S0 - r0) : kR;
+            const int n4 = rows * Gm::G / 4;
+            for (int q = 0; q < nv; ++q) {
+              const float4* src = reinterpret_cast<const float4*>(stage + q * Gm::STAGE_ENV);
+              float4* dst = reinterpret_cast<float4*>(out_base + (size_t)(e0 + q) * Gm::P + r0 * Gm::G);
+              for (int w = lane; w < n4; w += 32) dst[w] = src[w];
+            }
+            __syncwarp();
+          }
+          // visited bitmask: rows rmin .. rmin + S0 x columns cmin .. cmin + S1; lane = (row, word), one RED per lane
+          if (vm) {
+            for (int q = 0; q < nv; ++q) {
+              const int rcq = reinterpret_cast<const int*>(hdrs + e0 + q)[7];
+              const int rq = rcq & 0xffff, cq = rcq >> 16;
+              const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cq) & wmask);
+              const unsigned bits = vis_w == 0 ? (unsigned)cb : (unsigned)(cb >> 32);
+              if (vis_r <= S0 && rq + vis_r < IH && bits) atomicOr(vm + q * vis_words + (rq + vis_r) * kWords + vis_w, bits);
+            }
+          }
+        } else {
+          for (int q = 0; q < nv; ++q) {
+            const double2 ccq = reinterpret_cast<const double2*>(hdrs + e0 + q)[0];
+            const int idxq = reinterpret_cast<const int*>(hdrs + e0 + q)[6];
+            blend_env_general<S0, S1, C>(static_cast<const unsigned char*>(p.bank), p.H, p.W, p.words, p.bank_pitch, ccq.x,
+                                         ccq.y, p.half0, p.half1, p.scale, p.offy, p.offx, idxq, lane,
+                                         out_base + (size_t)(e0 + q) * Gm::P, vm ? vm + q * vis_words : nullptr);
+          }
+        }
+        if (vm) vm += nv * vis_words;
+        __syncwarp();  // every lane is done with stage s (and the row weights) before they are refilled
+      }
+#else
       // ---------------------------------------------------------------- phase B: warp = environment
       float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P + jc;
       unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
@@ -319,11 +476,6 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         mbar_wait_u(mbar_u + 8 * s, (unsigned)((it >> 1) & 1));  // this environment's tile has landed
         if (!slow) {
           const unsigned char* colp = tiles + s * Gm::TILE_STRIDE + ((cmin * C) & 15) + jc;
-#if APG_TMA_ARITH
-#define APG_PX(b) px_to_f64((unsigned char)(b))
-#else
-#define APG_PX(b) tab[(int)(b) * kReplicas]
-#endif
           double p00 = APG_PX(colp[0]), p01 = APG_PX(colp[C]);
 #pragma unroll
           for (int i = 0; i < S0; ++i) {
@@ -356,6 +508,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         if (vm) vm += vis_words;
         __syncwarp();  // every lane is done with stage s before it is refilled
       }
+#endif
     }
    }
   }
@@ -453,8 +606,11 @@ int tma_launch(const TmaPlan& plan, const ImgParams& p, const RolloutPlan& ro, c
   cfg.attrs = at;
   cfg.numAttrs = p.pdl ? 1 : 0;
   // groups of <= 32 consecutive environments, one (or a few) per persistent warp
+  // (every warp gets the same number of groups, give or take one short group: m rounds of <= 32 environments)
   const int n_range = p.n1 - p.n0;
-  int gs = (n_range + plan.warps - 1) / plan.warps;
+  const long long m = ((long long)n_range + 32ll * plan.warps - 1) / (32ll * plan.warps);
+  const long long target = m * plan.warps;
+  int gs = (int)((n_range + target - 1) / target);
   if (gs > 32) gs = 32;
   if (gs < 1) gs = 1;
   const int n_groups = (n_range + gs - 1) / gs;
