@@ -32,12 +32,21 @@ namespace {
 #ifndef APG_TMA_TRIPLE
 #define APG_TMA_TRIPLE 1  // 1: phase B blends 32 / S1 environments per pass, lane = (environment, column); 0: one per pass
 #endif
+#ifndef APG_TMA_TABLE_F32
+#define APG_TMA_TABLE_F32 APG_TMA_TRIPLE  // 1: float32 conversion table, one 4-byte bank per lane (widening to float64 is exact)
+#endif
 #ifndef APG_TMA_MINB
-#define APG_TMA_MINB (APG_TMA_TRIPLE ? 2 : 4)
+#define APG_TMA_MINB (APG_TMA_TRIPLE ? 1 : 4)
 #endif
 #ifndef APG_TMA_REPLICAS
-#define APG_TMA_REPLICAS 8
+#define APG_TMA_REPLICAS (APG_TMA_TRIPLE ? (APG_TMA_TABLE_F32 ? 32 : 16) : 8)
 #endif
+#ifndef APG_TMA_ROWSHIFT
+#define APG_TMA_ROWSHIFT APG_TMA_TRIPLE  // 1: the tile of slot q of a pass starts q rows early (own tensor map, box height + q)
+#endif
+// the box starts at the first tap column aligned down to 16 bytes: tile-mode copies of a uint8 tensor need a 16-byte
+// aligned start (an unaligned one raises an illegal instruction on sm_100a -- measured)
+#define APG_TMA_XALIGN 16
 #ifndef APG_TMA_WYSMEM
 #define APG_TMA_WYSMEM 1  // 1: row weights through shared memory (one LDS.64 per row) instead of three adds per row
 #endif
@@ -45,14 +54,24 @@ namespace {
 #define APG_TMA_ARITH 0  // 1: convert pixels arithmetically (px_to_f64) instead of the table lookup (experiment)
 #endif
 #ifndef APG_TMA_WARPS
-#define APG_TMA_WARPS (APG_TMA_TRIPLE ? 10 : 8)
+#define APG_TMA_WARPS (APG_TMA_TRIPLE ? 20 : 8)
 #endif
 #ifndef APG_TMA_STAGE_ROWS
 #define APG_TMA_STAGE_ROWS 10  // sensor rows staged in shared memory between two 128-bit copy-outs (triple mode)
 #endif
 constexpr int kWarps = APG_TMA_WARPS;
 constexpr int kReplicas = APG_TMA_REPLICAS;         // table copies: lane & (kReplicas - 1) picks its own
-constexpr int kTableBytes = 256 * kReplicas * 8;    // 16 KB at 8 copies
+#if APG_TMA_TABLE_F32
+// float32 entries (float32(u8) / 255; the widening to float64 is exact), one 4-byte bank per copy -- with 32 copies every
+// lane owns a bank and a lookup is one conflict-free wavefront whatever the pixel values are
+typedef float TableT;
+#else
+// float64 entries: with 16 copies the two half-warps of an LDS.64 are conflict-free (copy = 8-byte bank pair)
+typedef double TableT;
+#endif
+constexpr int kRowShift = APG_TMA_ROWSHIFT;
+constexpr int kXAlign = APG_TMA_XALIGN;
+constexpr int kTableBytes = 256 * kReplicas * (int)sizeof(TableT);
 
 struct __align__(16) TileHdr {  // 32 bytes per glimpse, phase H -> phase B (warp-private shared memory)
   double ccx, ccy;  // sensor centre in image-centred pixel coordinates (float64, like the reference)
@@ -66,10 +85,14 @@ template <int S0, int S1, int C>
 struct Geom {
   static constexpr int G = S1 * C;                            // floats per sensor row
   static constexpr int P = S0 * G;
-  static constexpr int BOX_W = ((S1 + 1) * C + 15 + 15) & ~15;  // footprint bytes + lead of the aligned-down start
+  static constexpr int BOX_W = ((S1 + 1) * C + (APG_TMA_XALIGN - 1) + 15) & ~15;  // footprint bytes + lead of the aligned-down start
   static constexpr int BOX_H = S0 + 1;
   static constexpr int TILE_BYTES = BOX_W * BOX_H;
-  static constexpr int TILE_STRIDE = (TILE_BYTES + 127) & ~127;  // tensor-map copies land on 128-byte boundaries
+  // tensor-map copies land on 128-byte boundaries.  Row shift (triple mode): the tile of slot q of a pass is fetched q
+  // rows early (box height BOX_H + q), so the rows the lanes of the E slots read at the same instruction sit
+  // q * BOX_W bytes = q * 12 banks apart instead of in the same banks (the 3-way LDS.U8 conflict of aligned tiles)
+  static constexpr int TILE_ROWS_MAX = BOX_H + (kRowShift ? 32 / S1 - 1 : 0);
+  static constexpr int TILE_STRIDE = (BOX_W * TILE_ROWS_MAX + 127) & ~127;
   static constexpr int TAPS = S0 + S1;
 #if APG_TMA_TRIPLE
   // lane = (environment of the pass, sensor column): E environments per pass, every lane blends the C channels of its
@@ -85,6 +108,7 @@ struct Geom {
   static constexpr int OFF_MBAR = OFF_STAGE + STAGE_BYTES;
   static constexpr int WARP_BYTES = (OFF_MBAR + 16 + 127) & ~127;
   static_assert(S0 <= S1, "lane (environment, column t) verifies tap row t");
+  static_assert(!kRowShift || E <= 3, "row shift: one tensor map per slot of a pass");
   static_assert((STAGE_ROWS * G) % 4 == 0 && (S0 * G) % 4 == 0, "128-bit copy-out");
 #else
   static constexpr int OFF_WY = 2 * TILE_STRIDE;
@@ -142,6 +166,21 @@ __device__ __forceinline__ void tma_load_2d_u(unsigned dst, const CUtensorMap* m
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// the same with an L2 cache policy (createpolicy): glimpse footprints are read once per step and the bank does not fit
+// in L2 -- evict-first keeps them from displacing the visited masks, which every step re-reads
+__device__ __forceinline__ void tma_load_2d_hint(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar,
+                                                 unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(x), "r"(y), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 // contiguous global -> shared bulk copy (bytes a multiple of 16), completion counted on `bar`
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -169,7 +208,7 @@ __device__ __forceinline__ void write_hdr(const ImgParams& p, TileHdr* out, doub
   tap_row(x0, p.offx, p.W, true, cmin, w);
   int4 a, b;
   a.x = __double2loint(ccx); a.y = __double2hiint(ccx); a.z = __double2loint(ccy); a.w = __double2hiint(ccy);
-  b.x = idx * p.H + rmin; b.y = (cmin * C) & ~15; b.z = idx; b.w = rmin | (cmin << 16);
+  b.x = idx * p.H + rmin; b.y = (cmin * C) & ~(kXAlign - 1); b.z = idx; b.w = rmin | (cmin << 16);
   reinterpret_cast<int4*>(out)[0] = a;
   reinterpret_cast<int4*>(out)[1] = b;
 }
@@ -208,18 +247,19 @@ __device__ __noinline__ void blend_env_general(const unsigned char* bank, int H,
 #if APG_TMA_ARITH
 #define APG_PX(b) px_to_f64((unsigned char)(b))
 #else
-#define APG_PX(b) tab[(int)(b) * kReplicas]
+#define APG_PX(b) ((double)tab[(int)(b) * kReplicas])
 #endif
 
 // IH x IW = the bank image size: compile-time, like the sensor geometry -- the per-environment prologue of phase B runs
 // once per glimpse on a warp with 64 registers per thread, every runtime constant it re-reads is an instruction.
 template <int S0, int S1, int C, int IH, int IW>
 __global__ void __launch_bounds__(kWarps * 32, APG_TMA_MINB)
-tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, const double* __restrict__ g_table,
-                const int group_size, const int n_groups, const RolloutPlan ro) {
+tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1,
+                const __grid_constant__ CUtensorMap tmap2, const TableT* __restrict__ g_table, const int group_size,
+                const int n_groups, const RolloutPlan ro) {
   using Gm = Geom<S0, S1, C>;
   extern __shared__ __align__(128) unsigned char smem[];
-  double* table = reinterpret_cast<double*>(smem);
+  TableT* table = reinterpret_cast<TableT*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* wbase = smem + kTableBytes + warp * Gm::WARP_BYTES;
   unsigned char* tiles = wbase;
@@ -252,6 +292,8 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   const int j = lane_ok ? lane - es_lane * S1 : S1 - 1;
   const int trow = min(j, S0 - 1);  // the tap row this lane verifies
   float* stage = reinterpret_cast<float*>(wbase + Gm::OFF_STAGE);
+  // lane q < E issues the tensor-map copy of slot q of a pass (its own map: box height + q rows under row shift)
+  const unsigned my_tile_u = smem_u32(wbase) + min(lane, Gm::E - 1) * Gm::TILE_STRIDE;
 #else
   // lane = (column j, channel c) of the sensor row; lanes past the row run element G-1 and skip the store
   const bool lane_ok = lane < Gm::G;
@@ -259,7 +301,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   const int j = jc / C;
   const int trow = min(lane, S0 - 1);
 #endif
-  const double* tab = table + (lane & (kReplicas - 1));
+  const TableT* tab = table + (lane & (kReplicas - 1));
   // sensor_scale == 1 on this path (tma_plan): tap coordinate t of an axis = centre + (t - (S-1)/2), the offsets are
   // compile-time constants for the rows and one register per lane for its column
   constexpr double kHalf0 = (S0 - 1) / 2.0, kHalf1 = (S1 - 1) / 2.0;
@@ -331,26 +373,24 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
       // and serve the C channels; one mbarrier stage holds the E tiles of a pass.
       float* const out_base = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P;
       unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
-      if (elect_one()) {
-        const int nn = min(Gm::E, cnt);
-        mbar_expect_tx_u(mbar_u + 8 * (it & 1), nn * Gm::TILE_BYTES);
-        for (int q = 0; q < nn; ++q) {
-          const int2 xy = reinterpret_cast<const int2*>(hdrs + q)[2];
-          tma_load_2d_u(tiles_u + ((it & 1) * Gm::E + q) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (it & 1));
+      // the E tiles of one pass -> stage st; slot q's box starts q rows early and is q rows taller (row shift, see Geom)
+      // (lane q issues the copy of slot q: the whole warp calls this; the transaction count is posted first, a copy that
+      //  completes before it only drives the count negative while the arrival is still pending)
+      auto issue_pass = [&](int st, int first, int nn) {
+        if (lane == 0) mbar_expect_tx_u(mbar_u + 8 * st, nn * Gm::TILE_BYTES + kRowShift * Gm::BOX_W * ((nn * (nn - 1)) >> 1));
+        if (lane < nn) {
+          const int2 xy = reinterpret_cast<const int2*>(hdrs + first + lane)[2];
+          const CUtensorMap* const my_map = (!kRowShift || lane == 0) ? &tmap : (lane == 1 ? &tmap1 : &tmap2);
+          tma_load_2d_hint(my_tile_u + st * (Gm::E * Gm::TILE_STRIDE), my_map, xy.y, xy.x - kRowShift * lane, mbar_u + 8 * st,
+                           policy_evict_first());
         }
-      }
+      };
+      issue_pass(it & 1, 0, min(Gm::E, cnt));
       for (int e0 = 0; e0 < cnt; e0 += Gm::E, ++it) {
         const int s = it & 1;
         const int nv = min(Gm::E, cnt - e0);
         // stage s^1 was last read in the previous pass (program order + the __syncwarp that ends it): refill it
-        if (e0 + Gm::E < cnt && elect_one()) {
-          const int nn = min(Gm::E, cnt - e0 - Gm::E);
-          mbar_expect_tx_u(mbar_u + 8 * (s ^ 1), nn * Gm::TILE_BYTES);
-          for (int q = 0; q < nn; ++q) {
-            const int2 xy = reinterpret_cast<const int2*>(hdrs + e0 + Gm::E + q)[2];
-            tma_load_2d_u(tiles_u + ((s ^ 1) * Gm::E + q) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (s ^ 1));
-          }
-        }
+        if (e0 + Gm::E < cnt) issue_pass(s ^ 1, e0 + Gm::E, min(Gm::E, cnt - e0 - Gm::E));
         const int es = min(es_lane, nv - 1);         // lanes past the pass recompute its last environment and store nothing
         const bool st_ok = lane_ok && es_lane < nv;
         const double2 cc = reinterpret_cast<const double2*>(hdrs + e0 + es)[0];  // sensor centre (x, y)
@@ -371,7 +411,8 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         __syncwarp();
         mbar_wait_u(mbar_u + 8 * s, (unsigned)((it >> 1) & 1));  // the tiles of this pass have landed
         if (!slow) {
-          const unsigned char* colp = tiles + (s * Gm::E + es) * Gm::TILE_STRIDE + ((cmin * C) & 15) + j * C;
+          const unsigned char* colp = tiles + (s * Gm::E + es) * Gm::TILE_STRIDE + kRowShift * es * Gm::BOX_W +
+                                      ((cmin * C) & (kXAlign - 1)) + j * C;
           const double* wyp = s_wy + es * S0;
           float* stg = stage + es * Gm::STAGE_ENV + j * C;
           double pa[C], pb[C];
@@ -404,24 +445,47 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
               }
             }
             __syncwarp();
-            // copy-out: rows r0 .. r0 + rows of every environment of the pass, 128 bits per lane and store
-            const int rows = (S0 - r0) < kR ? (S0 - r0) : kR;
-            const int n4 = rows * Gm::G / 4;
-            for (int q = 0; q < nv; ++q) {
-              const float4* src = reinterpret_cast<const float4*>(stage + q * Gm::STAGE_ENV);
-              float4* dst = reinterpret_cast<float4*>(out_base + (size_t)(e0 + q) * Gm::P + r0 * Gm::G);
-              for (int w = lane; w < n4; w += 32) dst[w] = src[w];
+            // copy-out: rows r0 .. r0 + kR of every environment of the pass, 128 bits per lane and store; streaming
+            // stores (evict-first: the observation is not read again by the engine)
+            static_assert(S0 % kR == 0, "whole stages");
+            constexpr int n4 = kR * Gm::G / 4;
+#pragma unroll
+            for (int q = 0; q < Gm::E; ++q) {
+              if (q < nv) {
+                const float4* src = reinterpret_cast<const float4*>(stage + q * Gm::STAGE_ENV);
+                float4* dst = reinterpret_cast<float4*>(out_base + (size_t)(e0 + q) * Gm::P + r0 * Gm::G);
+#pragma unroll
+                for (int w0 = 0; w0 < n4; w0 += 32)
+                  if (w0 + 32 <= n4 || w0 + lane < n4) __stcs(dst + w0 + lane, src[w0 + lane]);
+              }
             }
             __syncwarp();
           }
           // visited bitmask: rows rmin .. rmin + S0 x columns cmin .. cmin + S1; lane = (row, word), one RED per lane
           if (vm) {
-            for (int q = 0; q < nv; ++q) {
-              const int rcq = reinterpret_cast<const int*>(hdrs + e0 + q)[7];
-              const int rq = rcq & 0xffff, cq = rcq >> 16;
-              const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cq) & wmask);
-              const unsigned bits = vis_w == 0 ? (unsigned)cb : (unsigned)(cb >> 32);
-              if (vis_r <= S0 && rq + vis_r < IH && bits) atomicOr(vm + q * vis_words + (rq + vis_r) * kWords + vis_w, bits);
+            if constexpr (kWords == 2) {
+              // one 64-bit RED per (slot, row): lane = (slot of the round, row), 32 / (S0 + 1) slots per round
+              constexpr int RW = S0 + 1, SPR = 32 / RW;
+              const int qs = lane / RW, rr = lane - qs * RW;
+#pragma unroll
+              for (int qb = 0; qb < Gm::E; qb += SPR) {
+                const int q = qb + qs;
+                if (qs < SPR && q < nv) {
+                  const int rcq = reinterpret_cast<const int*>(hdrs + e0 + q)[7];
+                  const int rq = rcq & 0xffff, cq = rcq >> 16;
+                  const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cq) & wmask);
+                  if (rq + rr < IH)
+                    atomicOr(reinterpret_cast<unsigned long long*>(vm + q * vis_words) + (rq + rr), cb);
+                }
+              }
+            } else {
+              for (int q = 0; q < nv; ++q) {
+                const int rcq = reinterpret_cast<const int*>(hdrs + e0 + q)[7];
+                const int rq = rcq & 0xffff, cq = rcq >> 16;
+                const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cq) & wmask);
+                const unsigned bits = vis_w == 0 ? (unsigned)cb : (unsigned)(cb >> 32);
+                if (vis_r <= S0 && rq + vis_r < IH && bits) atomicOr(vm + q * vis_words + (rq + vis_r) * kWords + vis_w, bits);
+              }
             }
           }
         } else {
@@ -475,7 +539,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         }
         mbar_wait_u(mbar_u + 8 * s, (unsigned)((it >> 1) & 1));  // this environment's tile has landed
         if (!slow) {
-          const unsigned char* colp = tiles + s * Gm::TILE_STRIDE + ((cmin * C) & 15) + jc;
+          const unsigned char* colp = tiles + s * Gm::TILE_STRIDE + ((cmin * C) & (kXAlign - 1)) + jc;
           double p00 = APG_PX(colp[0]), p01 = APG_PX(colp[C]);
 #pragma unroll
           for (int i = 0; i < S0; ++i) {
@@ -560,9 +624,9 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
   plan.grid = sms * per_sm;
   plan.warps = plan.grid * kWarps;
   // the conversion table float64(float32(u) / 255), 16 copies interleaved (entry u of copy r at u * 16 + r)
-  std::vector<double> t((size_t)256 * kReplicas);
+  std::vector<TableT> t((size_t)256 * kReplicas);
   for (int u = 0; u < 256; ++u)
-    for (int r = 0; r < kReplicas; ++r) t[(size_t)u * kReplicas + r] = (double)((float)u / 255.0f);
+    for (int r = 0; r < kReplicas; ++r) t[(size_t)u * kReplicas + r] = (TableT)((float)u / 255.0f);
   *err = cudaMalloc(reinterpret_cast<void**>(&plan.d_table), kTableBytes);
   if (*err == cudaSuccess) *err = cudaMemcpy(plan.d_table, t.data(), kTableBytes, cudaMemcpyHostToDevice);
   if (*err != cudaSuccess) return false;
@@ -581,13 +645,17 @@ bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_i
   if (rows >= (1ll << 31)) return false;  // box coordinates are int32
   const cuuint64_t dims[2] = {(cuuint64_t)bank_pitch, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)bank_pitch};
-  const cuuint32_t box[2] = {(cuuint32_t)plan.box_w, (cuuint32_t)plan.box_h};
   const cuuint32_t estr[2] = {1, 1};
   // no L2 promotion: the copies are random 2-sector reads, anything wider would be wasted DRAM traffic
-  const CUresult r = encode_fn()(&plan.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(d_bank), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  plan.have_map = (r == CUDA_SUCCESS);
+  // (tmap[q]: the box of slot q of a pass, q rows taller -- row shift, see Geom)
+  plan.have_map = true;
+  for (int q = 0; q < 3; ++q) {
+    const cuuint32_t box[2] = {(cuuint32_t)plan.box_w, (cuuint32_t)(plan.box_h + kRowShift * q)};
+    const CUresult r = encode_fn()(&plan.tmap[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(d_bank), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    plan.have_map = plan.have_map && (r == CUDA_SUCCESS);
+  }
   return plan.have_map;
 }
 
@@ -618,8 +686,9 @@ int tma_launch(const TmaPlan& plan, const ImgParams& p, const RolloutPlan& ro, c
   cfg.gridDim = dim3((unsigned)(want < plan.grid ? want : plan.grid));
   cfg.blockDim = dim3(kWarps * 32);
   cfg.dynamicSmemBytes = plan.smem;
-  const double* table = plan.d_table;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tma_step_kernel<10, 10, 3, 64, 64>, p, plan.tmap, table, gs, n_groups, ro);
+  const TableT* table = reinterpret_cast<const TableT*>(plan.d_table);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tma_step_kernel<10, 10, 3, 64, 64>, p, plan.tmap[0], plan.tmap[1], plan.tmap[2], table,
+                                     gs, n_groups, ro);
   if (e != cudaSuccess) return -(int)e;
   return 1;
 }

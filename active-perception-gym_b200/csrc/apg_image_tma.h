@@ -13,10 +13,10 @@ struct TmaPlan {
   int spec = 0;        // 1: S0 = S1 = 10, C = 3 (the TinyImageNet shape); 0 = geometry not covered by this path
   int grid = 0;        // persistent grid of the step kernel (blocks)
   int warps = 0;       // grid * warps per block
-  double* d_table = nullptr;  // uint8 -> float64 pixel table (16 interleaved copies), device
+  void* d_table = nullptr;    // uint8 -> pixel value table (interleaved copies, float32 or float64 entries), device
   size_t smem = 0;     // dynamic shared memory of the blend kernel
   int box_w = 0, box_h = 0;
-  CUtensorMap tmap;    // the bank as a (rows, row bytes) uint8 tensor, box = one glimpse footprint
+  CUtensorMap tmap[3]; // the bank as a (rows, row bytes) uint8 tensor, box = one glimpse footprint (+ q rows, slot q)
   bool have_map = false;
 };
 

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "apg_common.h"
+#include "apg_lidar_filter.cuh"
 #include "apg_rng.h"
 
 namespace {
@@ -28,12 +29,17 @@ namespace {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kEnvsPerBlock = 32;
+constexpr int kFilterQ = 8;      // sub-cells per cell and axis of the swath-pattern table (16 bytes x B x 64 entries)
+constexpr int kQueueCap = 2048;  // rays per filter round of a block (a round covers kQueueCap / B environments)
 
 struct LidarParams {
   int N, W, H, words, B, G, T, M;
   int n0, n1;          // environments [n0, n1) of the shard are stepped by this launch (n0 a multiple of 32)
   int pad, pw, prows;  // shared-memory maps carry a free border of `pad` cells: (H + 2 pad) rows of pw words
   int static_map, static_idx, emit_cells, sparse;
+  int filter;  // 1: beams are pre-filtered (apg_lidar_filter.cuh) and only the rays that may touch a wall are walked
+  int fQ;                   // sub-cells per cell and axis of the swath-pattern table
+  const uint4* ftable;      // (B, fQ, fQ) swath patterns
   int mode;  // 0 = step with per-env autoreset, 2 = explicit reset (seed all streams), 3 = explicit reset (keep streams)
   float range;
   unsigned long long seed;  // mode 2: env i is seeded with seed + env_offset + i
@@ -472,6 +478,71 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   }
 
   // ---------------------------------------------------------------- phase 5: beams
+  if (p.filter) {
+    // Filtered form.  Round = kQueueCap / B environments: (a) every ray is tested against its precomputed swath pattern
+    // (apg_lidar_filter.cuh, ~60 instructions) -- rays that cannot touch a wall store |target - pos| at once, the others
+    // are appended to a block-wide queue (warp-aggregated); (b) the queue is walked by full warps.  In open maps half of
+    // the rays never reach the exact walk, which costs ~15x the test.
+    unsigned short* queue = reinterpret_cast<unsigned short*>(smem_maps + (size_t)kEnvsPerBlock * pmw + 1);
+    __shared__ int s_qn;
+    const int segs_per_env = (p.B + 31) >> 5;
+    const int envs_per_round = max(1, kQueueCap / (segs_per_env * 32));
+    for (int eb = 0; eb < nE; eb += envs_per_round) {
+      if (tid == 0) s_qn = 0;
+      __syncthreads();
+      const int ce = min(envs_per_round, nE - eb);
+      for (int el = warp; el < ce; el += kWarpsPerBlock) {
+        const int e = eb + el;
+        const unsigned* bits = smem_maps + (size_t)e * pmw;
+        const float posx = s_posx[e], posy = s_posy[e];
+        const size_t row = (size_t)(env0 + e) * p.B;
+        for (int b = lane; b < segs_per_env * 32; b += 32) {
+          bool hit = false;
+          if (b < p.B) {
+            hit = apg_lidar::may_touch_wall(bits, p.pw, p.pad, p.ftable, p.fQ, b, posx, posy);
+            if (!hit) {
+              const float2 dd = reinterpret_cast<const float2*>(p.dirs)[b];
+              const float tx = __fadd_rn(posx, dd.x), ty = __fadd_rn(posy, dd.y);
+              const float d = norm2f(__fsub_rn(tx, posx), __fsub_rn(ty, posy));
+              p.lidar[row + b] = fminf(fmaxf(__fdiv_rn(d, p.range), -1.0f), 1.0f);
+              if (p.cells) {
+                p.cells[(row + b) * 2] = -1;
+                p.cells[(row + b) * 2 + 1] = -1;
+                p.dists[row + b] = d;
+              }
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((el << 11) | b);
+          }
+        }
+      }
+      __syncthreads();
+      const int qn = s_qn;
+      for (int i = tid; i < qn; i += kThreads) {
+        const int q = queue[i];
+        const int e = eb + (q >> 11), b = q & 2047;
+        MapView mv{smem_maps + (size_t)e * pmw, p.pw, p.pad};
+        const float posx = s_posx[e], posy = s_posy[e];
+        const float2 dd = reinterpret_cast<const float2*>(p.dirs)[b];
+        int c0, c1;
+        const float d = scan_one(mv, posx, posy, __fadd_rn(posx, dd.x), __fadd_rn(posy, dd.y), c0, c1);
+        const size_t o = (size_t)(env0 + e) * p.B + b;
+        p.lidar[o] = fminf(fmaxf(__fdiv_rn(d, p.range), -1.0f), 1.0f);
+        if (p.cells) {
+          p.cells[o * 2] = c0;
+          p.cells[o * 2 + 1] = c1;
+          p.dists[o] = d;
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
   const int envs_per_warp = 32 / p.G;
   const int gi = lane / p.G;            // group inside the warp
   const int li = lane - gi * p.G;
@@ -525,6 +596,12 @@ struct apg_lidar_env {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[8] = {};
   float* lidar_out = nullptr;  // where this step's lidar observation goes (default: the engine's device buffer)
+  // beam pre-filter (may_touch_wall + queue): decided per map bank -- it pays when a good part of the free cells have
+  // no wall next to them (rooms), not in corridors one cell wide (mazes); APG_LIDAR_FILTER=0/1 overrides
+  int filter = 0;           // the bank is open enough for the filter to pay
+  bool filter_fits = false; // every beam fits the swath-pattern table (|dir| <= 5)
+  uint4* d_ftable = nullptr;
+  double open_fraction = 0.0;
 };
 
 namespace {
@@ -535,6 +612,8 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   LidarParams p{};
   p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
   p.pad = e->pad; p.pw = e->pw; p.prows = e->prows;
+  p.filter = (e->filter && e->filter_fits && e->d_ftable && c.beam_count <= kQueueCap) ? 1 : 0;
+  p.fQ = kFilterQ; p.ftable = e->d_ftable;
   p.n0 = e->r0; p.n1 = e->r1 < 0 ? c.num_envs : e->r1;
   p.T = c.step_limit; p.M = (int)e->n_maps; p.static_map = c.static_map; p.static_idx = c.static_map_index;
   p.emit_cells = c.emit_cells; p.sparse = c.sparse_reward ? 1 : 0; p.mode = mode; p.range = c.lidar_range; p.seed = seed; p.env_offset = c.env_offset;
@@ -549,7 +628,9 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   p.acc1 = e->d_acc1; p.acc2 = e->d_acc2; p.acc_ret = e->d_acc_ret; p.ep_avg1 = e->b.d_ep_avg1; p.ep_final1 = e->b.d_ep_final1;
   p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return; p.stats = e->d_stats;
   const int grid = apg::ceil_div(p.n1 - p.n0, kEnvsPerBlock);
-  lidar_step_kernel<<<grid, kThreads, e->smem, e->stream>>>(p);
+  // (+ one spare word behind the bitmaps and the ray queue of the filtered beam phase)
+  const size_t smem = e->smem + sizeof(unsigned) + (p.filter ? kQueueCap * sizeof(unsigned short) : 0);
+  lidar_step_kernel<<<grid, kThreads, smem, e->stream>>>(p);
   APG_CUDA(cudaGetLastError());
   apg::count_launch();
   return APG_OK;
@@ -596,6 +677,7 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
   // free border of the shared-memory bitmaps: a ray (<= lidar_range, or <= 1 for the collision rays) that starts inside
   // the map stays within range + 1 cells of it
   e->pad = (int)std::ceil((double)(cfg->lidar_range > 1.0f ? cfg->lidar_range : 1.0f)) + 2;
+  if (e->pad < apg_lidar::kColBias) e->pad = apg_lidar::kColBias;  // the 16-bit windows of the beam filter start at x - 7
   if (e->pad > 31) {
     delete e;
     return apg::fail(APG_ERR_INVALID, "lidar_range %g too large (at most 29 cells)", (double)cfg->lidar_range);
@@ -644,8 +726,8 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
   A(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev_in) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   A(apg::dev_alloc(&e->d_dirs, B * 2));
-  if (err == cudaSuccess && e->smem > 48 * 1024)
-    A(cudaFuncSetAttribute(lidar_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  if (err == cudaSuccess && e->smem + 8192 > 48 * 1024)
+    A(cudaFuncSetAttribute(lidar_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem + 8192));
   if (err != cudaSuccess) {
     apg_lidar_destroy(e);
     return apg::fail(APG_ERR_CUDA, "apg_lidar_create: allocation failed: %s", cudaGetErrorString(err));
@@ -659,6 +741,7 @@ void apg_lidar_destroy(apg_lidar_env* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   apg::dev_free(e->d_bank); apg::dev_free(e->d_dirs);
+  if (e->d_ftable) cudaFree(e->d_ftable);
   apg::dev_free(e->b.d_lidar); apg::dev_free(e->b.d_odometry); apg::dev_free(e->b.d_time_step); apg::dev_free(e->b.d_map);
   apg::dev_free(e->b.d_reward); apg::dev_free(e->b.d_base_reward); apg::dev_free(e->b.d_loss); apg::dev_free(e->b.d_target);
   apg::dev_free(e->b.d_terminated); apg::dev_free(e->b.d_truncated); apg::dev_free(e->b.d_stepped);
@@ -707,6 +790,29 @@ int apg_lidar_set_map_bank(apg_lidar_env* e, const uint32_t* h_bits, int64_t n_m
   APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_bank), count * sizeof(uint32_t)));
   APG_CUDA(cudaMemcpy(e->d_bank, clean.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice));
   e->n_maps = n_maps;
+  // share of the free cells whose eight neighbours are free as well (first <= 256 maps): the beam filter's payoff
+  {
+    const int W = e->cfg.width, H = e->cfg.height;
+    auto wall = [&](int64_t m, int x, int y) -> bool {
+      if (x < 0 || y < 0 || x >= W || y >= H) return false;
+      return (clean[((size_t)m * H + y) * e->words + (x >> 5)] >> (x & 31)) & 1u;
+    };
+    long long n_free = 0, n_open = 0;
+    for (int64_t m = 0; m < n_maps && m < 256; ++m)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+          if (wall(m, x, y)) continue;
+          n_free++;
+          bool open = true;
+          for (int dy = -1; dy <= 1 && open; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+              if (wall(m, x + dx, y + dy)) { open = false; break; }
+          n_open += open ? 1 : 0;
+        }
+    e->open_fraction = n_free ? (double)n_open / (double)n_free : 0.0;
+    e->filter = e->open_fraction >= 0.3 ? 1 : 0;
+    if (const char* ov = getenv("APG_LIDAR_FILTER")) e->filter = atoi(ov) != 0;
+  }
   return APG_OK;
 }
 
@@ -715,6 +821,21 @@ int apg_lidar_set_beams(apg_lidar_env* e, const float* h_dirs) {
   APG_CUDA(cudaSetDevice(e->cfg.device));
   APG_CUDA(cudaMemcpy(e->d_dirs, h_dirs, (size_t)e->cfg.beam_count * 2 * sizeof(float), cudaMemcpyHostToDevice));
   e->have_beams = true;
+  // swath patterns of the beam filter (apg_lidar_filter.cuh): one 16-byte entry per (beam, sub-cell of the start cell)
+  const int B = e->cfg.beam_count;
+  e->filter_fits = true;
+  for (int b = 0; b < B; ++b) e->filter_fits = e->filter_fits && apg_lidar::beam_pattern_fits(h_dirs[2 * b], h_dirs[2 * b + 1]);
+  if (e->filter_fits) {
+    static_assert(sizeof(apg_lidar::BeamPattern) == sizeof(uint4), "one uint4 per entry");
+    std::vector<apg_lidar::BeamPattern> t((size_t)B * kFilterQ * kFilterQ);
+    for (int b = 0; b < B; ++b)
+      for (int qy = 0; qy < kFilterQ; ++qy)
+        for (int qx = 0; qx < kFilterQ; ++qx)
+          t[((size_t)b * kFilterQ + qy) * kFilterQ + qx] =
+              apg_lidar::make_beam_pattern((double)h_dirs[2 * b], (double)h_dirs[2 * b + 1], qx, qy, kFilterQ);
+    if (!e->d_ftable) APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_ftable), t.size() * sizeof(uint4)));
+    APG_CUDA(cudaMemcpy(e->d_ftable, t.data(), t.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  }
   return APG_OK;
 }
 

@@ -86,6 +86,19 @@ def _beam_mask(B, reset_rows):
 @pytest.mark.parametrize("bank,B,N,steps", [("rooms32", 64, 2048, 230), ("maze21", 8, 1024, 120), ("maze63", 256, 256, 110),
                                             ("maze63", 256, 2304, 104)])
 def test_engine_matches_oracle_seeded(bank, B, N, steps):
+    _seeded_vs_oracle(bank, B, N, steps)
+
+
+@pytest.mark.parametrize("bank,B,N,steps,beam_filter", [("rooms32", 64, 1024, 120, "0"), ("rooms32", 64, 1024, 120, "1"),
+                                                        ("maze63", 256, 256, 60, "1"), ("maze21", 12, 512, 60, "1")])
+def test_beam_filter_on_and_off(bank, B, N, steps, beam_filter, monkeypatch):
+    """The beam pre-filter (csrc/apg_lidar_filter.cuh: rays that cannot touch a wall skip the exact walk) is chosen per
+    map bank; forced on and off here, both must reproduce the oracle bit for bit."""
+    monkeypatch.setenv("APG_LIDAR_FILTER", beam_filter)
+    _seeded_vs_oracle(bank, B, N, steps)
+
+
+def _seeded_vs_oracle(bank, B, N, steps):
     """Larger seeded runs (thousands of envs, >2 episodes incl. the device-side RNG resets) vs the C oracle; the last
     case is the LIDARLocMaze benchmark shape (63x63 mazes, 256 beams) at N = 2304 across one autoreset.  GEOS unpinned:
     see MASK_GEOS_RAYS above."""
