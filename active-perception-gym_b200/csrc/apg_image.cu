@@ -669,12 +669,24 @@ struct apg_image_env {
     uint8_t* d_inv = nullptr;
     unsigned char* h_pin = nullptr;  // pinned staging: idx | pos | target | inv
     cudaEvent_t copied = nullptr;
+    cudaEvent_t ready = nullptr;     // device draws run on the engine's own rng stream: recorded behind the draw
+    bool ready_pending = false;      // ... and waited for (on the step stream) by the first launch that reads the slot
     bool drawn = false;              // drawn from the reset streams (not queued by the caller)
     int snap = 0;                    // device mode: d_streams entry the payload was drawn from
     apg::Pcg64 h_snap[3];            // host mode: the stream states before the payload
   };
   std::vector<Slot> ring;
   int ring_head = 0, ring_count = 0;
+  // Device payload draws are queued on `rng_stream`, concurrently with the step kernels: a draw only depends on the
+  // stream states and on the slot it overwrites having been consumed (ev_step: recorded behind every launch that reads
+  // slots).  ev_topup[]: the draws queued behind window W are joined into the step stream at the end of window W + 1 --
+  // they overlap a whole window, and every window still pays for (waits for) one window's worth of draws.
+  cudaStream_t rng_stream = nullptr;
+  cudaEvent_t ev_step = nullptr;
+  bool step_dirty = false;
+  cudaEvent_t ev_topup[2] = {nullptr, nullptr};
+  bool topup_valid[2] = {false, false};
+  int topup_phase = 0;
   // staging for *_host
   float* d_in_action = nullptr;
   float* d_in_pred = nullptr;
@@ -848,6 +860,32 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   return APG_OK;
 }
 
+// Host-side join of the rng stream (rare paths: explicit reset, stream get/set, bank change, destroy).
+int join_rng(apg_image_env* e) {
+  if (e->rng_stream) APG_CUDA(cudaStreamSynchronize(e->rng_stream));
+  for (auto& s : e->ring) s.ready_pending = false;
+  e->topup_valid[0] = e->topup_valid[1] = false;
+  return APG_OK;
+}
+
+// the step stream waits for the draw of a slot it is about to read
+int wait_slot(apg_image_env* e, apg_image_env::Slot& s) {
+  if (s.ready_pending) {
+    APG_CUDA(cudaStreamWaitEvent(e->stream, s.ready, 0));
+    s.ready_pending = false;
+  }
+  return APG_OK;
+}
+
+// recorded behind every launch that reads payload slots: draws that overwrite them wait for it
+int mark_step(apg_image_env* e) {
+  if (e->device_rng) {
+    APG_CUDA(cudaEventRecord(e->ev_step, e->stream));
+    e->step_dirty = true;
+  }
+  return APG_OK;
+}
+
 // ---- the reference's three reset-path Generators ---------------------------------------------------------------------
 // Device mode (the normal case): the states live in d_streams, (ring + 1) x 3 entries -- entry `cur` holds the states
 // after every payload drawn so far, and the entry a payload was drawn FROM stays intact until that payload has been
@@ -856,6 +894,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
 // synchronises or loads a kernel for the first time.
 int configure_rng(apg_image_env* e) {
   e->device_rng = false;
+  if (int rc = join_rng(e)) return rc;
   if (!e->have_streams || !e->d_bank) return APG_OK;
   if (e->host_rng || !apg::payload_device_ok((unsigned long long)e->n_items, e->global_n)) return APG_OK;
   const size_t n_states = 3 * (e->ring.size() + 1);
@@ -875,6 +914,7 @@ int configure_rng(apg_image_env* e) {
 // host copies of the current states (device mode: fetched from entry `cur`; synchronises the stream)
 int streams_to_host(apg_image_env* e) {
   if (!e->device_rng) return APG_OK;
+  if (int rc = join_rng(e)) return rc;
   apg::Pcg64 h[3];
   APG_CUDA(cudaMemcpyAsync(h, e->d_streams + 3 * e->cur, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
   APG_CUDA(cudaStreamSynchronize(e->stream));
@@ -920,9 +960,15 @@ int generate_payload(apg_image_env* e) {
     a.rej = e->d_rej + (size_t)e->pp * (apg::kPayloadSlack + 1);
     a.rej_next = e->d_rej + (size_t)(e->pp ^ 1) * (apg::kPayloadSlack + 1);
     e->pp ^= 1;
-    const int n = apg::launch_device_payload(a, e->stream);
+    if (e->step_dirty) {  // the slot (and the stream-state entry) may still be read by a launch on the step stream
+      APG_CUDA(cudaStreamWaitEvent(e->rng_stream, e->ev_step, 0));
+      e->step_dirty = false;
+    }
+    const int n = apg::launch_device_payload(a, e->rng_stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "payload kernels: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
+    APG_CUDA(cudaEventRecord(s.ready, e->rng_stream));
+    s.ready_pending = true;
     s.drawn = true; s.snap = e->cur;
     e->cur = next;
     e->ring_count += 1;
@@ -991,7 +1037,8 @@ int rollout_window(apg_image_env* e, const float* d_actions, const float* d_pred
       if (rc != APG_OK) return rc;
     }
     for (int i = 0; i < resets; ++i) {
-      const apg_image_env::Slot& s = e->ring[(e->ring_head + i) % ring];
+      apg_image_env::Slot& s = e->ring[(e->ring_head + i) % ring];
+      if (int rc = wait_slot(e, s)) return rc;
       ro.slot_idx[i] = reinterpret_cast<const long long*>(s.d_idx); ro.slot_pos[i] = s.d_pos;
       ro.slot_target[i] = s.d_target; ro.slot_inv[i] = s.d_inv;
     }
@@ -1002,6 +1049,8 @@ int rollout_window(apg_image_env* e, const float* d_actions, const float* d_pred
     const int n = e->small.spec ? apg_img::small_launch(e->small, p, ro, e->stream) : apg_img::tma_launch(e->tma, p, ro, e->stream);
     if (n < 0) return apg::fail(APG_ERR_CUDA, "image rollout kernel: %s", cudaGetErrorString((cudaError_t)(-n)));
     apg::count_launch(n);
+    if (resets > 0)
+      if (int rc = mark_step(e)) return rc;
     if (!e->hold) {
       int drawn = 0;
       for (int i = 0; i < resets; ++i) drawn += e->ring[(e->ring_head + i) % ring].drawn ? 1 : 0;
@@ -1020,6 +1069,15 @@ int rollout_window(apg_image_env* e, const float* d_actions, const float* d_pred
     }
     done += m;
   }
+  // join: the draws queued behind the PREVIOUS window have had this whole window to run next to; the step stream
+  // waits for them here, so the device time of a window includes one window's worth of draws (overlapped, not skipped)
+  if (e->device_rng) {
+    const int ph = e->topup_phase;
+    APG_CUDA(cudaEventRecord(e->ev_topup[ph], e->rng_stream));
+    e->topup_valid[ph] = true;
+    if (e->topup_valid[ph ^ 1]) APG_CUDA(cudaStreamWaitEvent(e->stream, e->ev_topup[ph ^ 1], 0));
+    e->topup_phase = ph ^ 1;
+  }
   return APG_OK;
 }
 
@@ -1033,7 +1091,11 @@ int step_once(apg_image_env* e, const float* d_action, const float* d_pred, floa
     APG_CHECK(e->ring_count > 0, APG_ERR_NEED_PAYLOAD,
               "autoreset step is due but no reset payload is queued (apg_image_queue_reset_payload)");
     apg_image_env::Slot& s = e->ring[e->ring_head];
-    int rc = launch(e, 1, d_action, d_pred, &s, reward2, done2);
+    int rc = wait_slot(e, s);
+    if (rc != APG_OK) return rc;
+    rc = launch(e, 1, d_action, d_pred, &s, reward2, done2);
+    if (rc != APG_OK) return rc;
+    rc = mark_step(e);
     if (rc != APG_OK) return rc;
     if (!e->hold) {
       e->ring_head = (e->ring_head + 1) % (int)e->ring.size();
@@ -1189,6 +1251,9 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   }
   A(apg::dev_alloc(&e->d_in_action, N * 2));
   A(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&e->rng_stream, cudaStreamNonBlocking));
+  A(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+  for (auto& ev : e->ev_topup) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : e->ev_in) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   A(apg::dev_alloc(&e->d_in_pred, N * e->pred_width));
   int depth = cfg->payload_ring <= 0 ? APG_PAYLOAD_RING_DEFAULT : cfg->payload_ring;
@@ -1201,6 +1266,7 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
     A(apg::dev_alloc(&s.d_inv, N));
     A(cudaMallocHost(reinterpret_cast<void**>(&s.h_pin), slot_bytes(e)));
     A(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
   }
   if (err == cudaSuccess && e->smem > 48 * 1024) {
     A(cudaFuncSetAttribute(image_step_kernel<unsigned char, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -1254,6 +1320,9 @@ void apg_image_destroy(apg_image_env* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  if (e->rng_stream) { cudaStreamSynchronize(e->rng_stream); cudaStreamDestroy(e->rng_stream); }
+  if (e->ev_step) cudaEventDestroy(e->ev_step);
+  for (auto& ev : e->ev_topup) if (ev) cudaEventDestroy(ev);
   if (e->d_streams) cudaFree(e->d_streams);
   if (e->d_words) cudaFree(e->d_words);
   if (e->d_rej) cudaFree(e->d_rej);
@@ -1279,6 +1348,7 @@ void apg_image_destroy(apg_image_env* e) {
     apg::dev_free(s.d_idx); apg::dev_free(s.d_pos); apg::dev_free(s.d_target); apg::dev_free(s.d_inv);
     if (s.h_pin) cudaFreeHost(s.h_pin);
     if (s.copied) cudaEventDestroy(s.copied);
+    if (s.ready) cudaEventDestroy(s.ready);
   }
   delete e;
 }
@@ -1287,6 +1357,7 @@ int apg_image_set_stream(apg_image_env* e, void* cuda_stream) {
   APG_CHECK(e, APG_ERR_INVALID, "null env");
   APG_CUDA(cudaSetDevice(e->cfg.device));
   APG_CUDA(cudaStreamSynchronize(e->stream));
+  if (int rc = join_rng(e)) return rc;
   e->stream = static_cast<cudaStream_t>(cuda_stream);
   return APG_OK;
 }
@@ -1330,6 +1401,7 @@ int apg_image_reset(apg_image_env* e, const int64_t* h_idx, const double* h_pos,
   APG_CHECK(e->d_bank, APG_ERR_STATE, "apg_image_reset before apg_image_set_bank");
   APG_CUDA(cudaSetDevice(e->cfg.device));
   // an explicit reset drops queued autoreset payloads (the reference re-seeds its streams on reset(seed))
+  if (int rc = join_rng(e)) return rc;
   e->ring_head = 0;
   e->ring_count = 0;
   apg_image_env::Slot& s = e->ring[0];

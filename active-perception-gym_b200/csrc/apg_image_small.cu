@@ -129,12 +129,15 @@ __host__ __device__ inline SmallSmem small_smem(int S0, int P, int K, int H, int
   return m;
 }
 
-template <int S0, int S1, int PITCH>  // PITCH = bytes per bank row (a multiple of 16)
+// PITCH = bytes per bank row (a multiple of 16); KC = number of classes when known at compile time (the loops over the
+// logits unroll and their exp chains overlap), 0 = p.K
+template <int S0, int S1, int PITCH, int KC>
 __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const ImgParams p, const SmallRollout ro) {
   constexpr int P = S0 * S1;
+  const int K = KC ? KC : p.K;
   constexpr int kWarpsPerBlock = kSmallThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmallSmem sm = small_smem(S0, P, p.K, p.H, PITCH);
+  const SmallSmem sm = small_smem(S0, P, K, p.H, PITCH);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n0 + blockIdx.x * kSmallThreads + tid;  // [n0, n1): the environments this launch steps (n0 % 32 == 0)
   const bool live = n < p.n1;
@@ -178,9 +181,9 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     }
   }
   // logits of the first step on their way (stage 0)
-  const unsigned char* pred_w = reinterpret_cast<const unsigned char*>(p.pred + (size_t)warp_env0 * p.K);
-  const size_t pred_step = (size_t)p.N * p.K * 4;
-  if (ro.first_mode != 2 && n_env > 0) warp_copy_async(reinterpret_cast<unsigned char*>(s_lg), pred_w, n_env * p.K * 4, lane);
+  const unsigned char* pred_w = reinterpret_cast<const unsigned char*>(p.pred + (size_t)warp_env0 * K);
+  const size_t pred_step = (size_t)p.N * K * 4;
+  if (ro.first_mode != 2 && n_env > 0) warp_copy_async(reinterpret_cast<unsigned char*>(s_lg), pred_w, n_env * K * 4, lane);
   __pipeline_commit();
   __syncwarp();
   double st1 = 0.0, st2 = 0.0, st3 = 0.0, st4 = 0.0, st5 = 0.0, st0 = 0.0;  // this thread's share of the shard statistics
@@ -188,6 +191,10 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
   int t = ro.t0;
   bool need_reset = ro.need_reset0 != 0;
   const float2* act = reinterpret_cast<const float2*>(p.action) + n;
+  // the action of step k + 1 is requested during step k (registers): its latency is off the step's critical path
+  float2 act_next = make_float2(0.0f, 0.0f);
+  const bool have_act = live && p.action != nullptr;  // (an explicit reset launches without actions)
+  if (have_act && ro.n_steps > 0) act_next = __ldcs(act);
   float* rew2 = p.reward2 ? p.reward2 + n : nullptr;
   unsigned char* don2 = p.done2 ? p.done2 + n : nullptr;
   float* gout = p.glimpse + (size_t)warp_env0 * P;
@@ -198,13 +205,14 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     const int t_after = (mode == 0) ? t + 1 : 0;
     const bool terminated = (mode == 0) && (t_after >= p.T);
     const float time_obs = (float)(((double)t_after / (double)p.T) * 2.0 - 1.0);
-    const float* x = s_lg + (k & 1) * lg_words + lane * p.K;
+    const float* x = s_lg + (k & 1) * lg_words + lane * K;
 
     // ---- inputs of the step
     float a0 = 0.0f, a1 = 0.0f;
+    const float2 aa = act_next;
+    if (have_act && k + 1 < ro.n_steps) act_next = __ldcs(act + (size_t)(k + 1) * p.N);
     if (live) {
       if (mode == 0) {
-        const float2 aa = act[(size_t)k * p.N];
         a0 = aa.x; a1 = aa.y;
       } else {
         const int slot = (mode == 2) ? 0 : ro.reset_slot[k];
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     // footprints so that waiting for the footprints does not wait for them
     if (k + 1 < ro.n_steps && n_env > 0)
       warp_copy_async(reinterpret_cast<unsigned char*>(s_lg + ((k + 1) & 1) * lg_words), pred_w + (size_t)(k + 1) * pred_step,
-                      n_env * p.K * 4, lane);
+                      n_env * K * 4, lane);
     __pipeline_commit();
 
     // ---- label, cross-entropy, reward, flags (image_classification.py:113-127, loss_fn.py:100-110,212-220); the
@@ -287,14 +295,15 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     if (live) {
       if (mode != 0) {
         label = p.bank_labels[idx];
-        if (p.invert && inv) label = p.K - label - 1;
+        if (p.invert && inv) label = K - label - 1;
       }
       if (p.invert) p.inverted_label[n] = (mode == 0) ? 2 : (int)inv;
       p.target_label[n] = label;
       if (mode != 2) {
         float mx = x[0];
         bool has_nan = isnan(mx);
-        for (int c = 1; c < p.K; ++c) {
+#pragma unroll
+        for (int c = 1; c < K; ++c) {
           const float v = x[c];
           has_nan |= isnan(v);
           mx = fmaxf(mx, v);
@@ -302,7 +311,8 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
         if (has_nan) err |= APG_FLAG_NAN_PRED;
         if (!isfinite(mx)) mx = 0.0f;
         float s = 0.0f;
-        for (int c = 0; c < p.K; ++c) s = __fadd_rn(s, expf(__fsub_rn(x[c], mx)));
+#pragma unroll
+        for (int c = 0; c < K; ++c) s = __fadd_rn(s, expf(__fsub_rn(x[c], mx)));
         const float tl = __fsub_rn(x[label], mx);
         const float ce = -__fsub_rn(tl, logf(s));  // -log_softmax(x)[label], float32 like scipy
         const float pq = __fdiv_rn(expf(tl), s);   // softmax(x)[label], overlay colour only
@@ -460,7 +470,9 @@ bool small_plan(SmallPlan& plan, const apg_image_cfg& cfg, int words) {
 cudaError_t small_preload(const SmallPlan& plan) {
   if (!plan.spec) return cudaSuccess;
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32>);
+  cudaError_t e = cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 10>);
+  if (e != cudaSuccess) return e;
+  return cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 0>);
 }
 
 int small_launch(const SmallPlan& plan, const ImgParams& p, const SmallRollout& ro, cudaStream_t stream) {
@@ -474,7 +486,8 @@ int small_launch(const SmallPlan& plan, const ImgParams& p, const SmallRollout& 
   cfg.gridDim = dim3((unsigned)((p.n1 - p.n0 + kSmallThreads - 1) / kSmallThreads));
   cfg.blockDim = dim3(kSmallThreads);
   cfg.dynamicSmemBytes = plan.smem;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32>, p, ro);
+  cudaError_t e = (p.K == 10) ? cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 10>, p, ro)
+                              : cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 0>, p, ro);
   if (e != cudaSuccess) return -(int)e;
   return 1;
 }

@@ -1,26 +1,32 @@
-// Image step for LARGE glimpses (one warp per environment) on uint8 banks at sensor_scale == 1 -- the
-// TinyImageNetLoc shape (64x64x3 bank, 10x10x3 sensor) of BASELINE.json.  Reference path:
+// Image step for LARGE glimpses on uint8 banks at sensor_scale == 1 -- the TinyImageNetLoc shape (64x64x3 bank,
+// 10x10x3 sensor) of BASELINE.json.  Reference path:
 //   ImagePerceptionModule.step / get_glimpse      ap_gym/envs/image/image_perception_module.py:191-217,294-331
 //   ImageLocalizationVectorEnv._step              ap_gym/envs/image_localization.py:151-181
 //
-// ONE launch per vector step, PERSISTENT warps.  A warp owns a group of <= 32 consecutive environments:
+// ONE launch per rollout window, PERSISTENT warps (one block of 20 warps per SM).  A warp owns a group of <= 32
+// consecutive environments and takes it through every step of the window:
 //   phase H  lane = environment: the two scalar chains of apg_image_dev.cuh (move / loss / reward / flags / statistics)
 //            and a 32-byte tile header per environment in the warp's shared memory (sensor centre in pixels, first tap
 //            row / column, tensor-map box coordinates);
-//   phase B  warp = environment, lane = (sensor column, channel): the warp walks its environments with a two-stage ring
-//            of shared-memory tiles.  One elected lane issues ONE tensor-map copy (cp.async.bulk.tensor.2d, SASS
-//            UTMALDG) per glimpse -- box = (S0+1) rows x 48 bytes of the bank image, start aligned down to 16 bytes --
-//            for environment k+1 while the warp blends environment k; completion is an mbarrier transaction count.
-//            Nothing in the loop synchronises more than one warp.
+//   phase B  the warp blends E = 32 / S1 = 3 environments per pass, lane = (environment of the pass, sensor column): the
+//            four weight products of a (row, column) are formed once and serve the C channels.  A two-stage ring of
+//            shared-memory tiles per warp: lane q < E issues ONE tensor-map copy (cp.async.bulk.tensor.2d, SASS UTMALDG,
+//            L2 evict-first) for the glimpse of slot q of the NEXT pass -- box = (S0 + 1 + q) rows x 48 bytes of the bank
+//            image, start aligned down to 16 bytes -- while the warp blends the current pass; completion is an
+//            mbarrier transaction count.  Nothing in the loop synchronises more than one warp.
+//            Row shift: slot q's box starts q rows early (its own tensor map), so the tile rows the three slots read at
+//            the same instruction lie 12 banks apart instead of in the same banks.
+//            The float32 rows of a pass are parked in a shared-memory stage and leave as contiguous 128-bit streaming
+//            stores; the visited mask takes one 64-bit RED per (slot, row).
 // Blend: the reference's 4-term float64 sum in scipy's order (bit-exact pixels).  The exact uint8 -> float64 pixel
-// value float64(float32(u8) / 255) comes from a 256-entry table, replicated 8x (lane & 7 picks its copy: at most two
-// lanes of a half-warp share one) -- one LDS.64 instead of the five-instruction conversion; the 16 KB table is computed once on
-// the host and lands in every block's shared memory with one bulk copy (cp.async.bulk, SASS UBLKCP).  Taps: the first
-// tap of each axis is scipy's find_indices in full (phase H), the others are assumed consecutive and VERIFIED -- their
-// weight w = coord - grid[k0 + t], computed exactly like the reference's, must lie in [0, 1), which is precisely the
+// value float64(float32(u8) / 255) comes from a 256-entry float32 table (the widening is exact), replicated 32x -- lane l
+// reads copy l, i.e. bank l: one conflict-free wavefront per lookup; the 32 KB table is computed once on the host and
+// lands in every block's shared memory with one bulk copy (cp.async.bulk, SASS UBLKCP).  Taps: the first tap of each
+// axis is scipy's find_indices in full (phase H), the others are assumed consecutive and VERIFIED -- their weight
+// w = coord - grid[k0 + t], computed exactly like the reference's, must lie in [0, 1), which is precisely the
 // condition under which find_indices returns that index.  With consecutive tap rows every tile row is fetched and
-// converted once.  Environments that break the pattern (a float64 rounding accident at a grid line, probability
-// ~1e-15 per tap) take a general per-output path from global memory.
+// converted once per lane.  Environments that break the pattern (a float64 rounding accident at a grid line,
+// probability ~1e-15 per tap) take a general per-output path from global memory.
 #include "apg_image_tma.h"
 
 #include <cstdint>
@@ -29,44 +35,39 @@
 namespace apg_img {
 namespace {
 
-#ifndef APG_TMA_TRIPLE
-#define APG_TMA_TRIPLE 1  // 1: phase B blends 32 / S1 environments per pass, lane = (environment, column); 0: one per pass
-#endif
+// A/B switches (tools/build_variants.py); the defaults are the measured best (profiles/README.md, round 2)
 #ifndef APG_TMA_TABLE_F32
-#define APG_TMA_TABLE_F32 APG_TMA_TRIPLE  // 1: float32 conversion table, one 4-byte bank per lane (widening to float64 is exact)
-#endif
-#ifndef APG_TMA_MINB
-#define APG_TMA_MINB (APG_TMA_TRIPLE ? 1 : 4)
+#define APG_TMA_TABLE_F32 1  // 1: float32 table, one 4-byte bank per lane; 0: float64 table, 16 copies (equal speed)
 #endif
 #ifndef APG_TMA_REPLICAS
-#define APG_TMA_REPLICAS (APG_TMA_TRIPLE ? (APG_TMA_TABLE_F32 ? 32 : 16) : 8)
+#define APG_TMA_REPLICAS (APG_TMA_TABLE_F32 ? 32 : 16)
 #endif
 #ifndef APG_TMA_ROWSHIFT
-#define APG_TMA_ROWSHIFT APG_TMA_TRIPLE  // 1: the tile of slot q of a pass starts q rows early (own tensor map, box height + q)
+#define APG_TMA_ROWSHIFT 1  // 1: the tile of slot q of a pass starts q rows early (own tensor map, box height + q): -7 %
 #endif
 // the box starts at the first tap column aligned down to 16 bytes: tile-mode copies of a uint8 tensor need a 16-byte
 // aligned start (an unaligned one raises an illegal instruction on sm_100a -- measured)
 #define APG_TMA_XALIGN 16
-#ifndef APG_TMA_WYSMEM
-#define APG_TMA_WYSMEM 1  // 1: row weights through shared memory (one LDS.64 per row) instead of three adds per row
-#endif
 #ifndef APG_TMA_ARITH
 #define APG_TMA_ARITH 0  // 1: convert pixels arithmetically (px_to_f64) instead of the table lookup (experiment)
 #endif
 #ifndef APG_TMA_WARPS
-#define APG_TMA_WARPS (APG_TMA_TRIPLE ? 20 : 8)
+#define APG_TMA_WARPS 20  // warps per block, one block per SM (96 registers per thread)
+#endif
+#ifndef APG_TMA_MINB
+#define APG_TMA_MINB 1
+#endif
+#ifndef APG_TMA_BULK_OUT
+#define APG_TMA_BULK_OUT 1  // 1: a staged glimpse leaves with ONE bulk store (cp.async.bulk shared -> global), 0: LDS.128 + STG.128
 #endif
 #ifndef APG_TMA_STAGE_ROWS
-#define APG_TMA_STAGE_ROWS 10  // sensor rows staged in shared memory between two 128-bit copy-outs (triple mode)
+#define APG_TMA_STAGE_ROWS 10  // sensor rows staged in shared memory between two 128-bit copy-outs
 #endif
 constexpr int kWarps = APG_TMA_WARPS;
 constexpr int kReplicas = APG_TMA_REPLICAS;         // table copies: lane & (kReplicas - 1) picks its own
 #if APG_TMA_TABLE_F32
-// float32 entries (float32(u8) / 255; the widening to float64 is exact), one 4-byte bank per copy -- with 32 copies every
-// lane owns a bank and a lookup is one conflict-free wavefront whatever the pixel values are
 typedef float TableT;
 #else
-// float64 entries: with 16 copies the two half-warps of an LDS.64 are conflict-free (copy = 8-byte bank pair)
 typedef double TableT;
 #endif
 constexpr int kRowShift = APG_TMA_ROWSHIFT;
@@ -94,7 +95,6 @@ struct Geom {
   static constexpr int TILE_ROWS_MAX = BOX_H + (kRowShift ? 32 / S1 - 1 : 0);
   static constexpr int TILE_STRIDE = (BOX_W * TILE_ROWS_MAX + 127) & ~127;
   static constexpr int TAPS = S0 + S1;
-#if APG_TMA_TRIPLE
   // lane = (environment of the pass, sensor column): E environments per pass, every lane blends the C channels of its
   // column; the float32 rows go through a shared-memory stage so that the global stores are 128-bit and contiguous
   static constexpr int E = 32 / S1;
@@ -110,12 +110,6 @@ struct Geom {
   static_assert(S0 <= S1, "lane (environment, column t) verifies tap row t");
   static_assert(!kRowShift || E <= 3, "row shift: one tensor map per slot of a pass");
   static_assert((STAGE_ROWS * G) % 4 == 0 && (S0 * G) % 4 == 0, "128-bit copy-out");
-#else
-  static constexpr int OFF_WY = 2 * TILE_STRIDE;
-  static constexpr int OFF_HDR = OFF_WY + TAPS * 16;
-  static constexpr int OFF_MBAR = OFF_HDR + 32 * 32;
-  static constexpr int WARP_BYTES = (2 * TILE_STRIDE + TAPS * 16 + 32 * 32 + 16 + 127) & ~127;
-#endif
   static constexpr int SMEM = kTableBytes + kWarps * WARP_BYTES + 128;
   static_assert(G <= 32 && TAPS <= 32, "one lane per (column, channel) and one lane per tap");
 };
@@ -152,21 +146,8 @@ __device__ __forceinline__ void mbar_wait_u(unsigned bar, unsigned parity) {
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-// exactly one lane of the (converged) warp gets true
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-// one glimpse footprint: box (BOX_W bytes x BOX_H rows) of the bank tensor at (x, y) -> shared memory, completion
-// counted on `bar` (shared-window addresses)
-__device__ __forceinline__ void tma_load_2d_u(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(x), "r"(y)
-      : "memory");
-}
-// the same with an L2 cache policy (createpolicy): glimpse footprints are read once per step and the bank does not fit
+// one glimpse footprint: box (BOX_W bytes x box rows) of the bank tensor at (x, y) -> shared memory, completion counted on
+// `bar` (shared-window addresses), with an L2 cache policy (createpolicy): glimpse footprints are read once per step and the bank does not fit
 // in L2 -- evict-first keeps them from displacing the visited masks, which every step re-reads
 __device__ __forceinline__ void tma_load_2d_hint(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar,
                                                  unsigned long long policy) {
@@ -181,6 +162,15 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// contiguous shared -> global bulk store (bytes a multiple of 16, both sides 16-byte aligned) in the thread's bulk group
+__device__ __forceinline__ void bulk_store_hint(void* gdst, unsigned ssrc, unsigned bytes, unsigned long long policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(ssrc),
+               "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the bulk stores of this thread have finished READING shared memory (their source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // contiguous global -> shared bulk copy (bytes a multiple of 16), completion counted on `bar`
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -285,7 +275,6 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   }
   grid_dependency_wait(p.pdl);
 
-#if APG_TMA_TRIPLE
   // lane = (environment es of the pass, column j); lanes past E * S1 shadow the last column of the last environment
   const bool lane_ok = lane < Gm::E * S1;
   const int es_lane = lane_ok ? lane / S1 : Gm::E - 1;
@@ -294,13 +283,6 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   float* stage = reinterpret_cast<float*>(wbase + Gm::OFF_STAGE);
   // lane q < E issues the tensor-map copy of slot q of a pass (its own map: box height + q rows under row shift)
   const unsigned my_tile_u = smem_u32(wbase) + min(lane, Gm::E - 1) * Gm::TILE_STRIDE;
-#else
-  // lane = (column j, channel c) of the sensor row; lanes past the row run element G-1 and skip the store
-  const bool lane_ok = lane < Gm::G;
-  const int jc = lane_ok ? lane : Gm::G - 1;
-  const int j = jc / C;
-  const int trow = min(lane, S0 - 1);
-#endif
   const TableT* tab = table + (lane & (kReplicas - 1));
   // sensor_scale == 1 on this path (tma_plan): tap coordinate t of an axis = centre + (t - (S-1)/2), the offsets are
   // compile-time constants for the rows and one register per lane for its column
@@ -367,7 +349,6 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         mbar_wait(tbar, 0);
         table_ready = true;
       }
-#if APG_TMA_TRIPLE
       // ---------------------------------------------------------------- phase B: warp = E environments per pass
       // lane = (environment es of the pass, sensor column col): the weight products of a (row, column) are formed once
       // and serve the C channels; one mbarrier stage holds the E tiles of a pass.
@@ -418,6 +399,11 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
           double pa[C], pb[C];
 #pragma unroll
           for (int ch = 0; ch < C; ++ch) { pa[ch] = APG_PX(colp[ch]); pb[ch] = APG_PX(colp[C + ch]); }
+#if APG_TMA_BULK_OUT
+          // the bulk stores of the previous pass have read the stage (they had its whole epilogue and this prologue)
+          if (lane < Gm::E) bulk_wait_read();
+          __syncwarp();
+#endif
 #pragma unroll
           for (int r0 = 0; r0 < S0; r0 += Gm::STAGE_ROWS) {
             constexpr int kR = Gm::STAGE_ROWS;
@@ -444,6 +430,19 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
                 }
               }
             }
+#if APG_TMA_BULK_OUT
+            // copy-out: lane q hands the staged glimpse of slot q to the bulk-copy engine (one contiguous 16-byte
+            // aligned run of P floats, L2 evict-first: the observation is not read again by the engine) -- no LDS / STG
+            // wavefronts on the warp's load-store path.  The generic-proxy stores above are fenced for the async proxy.
+            static_assert(kR == S0 && (Gm::P * 4) % 16 == 0 && (Gm::STAGE_ENV * 4) % 16 == 0, "whole glimpses, 16-byte runs");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < nv) {
+              bulk_store_hint(out_base + (size_t)(e0 + lane) * Gm::P, smem_u32(stage) + lane * (Gm::STAGE_ENV * 4), Gm::P * 4,
+                              policy_evict_first());
+              bulk_commit();
+            }
+#else
             __syncwarp();
             // copy-out: rows r0 .. r0 + kR of every environment of the pass, 128 bits per lane and store; streaming
             // stores (evict-first: the observation is not read again by the engine)
@@ -460,6 +459,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
               }
             }
             __syncwarp();
+#endif
           }
           // visited bitmask: rows rmin .. rmin + S0 x columns cmin .. cmin + S1; lane = (row, word), one RED per lane
           if (vm) {
@@ -500,82 +500,12 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
         if (vm) vm += nv * vis_words;
         __syncwarp();  // every lane is done with stage s (and the row weights) before they are refilled
       }
-#else
-      // ---------------------------------------------------------------- phase B: warp = environment
-      float* out = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P + jc;
-      unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
-      if (elect_one()) {
-        const int2 xy = reinterpret_cast<const int2*>(hdrs)[2];  // (y0, x0) of environment 0
-        mbar_expect_tx_u(mbar_u + 8 * (it & 1), Gm::TILE_BYTES);
-        tma_load_2d_u(tiles_u + (it & 1) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (it & 1));
-      }
-      for (int e = 0; e < cnt; ++e, ++it, out += Gm::P) {
-        const int s = it & 1;
-        // stage s^1 was last read in the previous iteration (program order + the __syncwarp that ends it): refill it
-        if (e + 1 < cnt && elect_one()) {
-          const int2 xy = reinterpret_cast<const int2*>(hdrs + e + 1)[2];
-          mbar_expect_tx_u(mbar_u + 8 * (s ^ 1), Gm::TILE_BYTES);
-          tma_load_2d_u(tiles_u + (s ^ 1) * Gm::TILE_STRIDE, &tmap, xy.y, xy.x, mbar_u + 8 * (s ^ 1));
-        }
-        const double2 cc = reinterpret_cast<const double2*>(hdrs + e)[0];  // sensor centre (x, y), broadcast
-        const int2 hi = reinterpret_cast<const int2*>(hdrs + e)[3];        // (bank index, first taps)
-        const int rmin = hi.y & 0xffff, cmin = hi.y >> 16;
-        // ---- taps under the consecutive-index assumption (see the file header): the weight of tap t of an axis is
-        // coord_t - grid[k0 + t] with grid[k] = k - off; this lane's column weight lives in registers, the row
-        // weights are recomputed inside the row loop (three float64 adds per row, no shared-memory round trip)
-        const double gy0 = int_to_double(rmin) - kOffY, gx0 = int_to_double(cmin) - kOffX;
-        const double wx = (cc.x + col_off) - (gx0 + col_j), omx = 1.0 - wx;
-        const double wyl = (cc.y + row_off_lane) - (gy0 + row_lane);  // lane t < S0 verifies tap row t
-        const bool bad = !(wx >= 0.0) || !(wx < 1.0) || (cmin + j > IW - 1) || !(wyl >= 0.0) || !(wyl < 1.0) ||
-                         (rmin + min(lane, S0 - 1) > IH - 1);
-        const bool slow = __any_sync(0xffffffffu, bad) || p.force_slow;
-#if APG_TMA_WYSMEM
-        if (lane < S0) s_wy[lane] = wyl;
-        __syncwarp();
-#endif
-        if (vm && c.mode != 0) {
-          for (int w = lane; w < vis_words; w += 32) vm[w] = 0u;
-          __syncwarp();
-        }
-        mbar_wait_u(mbar_u + 8 * s, (unsigned)((it >> 1) & 1));  // this environment's tile has landed
-        if (!slow) {
-          const unsigned char* colp = tiles + s * Gm::TILE_STRIDE + ((cmin * C) & (kXAlign - 1)) + jc;
-          double p00 = APG_PX(colp[0]), p01 = APG_PX(colp[C]);
-#pragma unroll
-          for (int i = 0; i < S0; ++i) {
-            colp += Gm::BOX_W;
-            const double p10 = APG_PX(colp[0]), p11 = APG_PX(colp[C]);
-#if APG_TMA_WYSMEM
-            const double wy = s_wy[i], omy = 1.0 - wy;
-#else
-            const double wy = (cc.y + ((double)i - kHalf0)) - (gy0 + (double)i), omy = 1.0 - wy;
-#endif
-            double acc = p00 * (omy * omx);  // the reference's leading `0.0 +` is an exact no-op for products >= +0
-            acc = acc + p01 * (omy * wx);
-            acc = acc + p10 * (wy * omx);
-            acc = acc + p11 * (wy * wx);
-            // uint8 pixels are in [0,1] and the weights sum to 1 (+ a few ulp): float32(acc) is already clipped
-            if (lane_ok) out[i * Gm::G] = (float)acc;
-            p00 = p10;
-            p01 = p11;
-          }
-          // visited bitmask: rows rmin .. rmin + S0 x columns cmin .. cmin + S1; lane = (row, word), one RED per lane
-          if (vm) {
-            const unsigned long long cb = ((((1ull << (S1 + 1)) - 1ull) << cmin) & wmask);
-            const unsigned bits = vis_w == 0 ? (unsigned)cb : (unsigned)(cb >> 32);
-            if (vis_r <= S0 && rmin + vis_r < IH && bits) atomicOr(vm + (rmin + vis_r) * kWords + vis_w, bits);
-          }
-        } else {
-          blend_env_general<S0, S1, C>(static_cast<const unsigned char*>(p.bank), p.H, p.W, p.words, p.bank_pitch, cc.x,
-                                       cc.y, p.half0, p.half1, p.scale, p.offy, p.offx, hi.x, lane, out - jc, vm);
-        }
-        if (vm) vm += vis_words;
-        __syncwarp();  // every lane is done with stage s before it is refilled
-      }
-#endif
     }
    }
   }
+#if APG_TMA_BULK_OUT
+  if (lane < Gm::E) bulk_wait_read();    // the last bulk stores must not outlive the block's shared memory
+#endif
   if (!table_ready) mbar_wait(tbar, 0);  // a warp without work: the bulk copy must not outlive the block
   if (__syncthreads_or(any_ep_end ? 1 : 0)) {
     if (tid < 6) atomicAdd(p.stats + tid, s_stats[tid]);
@@ -667,12 +597,16 @@ cudaError_t tma_preload(const TmaPlan& plan) {
 
 int tma_launch(const TmaPlan& plan, const ImgParams& p, const RolloutPlan& ro, cudaStream_t stream) {
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  int n_at = 0;
+  if (p.pdl) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    n_at++;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.stream = stream;
   cfg.attrs = at;
-  cfg.numAttrs = p.pdl ? 1 : 0;
+  cfg.numAttrs = n_at;
   // groups of <= 32 consecutive environments, one (or a few) per persistent warp
   // (every warp gets the same number of groups, give or take one short group: m rounds of <= 32 environments)
   const int n_range = p.n1 - p.n0;

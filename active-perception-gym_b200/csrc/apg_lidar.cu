@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   extern __shared__ unsigned smem_maps[];  // kEnvsPerBlock x (prows * pw): padded bitmaps, see MapView
   __shared__ float s_posx[kEnvsPerBlock], s_posy[kEnvsPerBlock];
   __shared__ int s_midx[kEnvsPerBlock];
-  __shared__ unsigned char s_reset[kEnvsPerBlock];
+  __shared__ unsigned s_reset_mask;  // bit e: environment e of the block is reset by this step
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
       midx = p.map_idx[n];
     }
     s_midx[lane] = midx;
-    s_reset[lane] = do_reset ? 1 : 0;
+  }
+  if (warp == 0) {
+    const unsigned rm = __ballot_sync(0xffffffffu, act && do_reset);
+    if (lane == 0) s_reset_mask = rm;
   }
   __syncthreads();
 
@@ -314,20 +317,22 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   // padded word j of padded row yp holds the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad (pad <= 31)
   // (item = (environment, padded row): a warp stages 32 rows at a time, each lane walks the few words of its row --
   //  no integer divisions in the inner loop)
-  for (int q = tid; q < nE * p.prows; q += kThreads) {
-    const int e = q / p.prows, yp = q - e * p.prows;
-    const int y = yp - p.pad;
-    unsigned* dst = smem_maps + e * pmw + yp * p.pw;
-    if (y >= 0 && y < p.H) {
-      const unsigned* row = p.bank + (size_t)s_midx[e] * mw + (size_t)y * p.words;
-      unsigned lo = 0u;
-      for (int j = 0; j < p.pw; ++j) {
-        const unsigned hi = (j < p.words) ? row[j] : 0u;
-        dst[j] = __funnelshift_l(lo, hi, p.pad);  // (hi << pad) | (lo >> (32 - pad))
-        lo = hi;
+  for (int e = warp; e < nE; e += kWarpsPerBlock) {
+    const unsigned* map = p.bank + (size_t)s_midx[e] * mw;
+    for (int yp = lane; yp < p.prows; yp += 32) {
+      const int y = yp - p.pad;
+      unsigned* dst = smem_maps + e * pmw + yp * p.pw;
+      if (y >= 0 && y < p.H) {
+        const unsigned* row = map + (size_t)y * p.words;
+        unsigned lo = 0u;
+        for (int j = 0; j < p.pw; ++j) {
+          const unsigned hi = (j < p.words) ? row[j] : 0u;
+          dst[j] = __funnelshift_l(lo, hi, p.pad);  // (hi << pad) | (lo >> (32 - pad))
+          lo = hi;
+        }
+      } else {
+        for (int j = 0; j < p.pw; ++j) dst[j] = 0u;
       }
-    } else {
-      for (int j = 0; j < p.pw; ++j) dst[j] = 0u;
     }
   }
   __syncthreads();
@@ -465,8 +470,8 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   if (p.map_obs) {
     const float one = __fdiv_rn(1.0f, 255.0f);  // map.astype(f32)[..., None] / 255 -> {0, 1/255}
     const int hw = p.H * p.W;
-    for (int e = 0; e < nE; ++e) {
-      if (!s_reset[e]) continue;
+    for (unsigned rm = s_reset_mask; rm; rm &= rm - 1u) {
+      const int e = __ffs((int)rm) - 1;
       float* mo = p.map_obs + (size_t)(env0 + e) * hw;
       const unsigned* bits = smem_maps + (size_t)e * pmw;
       for (int q = tid; q < hw; q += kThreads) {
