@@ -129,6 +129,7 @@ SYMBOLS = {
     "apg_rng_device_payload": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int32,
                                          C.c_int32, _P, _P, _P, _P]),
     "apg_maps_generate_maze": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_double, _P]),
+    "apg_maps_generate_rooms": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "apg_dlpack_wrap": (_P, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
 }
 

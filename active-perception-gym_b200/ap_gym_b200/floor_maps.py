@@ -77,6 +77,24 @@ class FloorMapBank:
         return cls(bits, int(width), int(height))
 
     @classmethod
+    def generate_rooms(cls, indices, width: int = 32, height: int = 32, max_rooms: int = 10, door_width: int = 3,
+                       device: int = 0) -> "FloorMapBank":
+        """`FloorMapDatasetRooms(width, height, max_rooms, door_width)[indices]` generated on the GPU (csrc/apg_rooms.cuh,
+        csrc/apg_maps.cu): bit-identical to the reference's generator (its numpy draws restated on the PCG64 stream)."""
+        import ctypes as C
+
+        from . import _capi
+
+        if width != height:
+            raise ValueError("rooms maps must be square (the reference transposes half of them)")
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64).ravel())
+        bits = np.empty((len(idx), height, (width + 31) // 32), dtype=np.uint32)
+        _capi.check(_capi.lib().apg_maps_generate_rooms(int(device), idx.ctypes.data_as(C.c_void_p), len(idx), int(width),
+                                                        int(height), int(max_rooms), int(door_width),
+                                                        bits.ctypes.data_as(C.c_void_p)))
+        return cls(bits, int(width), int(height))
+
+    @classmethod
     def from_maps(cls, maps: np.ndarray) -> "FloorMapBank":
         maps = np.asarray(maps, dtype=bool)
         return cls(pack_maps(maps), maps.shape[-1], maps.shape[-2])

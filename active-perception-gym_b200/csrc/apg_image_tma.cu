@@ -60,6 +60,12 @@ namespace {
 #ifndef APG_TMA_BULK_OUT
 #define APG_TMA_BULK_OUT 1  // 1: a staged glimpse leaves with ONE bulk store (cp.async.bulk shared -> global), 0: LDS.128 + STG.128
 #endif
+#ifndef APG_TMA_EARLY_ISSUE
+#define APG_TMA_EARLY_ISSUE 0  // 1: the first pass's tiles are requested between the header and the loss chain of phase H
+#endif
+#ifndef APG_TMA_PREFETCH_IN
+#define APG_TMA_PREFETCH_IN 0  // 1: prefetch.global.L2 of the next step's action / prediction at the end of phase H
+#endif
 #ifndef APG_TMA_STAGE_ROWS
 #define APG_TMA_STAGE_ROWS 10  // sensor rows staged in shared memory between two 128-bit copy-outs
 #endif
@@ -330,30 +336,6 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
     double tcx = 0.0, tcy = 0.0;
     int idx = 0;
     for (int set = 0; set < n_sets; ++set) {
-      // ---------------------------------------------------------------- phase H: lane = environment
-      if (lane < cnt) {
-        unsigned err = 0;
-        const int n = env_base + lane;
-        if (set == 0) {
-          double px = 0.0, py = 0.0;
-          env_move(p, c, n, px, py, tcx, tcy, idx, err);
-          write_hdr<C>(p, hdrs + lane, px * p.lim_x, py * p.lim_y, idx, err);
-          env_loss(p, c, n, s_stats, ep_end, err);
-        } else {
-          write_hdr<C>(p, hdrs + lane, tcx, tcy, idx, err);
-        }
-        if (err) atomicOr(p.err, err);
-      }
-      __syncwarp();
-      if (!table_ready) {
-        mbar_wait(tbar, 0);
-        table_ready = true;
-      }
-      // ---------------------------------------------------------------- phase B: warp = E environments per pass
-      // lane = (environment es of the pass, sensor column col): the weight products of a (row, column) are formed once
-      // and serve the C channels; one mbarrier stage holds the E tiles of a pass.
-      float* const out_base = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P;
-      unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
       // the E tiles of one pass -> stage st; slot q's box starts q rows early and is q rows taller (row shift, see Geom)
       // (lane q issues the copy of slot q: the whole warp calls this; the transaction count is posted first, a copy that
       //  completes before it only drives the count negative while the arrival is still pending)
@@ -366,7 +348,50 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
                            policy_evict_first());
         }
       };
+      // ---------------------------------------------------------------- phase H: lane = environment
+      // move -> header -> (the tiles of the first pass are requested: lane q reads the header it has just written) -> loss,
+      // reward, flags, statistics while they fly
+      unsigned err = 0;
+      const int n = env_base + lane;
+      if (lane < cnt) {
+        if (set == 0) {
+          double px = 0.0, py = 0.0;
+          env_move(p, c, n, px, py, tcx, tcy, idx, err);
+          write_hdr<C>(p, hdrs + lane, px * p.lim_x, py * p.lim_y, idx, err);
+        } else {
+          write_hdr<C>(p, hdrs + lane, tcx, tcy, idx, err);
+        }
+      }
+#if APG_TMA_EARLY_ISSUE
       issue_pass(it & 1, 0, min(Gm::E, cnt));
+#endif
+      if (lane < cnt) {
+        if (set == 0) {
+          env_loss(p, c, n, s_stats, ep_end, err);
+#if APG_TMA_PREFETCH_IN
+          // the inputs of the next step on their way into L2 (their first use is the head of the next phase H)
+          if (k + 1 < ro.n_steps && p.action != nullptr) {
+            const int pw = (p.task == APG_TASK_CLASSIFICATION) ? p.K : 2;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(c.action + ((size_t)p.N + n) * 2));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(c.pred + ((size_t)p.N + n) * pw));
+          }
+#endif
+        }
+        if (err) atomicOr(p.err, err);
+      }
+      __syncwarp();
+#if !APG_TMA_EARLY_ISSUE
+      issue_pass(it & 1, 0, min(Gm::E, cnt));
+#endif
+      if (!table_ready) {
+        mbar_wait(tbar, 0);
+        table_ready = true;
+      }
+      // ---------------------------------------------------------------- phase B: warp = E environments per pass
+      // lane = (environment es of the pass, sensor column col): the weight products of a (row, column) are formed once
+      // and serve the C channels; one mbarrier stage holds the E tiles of a pass.
+      float* const out_base = (set == 0 ? p.glimpse : p.target_glimpse) + (size_t)env_base * Gm::P;
+      unsigned* vm = (p.track && set == 0) ? p.visited + (size_t)env_base * vis_words : nullptr;
       for (int e0 = 0; e0 < cnt; e0 += Gm::E, ++it) {
         const int s = it & 1;
         const int nv = min(Gm::E, cnt - e0);

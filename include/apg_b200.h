@@ -297,9 +297,17 @@ int apg_lidar_sync(apg_lidar_env* env);
  * FloorMapDatasetMaze.get_data_point (ap_gym/envs/floor_map/floor_map_dataset_maze.py:24-55; the recursive carve as an
  * explicit stack, the numpy draws of default_rng(index) in the same order): map i of the result is dataset[h_indices[i]],
  * bit-packed like apg_lidar_set_map_bank expects ((n_maps, height, ceil(width/32)) uint32, bit = wall).  Odd sizes up
- * to 255.  Synchronous.  The rooms generator (floor_map_dataset_rooms.py) is not provided. */
+ * to 255.  Synchronous. */
 int apg_maps_generate_maze(int32_t device, const uint64_t* h_indices, int64_t n_maps, int32_t width, int32_t height,
                            double branching_prob, uint32_t* h_bits);
+
+/* Procedural rooms maps generated ON THE DEVICE, bit-identical to FloorMapDatasetRooms.get_data_point
+ * (ap_gym/envs/floor_map/floor_map_dataset_rooms.py:25-89): the recursive split_room as an explicit stack of room views,
+ * numpy's binomial (inversion), choice(replace=False) (Floyd + shuffle draws) and integers (Lemire) restated on the
+ * PCG64 stream of default_rng(index) (csrc/apg_rooms.cuh).  Same output layout as apg_maps_generate_maze.  Square maps
+ * (the reference transposes half of them), max_rooms <= 16.  Synchronous. */
+int apg_maps_generate_rooms(int32_t device, const uint64_t* h_indices, int64_t n_maps, int32_t width, int32_t height,
+                            int32_t max_rooms, int32_t door_width, uint32_t* h_bits);
 
 /* Host-side test hook for the numpy-compatible random streams used on the device reset path (csrc/apg_rng.h):
  * a Generator(PCG64(SeedSequence(seed))) driven by n_ops operations --

@@ -1,5 +1,6 @@
-"""Procedural maze maps: the iterative CPU restatement (oracle/floor_map_oracle.py) against the reference-generated
-golden banks (CPU), and the device generator (csrc/apg_maps.cu, through the C-ABI) against both (-m gpu)."""
+"""Procedural maps (mazes, rooms): the iterative CPU restatements (oracle/floor_map_oracle.py) against the
+reference-generated golden banks (CPU), the product's host/device rooms generator compiled as host code against the same
+bank (CPU), and the device generators (csrc/apg_maps.cu, through the C-ABI) against both (-m gpu)."""
 import os
 
 import numpy as np
@@ -49,3 +50,79 @@ def test_device_maze_generator_matches_oracle_other_parameters():
         bank = apg.FloorMapBank.generate_maze(idx, W, H, branching_prob=p)
         want = _pack([maze(i, W, H, p) for i in idx])
         assert np.array_equal(bank.bits, want), (W, H, p)
+
+
+# ------------------------------------------------------------------------------------------------ rooms
+def test_iterative_rooms_oracle_matches_reference_bank():
+    """The golden is FloorMapDatasetRooms()[0..4095] of the unmodified reference (tests/golden/make_golden_lidar.py)."""
+    from oracle.floor_map_oracle import rooms
+
+    bits, W, H = _golden("rooms32", 300)
+    assert np.array_equal(_pack([rooms(i, W, H) for i in range(300)]), bits)
+
+
+@pytest.mark.reference
+def test_iterative_rooms_oracle_matches_live_reference_other_parameters():
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "shim"))
+    sys.path.insert(0, "/root/reference")
+    from ap_gym.envs.floor_map.floor_map_dataset_rooms import FloorMapDatasetRooms
+
+    from oracle.floor_map_oracle import rooms
+
+    for W, mr, dw, idx in [(48, 6, 2, [0, 1, 2, 3, 99]), (64, 10, 3, [5, 2**31 + 7]), (24, 4, 4, [11, 12]), (96, 14, 2, [3])]:
+        ds = FloorMapDatasetRooms(W, W, mr, dw)
+        for i in idx:
+            assert np.array_equal(rooms(i, W, W, mr, dw), ds.get_data_point(i)), (W, mr, dw, i)
+
+
+def _rooms_host(idx, W, mr, dw, tmp_path):
+    """csrc/apg_rooms.cuh (the code the kernel runs per thread) compiled with g++."""
+    import ctypes as C
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_path = str(tmp_path / "librooms_harness.so")
+    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
+                        os.path.join(root, "active-perception-gym_b200", "csrc"), "-o", lib_path,
+                        os.path.join(root, "tests", "native", "rooms_harness.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(lib_path)
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    out = np.zeros((len(idx), W, (W + 31) // 32), dtype=np.uint32)
+    bad = lib.apg_rooms_host(idx.ctypes.data_as(C.c_void_p), C.c_longlong(len(idx)), W, W, mr, dw,
+                             out.ctypes.data_as(C.c_void_p))
+    assert bad == 0
+    return out
+
+
+def test_host_device_rooms_generator_matches_reference_bank(tmp_path):
+    """All 4096 maps of the golden bank, and other parameters against the oracle."""
+    from oracle.floor_map_oracle import rooms
+
+    bits, W, H = _golden("rooms32", 4096)
+    assert np.array_equal(_rooms_host(np.arange(4096), W, 10, 3, tmp_path), bits)
+    for W, mr, dw, idx in [(48, 6, 2, [0, 1, 2, 3, 99]), (64, 10, 3, [5, 2**31 + 7, 2**32 - 1]), (24, 4, 4, [11, 12]),
+                           (96, 14, 2, [3])]:
+        assert np.array_equal(_rooms_host(idx, W, mr, dw, tmp_path), _pack([rooms(i, W, W, mr, dw) for i in idx])), (W, mr, dw)
+
+
+@pytest.mark.gpu
+def test_device_rooms_generator_matches_reference_bank():
+    import ap_gym_b200 as apg
+
+    bits, W, H = _golden("rooms32", 4096)
+    bank = apg.FloorMapBank.generate_rooms(np.arange(4096), W, H)
+    assert bank.bits.shape == bits.shape and np.array_equal(bank.bits, bits)
+
+
+@pytest.mark.gpu
+def test_device_rooms_generator_matches_oracle_other_parameters():
+    import ap_gym_b200 as apg
+    from oracle.floor_map_oracle import rooms
+
+    for W, mr, dw, idx in [(48, 6, 2, [0, 1, 2, 3, 99]), (64, 10, 3, [5, 2**31 + 7, 2**32 - 1]), (24, 4, 4, [11, 12]),
+                           (96, 14, 2, [3])]:
+        bank = apg.FloorMapBank.generate_rooms(idx, W, W, max_rooms=mr, door_width=dw)
+        assert np.array_equal(bank.bits, _pack([rooms(i, W, W, mr, dw) for i in idx])), (W, mr, dw)
