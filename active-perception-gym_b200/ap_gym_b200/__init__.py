@@ -8,7 +8,7 @@ from .loss_fn import (CrossEntropyLossFn, LambdaLossFn, LossFn, LossFnAffineTran
                       WeightedLossFn, ZeroLossFn)
 from .spaces import ActivePerceptionActionSpace, ImageSpace, LogitSpace
 from .datasets import ArrayImageDataset, ImageBank, SyntheticImageDataset, bank_from_dataset
-from .floor_maps import FloorMapBank, pack_maps, unpack_maps
+from .floor_maps import FloorMapBank, FloorMapDatasetMaze, FloorMapDatasetRooms, pack_maps, unpack_maps
 from .lidar_env import LIDARLocalization2DVectorEnv, lidar_directions
 from .image_env import ImageClassificationVectorEnv, ImageLocalizationVectorEnv, ImagePerceptionConfig
 from .reference_compat import enable_reference_compat, register_envs

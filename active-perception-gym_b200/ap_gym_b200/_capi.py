@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("APG_B200_LIB") or os.path.join(_PKG, "_lib", "libapg_
 
 APG_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NEED_PAYLOAD, ERR_NAN_ACTION, ERR_NAN_PRED, ERR_OUT_OF_GRID = range(-1, -8, -1)
-FLAG_NAN_ACTION, FLAG_NAN_PRED, FLAG_OUT_OF_GRID = 1, 2, 4
+FLAG_NAN_ACTION, FLAG_NAN_PRED, FLAG_OUT_OF_GRID, FLAG_MAPGEN = 1, 2, 4, 8
 TASK_CLASSIFICATION, TASK_LOCALIZATION = 0, 1
 BANK_U8, BANK_F32 = 0, 1
 PAYLOAD_RING_DEFAULT, PAYLOAD_RING_MAX = 4, 64
@@ -113,6 +113,7 @@ SYMBOLS = {
     "apg_lidar_create": (C.c_int, [C.POINTER(LidarCfg), C.POINTER(_P)]),
     "apg_lidar_destroy": (None, [_P]),
     "apg_lidar_set_stream": (C.c_int, [_P, _P]),
+    "apg_lidar_set_map_generator": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double]),
     "apg_lidar_set_map_bank": (C.c_int, [_P, _P, C.c_int64]),
     "apg_lidar_set_beams": (C.c_int, [_P, _P]),
     "apg_lidar_reset": (C.c_int, [_P, C.c_uint64]),

@@ -3,9 +3,13 @@
 
 A bank is a FINITE list of occupancy maps stored bit-packed, (M, H, ceil(W/32)) uint32 with bit x&31 of word
 x>>5 set for a wall.  Any object with the reference's FloorMapDataset surface (`map_width`, `map_height`,
-`__len__`, `__getitem__`) can be turned into a bank; the reference's procedural datasets report
-`len == 2**32`, so for those an explicit index list is required (documented deviation: the engine draws
-`integers(0, M)` over the bank where the reference draws `integers(0, 2**32)` over the generator).
+`__len__`, `__getitem__`) can be turned into a bank.
+
+The reference's PROCEDURAL datasets (`FloorMapDatasetRooms`, `FloorMapDatasetMaze`, len == 2**32) are mirrored here by
+classes of the same names and constructor signatures; handed to `LIDARLocalization2DVectorEnv` -- these or the
+reference's own objects -- they switch the engine to procedural-dataset mode: every (auto)reset draws
+`integers(0, 2**32)` from the environment's DatasetIterator stream and generates that map on the device, exactly what the
+reference's `next(data_loader)` yields (csrc/apg_rooms.cuh, csrc/apg_maze.cuh, apg_lidar_set_map_generator).
 """
 from __future__ import annotations
 
@@ -31,6 +35,73 @@ def pack_maps(maps: np.ndarray) -> np.ndarray:
 def unpack_maps(bits: np.ndarray, width: int) -> np.ndarray:
     x = np.arange(width)
     return ((bits[..., x >> 5] >> (x & 31).astype(np.uint32)) & 1).astype(bool)
+
+
+class _ProceduralDataset:
+    """Common surface of the procedural datasets (ap_gym/envs/floor_map/floor_map_dataset.py, envs/dataset/dataset.py)."""
+
+    def __len__(self):
+        return 2 ** 32
+
+    def load(self):
+        pass
+
+    def get_data_point(self, idx) -> np.ndarray:
+        return self.get_data_point_batch([idx])[0]
+
+    def __getitem__(self, item):
+        if isinstance(item, (list, tuple, np.ndarray)):
+            return self.get_data_point_batch(item)
+        return self.get_data_point(item)
+
+
+class FloorMapDatasetRooms(_ProceduralDataset):
+    """Mirror of the reference's `FloorMapDatasetRooms(width, height, max_rooms, door_width)`
+    (floor_map_dataset_rooms.py:9-23); maps are generated on the GPU, bit-identical to the reference's."""
+
+    def __init__(self, width: int = 32, height: int = 32, max_rooms: int = 10, door_width: int = 3, device: int = 0):
+        self.map_width, self.map_height = int(width), int(height)
+        self.max_rooms, self.door_width, self.device = int(max_rooms), int(door_width), int(device)
+
+    def get_data_point_batch(self, idx) -> np.ndarray:
+        bank = FloorMapBank.generate_rooms(idx, self.map_width, self.map_height, self.max_rooms, self.door_width, self.device)
+        return unpack_maps(bank.bits, self.map_width)
+
+
+class FloorMapDatasetMaze(_ProceduralDataset):
+    """Mirror of the reference's `FloorMapDatasetMaze(width, height, branching_prob)` (floor_map_dataset_maze.py:10-22)."""
+
+    def __init__(self, width: int = 21, height: int = 21, branching_prob: float = 1.0, device: int = 0):
+        if width % 2 == 0 or height % 2 == 0:
+            raise ValueError("Width and height must be odd.")
+        self.map_width, self.map_height = int(width), int(height)
+        self.branching_prob, self.device = float(branching_prob), int(device)
+
+    def get_data_point_batch(self, idx) -> np.ndarray:
+        bank = FloorMapBank.generate_maze(idx, self.map_width, self.map_height, self.branching_prob, self.device)
+        return unpack_maps(bank.bits, self.map_width)
+
+
+def procedural_spec(dataset):
+    """("rooms" | "maze", parameters) when `dataset` is a procedural map dataset -- one of the mirrors above or the
+    reference's own object (recognised by class name, parameters read from its name-mangled attributes) -- else None."""
+    name = type(dataset).__name__
+    if isinstance(dataset, FloorMapDatasetRooms):
+        return "rooms", dict(width=dataset.map_width, height=dataset.map_height, max_rooms=dataset.max_rooms,
+                             door_width=dataset.door_width)
+    if isinstance(dataset, FloorMapDatasetMaze):
+        return "maze", dict(width=dataset.map_width, height=dataset.map_height, branching_prob=dataset.branching_prob)
+    try:
+        if name == "FloorMapDatasetRooms":
+            g = lambda a: getattr(dataset, "_FloorMapDatasetRooms__" + a)  # noqa: E731
+            return "rooms", dict(width=int(g("width")), height=int(g("height")), max_rooms=int(g("max_rooms")),
+                                 door_width=int(g("door_width")))
+        if name == "FloorMapDatasetMaze":
+            g = lambda a: getattr(dataset, "_FloorMapDatasetMaze__" + a)  # noqa: E731
+            return "maze", dict(width=int(g("width")), height=int(g("height")), branching_prob=float(g("branching_prob")))
+    except AttributeError:
+        return None
+    return None
 
 
 @dataclass

@@ -14,7 +14,7 @@ from typing import Any, Literal
 import numpy as np
 
 from . import _capi
-from .floor_maps import FloorMapBank
+from .floor_maps import FloorMapBank, procedural_spec
 from .loss_fn import WeightedLossFn, make_mse_loss_fn_and_target_space
 from .spaces import (NEXT_STEP, ActivePerceptionActionSpace, Box, Dict, ImageSpace, VectorEnvBase, batch_box,
                      sparse_target_spaces)
@@ -57,12 +57,28 @@ class LIDARLocalization2DVectorEnv(VectorEnvBase):
         self._render_mode = render_mode
         self.num_envs = int(num_envs)
         self._device = int(device)
-        self._bank = FloorMapBank.from_dataset(dataset)
         self._static = bool(static_map)
+        # procedural datasets (len == 2**32: ours or the reference's FloorMapDatasetRooms / FloorMapDatasetMaze): every
+        # (auto)reset draws its dataset index and generates the map on the device; a static map is generated once
+        self._procedural = procedural_spec(dataset)
+        self._dataset = dataset
+        if self._procedural is not None:
+            kind, kw = self._procedural
+            gen = FloorMapBank.generate_rooms if kind == "rooms" else FloorMapBank.generate_maze
+            if self._static:
+                self._bank = gen([int(static_map_index)], device=int(device), **kw)
+                static_map_index = 0
+                self._procedural = None
+            else:
+                self._bank = None
+                self._W, self._H = int(kw["width"]), int(kw["height"])
+        else:
+            self._bank = FloorMapBank.from_dataset(dataset)
         self._B = int(lidar_beam_count)
         self._range = lidar_range
         self._T = int(max_episode_steps)
-        self._W, self._H = int(self._bank.map_width), int(self._bank.map_height)
+        if self._bank is not None:
+            self._W, self._H = int(self._bank.map_width), int(self._bank.map_height)
         self._check_errors = check_errors
         self._numpy_mode = output == "numpy"
         self._steps_since_poll = 0
@@ -78,7 +94,13 @@ class LIDARLocalization2DVectorEnv(VectorEnvBase):
         _capi.check(self._lib.apg_lidar_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self._closed = False
-        _capi.check(self._lib.apg_lidar_set_map_bank(self._h, _void(self._bank.bits), len(self._bank)))
+        if self._procedural is not None:
+            kind, kw = self._procedural
+            _capi.check(self._lib.apg_lidar_set_map_generator(
+                self._h, 1 if kind == "rooms" else 2, int(kw.get("max_rooms", 0)), int(kw.get("door_width", 0)),
+                float(kw.get("branching_prob", 1.0))))
+        else:
+            _capi.check(self._lib.apg_lidar_set_map_bank(self._h, _void(self._bank.bits), len(self._bank)))
         self._dirs = lidar_directions(self._B, lidar_range)
         _capi.check(self._lib.apg_lidar_set_beams(self._h, _void(self._dirs)))
         self._views = self._make_views()
@@ -111,7 +133,7 @@ class LIDARLocalization2DVectorEnv(VectorEnvBase):
     single_prediction_space = property(lambda self: self.single_action_space["prediction"])
     single_inner_action_space = property(lambda self: self.single_action_space["action"])
     render_mode = property(lambda self: self._render_mode)
-    dataset = property(lambda self: self._bank)
+    dataset = property(lambda self: self._bank if self._bank is not None else self._dataset)
     unwrapped = property(lambda self: self)
 
     def _make_views(self):
@@ -170,6 +192,8 @@ class LIDARLocalization2DVectorEnv(VectorEnvBase):
             raise ValueError("NaN values detected in action.")
         if flags.value & _capi.FLAG_NAN_PRED:
             raise ValueError("NaN values detected in prediction.")
+        if flags.value & _capi.FLAG_MAPGEN:
+            raise ValueError("a procedural map exceeded the device generator's limits (door_width >= room width?)")
 
     def _maybe_poll(self, host_mode):
         self._steps_since_poll += 1

@@ -22,7 +22,9 @@
 
 #include "apg_common.h"
 #include "apg_lidar_filter.cuh"
+#include "apg_maze.cuh"
 #include "apg_rng.h"
+#include "apg_rooms.cuh"
 
 namespace {
 
@@ -45,6 +47,10 @@ struct LidarParams {
   unsigned long long seed;  // mode 2: env i is seeded with seed + env_offset + i
   long long env_offset;
   const unsigned* bank;     // (M, H, words)
+  // procedural-dataset mode (apg_lidar_set_map_generator): every environment owns its current map, generated on the
+  // device at its (auto)reset by lidar_mapgen_kernel BEFORE this kernel; map_idx then holds the dataset index (uint32)
+  const unsigned* env_maps; // (N, H, words) or nullptr (bank mode)
+  int* gen_count;           // length of the reset list (zeroed here for the next step's list kernel)
   const float* dirs;        // (B, 2) lidar_directions
   const float* action;
   const float* pred;
@@ -285,7 +291,9 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   if (act) {
     do_reset = (p.mode != 0) || (p.prev_done[n] != 0);
     int midx;
-    if (do_reset) {
+    if (p.env_maps) {
+      midx = p.map_idx[n];  // seeding, the dataset-index draw and the map itself: lidar_mapgen_kernel, already done
+    } else if (do_reset) {
       apg::Pcg64 g0, g2;
       if (p.mode == 2) {
         apg::pcg64_seed(g0, p.seed + (unsigned long long)(p.env_offset + n));
@@ -307,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
     }
     s_midx[lane] = midx;
   }
+  if (p.gen_count && blockIdx.x == 0 && tid == 0) *p.gen_count = 0;
   if (warp == 0) {
     const unsigned rm = __ballot_sync(0xffffffffu, act && do_reset);
     if (lane == 0) s_reset_mask = rm;
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   // (item = (environment, padded row): a warp stages 32 rows at a time, each lane walks the few words of its row --
   //  no integer divisions in the inner loop)
   for (int e = warp; e < nE; e += kWarpsPerBlock) {
-    const unsigned* map = p.bank + (size_t)s_midx[e] * mw;
+    const unsigned* map = p.env_maps ? p.env_maps + (size_t)(env0 + e) * mw : p.bank + (size_t)s_midx[e] * mw;
     for (int yp = lane; yp < p.prows; yp += 32) {
       const int y = yp - p.pad;
       unsigned* dst = smem_maps + e * pmw + yp * p.pw;
@@ -341,7 +350,8 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   if (act) {
     MapView mv{smem_maps + (size_t)lane * pmw, p.pw, p.pad};
     const int midx = s_midx[lane];
-    const unsigned* gbits = p.bank + (size_t)midx * mw;  // the unpadded bitmap (reset only: free-cell count / pick)
+    // the unpadded bitmap (reset only: free-cell count / pick)
+    const unsigned* gbits = p.env_maps ? p.env_maps + (size_t)n * mw : p.bank + (size_t)midx * mw;
     float posx, posy, initx, inity;
     int elapsed;
     bool aliased;
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
       if (p.reward2) p.reward2[n] = rew_out;
     }
     // ---- state write-back + scalar observations
-    p.map_idx_out[n] = (long long)midx;
+    p.map_idx_out[n] = p.env_maps ? (long long)(unsigned)midx : (long long)midx;
     p.pos[2 * n] = posx; p.pos[2 * n + 1] = posy;
     p.init[2 * n] = initx; p.init[2 * n + 1] = inity;
     p.aliased[n] = aliased ? 1 : 0;
@@ -569,6 +579,74 @@ __global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarPara
   }
 }
 
+// ---- procedural-dataset mode: the reference's per-episode `next(data_loader)` on the device -------------------------
+// (lidar_localization2d.py:297-298 -> dataset_iterator.py:27-32 -> floor_map_dataset_{rooms,maze}.py get_data_point)
+struct MapGenParams {
+  int N, W, H, words, n0, n1, mode, kind;  // kind 1 = rooms, 2 = maze
+  int max_rooms, door_width, maze_cells;
+  double branching_prob;
+  unsigned long long seed;
+  long long env_offset;
+  const unsigned char* prev_done;
+  apg::Pcg64* g0;
+  apg::Pcg64* g2;
+  int* map_idx;
+  unsigned* env_maps;
+  const double* qn_table;
+  int* list;
+  int* count;
+  unsigned* scratch;    // per generator thread: rooms = two bit planes + the view stack, maze = the frame stack
+  size_t scratch_words; // per thread
+  unsigned* err;
+};
+
+// the environments of [n0, n1) that this step resets, compacted (map generation is long and divergent: it runs on the
+// compacted list with full warps instead of on the few resetting lanes of every warp)
+__global__ void lidar_reset_list_kernel(const MapGenParams p) {
+  const int n = p.n0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool r = n < p.n1 && ((p.mode != 0) || (p.prev_done[n] != 0));
+  const unsigned bal = __ballot_sync(0xffffffffu, r);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(p.count, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (r) p.list[base + __popc(bal & ((1u << lane) - 1u))] = n;
+}
+
+// one thread per list entry: (mode 2: seed the env's streams,) draw the dataset index from the env's DatasetIterator
+// stream -- integers(0, 2**32) -- and generate that map into the env's slot
+__global__ void lidar_mapgen_kernel(const MapGenParams p) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
+  const int count = *p.count;
+  const int mw = p.H * p.words;
+  unsigned* scr = p.scratch + (size_t)gtid * p.scratch_words;
+  for (int i = gtid; i < count; i += total) {
+    const int n = p.list[i];
+    apg::Pcg64 g2;
+    if (p.mode == 2) {
+      apg::Pcg64 g0;
+      apg::pcg64_seed(g0, p.seed + (unsigned long long)(p.env_offset + n));
+      const uint64_t s2 = apg::rng_integers_0_to_2p32_inclusive(g0);  // DatasetIterator seed (:552)
+      apg::pcg64_seed(g2, s2);
+      p.g0[n] = g0;
+    } else {
+      g2 = p.g2[n];
+    }
+    const unsigned idx = (unsigned)apg::rng_integers_below(g2, 0x100000000ull);  // dataset_iterator.py:30, len == 2**32
+    p.g2[n] = g2;
+    p.map_idx[n] = (int)idx;
+    unsigned* out = p.env_maps + (size_t)n * mw;
+    if (p.kind == 1) {
+      const int rc = apg_rooms::generate(idx, p.W, p.H, p.max_rooms, p.door_width, p.qn_table, scr, scr + mw,
+                                         reinterpret_cast<apg_rooms::View*>(scr + 2 * mw), out);
+      if (rc) atomicOr(p.err, APG_FLAG_MAPGEN);
+    } else {
+      apg_maze::generate(idx, p.W, p.H, p.branching_prob, out, scr);
+    }
+  }
+}
+
 }  // namespace
 
 // ======================================================================================================
@@ -607,6 +685,15 @@ struct apg_lidar_env {
   bool filter_fits = false; // every beam fits the swath-pattern table (|dir| <= 5)
   uint4* d_ftable = nullptr;
   double open_fraction = 0.0;
+  // procedural-dataset mode (apg_lidar_set_map_generator)
+  int gen_kind = 0, gen_max_rooms = 0, gen_door = 0, gen_cells = 0, gen_threads = 0;
+  double gen_branch = 1.0;
+  unsigned* d_env_maps = nullptr;
+  unsigned* d_gen_scratch = nullptr;
+  size_t gen_scratch_words = 0;
+  int* d_gen_list = nullptr;
+  int* d_gen_count = nullptr;
+  double* d_qn = nullptr;
 };
 
 namespace {
@@ -632,6 +719,20 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   p.reward2 = reward2; p.done2 = done2; p.err = e->d_err;
   p.acc1 = e->d_acc1; p.acc2 = e->d_acc2; p.acc_ret = e->d_acc_ret; p.ep_avg1 = e->b.d_ep_avg1; p.ep_final1 = e->b.d_ep_final1;
   p.ep_avg2 = e->b.d_ep_avg2; p.ep_final2 = e->b.d_ep_final2; p.ep_return = e->b.d_ep_return; p.stats = e->d_stats;
+  if (e->gen_kind) {
+    MapGenParams g{};
+    g.N = p.N; g.W = p.W; g.H = p.H; g.words = p.words; g.n0 = p.n0; g.n1 = p.n1; g.mode = mode; g.kind = e->gen_kind;
+    g.max_rooms = e->gen_max_rooms; g.door_width = e->gen_door; g.maze_cells = e->gen_cells; g.branching_prob = e->gen_branch;
+    g.seed = seed; g.env_offset = c.env_offset; g.prev_done = e->d_prev_done; g.g0 = e->d_g0; g.g2 = e->d_g2;
+    g.map_idx = e->d_map_idx; g.env_maps = e->d_env_maps; g.qn_table = e->d_qn; g.list = e->d_gen_list;
+    g.count = e->d_gen_count; g.scratch = e->d_gen_scratch; g.scratch_words = e->gen_scratch_words; g.err = e->d_err;
+    lidar_reset_list_kernel<<<apg::ceil_div(p.n1 - p.n0, 256), 256, 0, e->stream>>>(g);
+    lidar_mapgen_kernel<<<e->gen_threads / 64, 64, 0, e->stream>>>(g);
+    APG_CUDA(cudaGetLastError());
+    apg::count_launch(2);
+    p.env_maps = e->d_env_maps;
+    p.gen_count = e->d_gen_count;
+  }
   const int grid = apg::ceil_div(p.n1 - p.n0, kEnvsPerBlock);
   // (+ one spare word behind the bitmaps and the ray queue of the filtered beam phase)
   const size_t smem = e->smem + sizeof(unsigned) + (p.filter ? kQueueCap * sizeof(unsigned short) : 0);
@@ -747,6 +848,11 @@ void apg_lidar_destroy(apg_lidar_env* e) {
   cudaStreamSynchronize(e->stream);
   apg::dev_free(e->d_bank); apg::dev_free(e->d_dirs);
   if (e->d_ftable) cudaFree(e->d_ftable);
+  if (e->d_env_maps) cudaFree(e->d_env_maps);
+  if (e->d_gen_scratch) cudaFree(e->d_gen_scratch);
+  if (e->d_gen_list) cudaFree(e->d_gen_list);
+  if (e->d_gen_count) cudaFree(e->d_gen_count);
+  if (e->d_qn) cudaFree(e->d_qn);
   apg::dev_free(e->b.d_lidar); apg::dev_free(e->b.d_odometry); apg::dev_free(e->b.d_time_step); apg::dev_free(e->b.d_map);
   apg::dev_free(e->b.d_reward); apg::dev_free(e->b.d_base_reward); apg::dev_free(e->b.d_loss); apg::dev_free(e->b.d_target);
   apg::dev_free(e->b.d_terminated); apg::dev_free(e->b.d_truncated); apg::dev_free(e->b.d_stepped);
@@ -844,9 +950,58 @@ int apg_lidar_set_beams(apg_lidar_env* e, const float* h_dirs) {
   return APG_OK;
 }
 
+int apg_lidar_set_map_generator(apg_lidar_env* e, int32_t kind, int32_t max_rooms, int32_t door_width,
+                                double branching_prob) {
+  APG_CHECK(e, APG_ERR_INVALID, "null env");
+  APG_CHECK(kind == APG_MAPGEN_ROOMS || kind == APG_MAPGEN_MAZE, APG_ERR_INVALID, "unknown map generator %d", kind);
+  APG_CHECK(!e->cfg.static_map, APG_ERR_INVALID, "static_map takes a one-map bank (generate it with apg_maps_generate_*)");
+  const int W = e->cfg.width, H = e->cfg.height;
+  if (kind == APG_MAPGEN_ROOMS) {
+    APG_CHECK(W == H, APG_ERR_INVALID, "rooms maps must be square (the reference transposes half of them)");
+    APG_CHECK(W >= 4 && W <= 255, APG_ERR_INVALID, "bad map size");
+    APG_CHECK(max_rooms >= 1 && max_rooms <= apg_rooms::kMaxRooms, APG_ERR_INVALID, "max_rooms must be in [1, %d]",
+              apg_rooms::kMaxRooms);
+    APG_CHECK(door_width >= 1 && door_width <= 64, APG_ERR_INVALID, "bad door_width");
+  } else {
+    APG_CHECK(W >= 3 && H >= 3 && W <= 255 && H <= 255 && (W & 1) && (H & 1), APG_ERR_INVALID,
+              "Width and height must be odd (and at most 255).");
+  }
+  APG_CUDA(cudaSetDevice(e->cfg.device));
+  APG_CUDA(cudaStreamSynchronize(e->stream));
+  const size_t N = e->cfg.num_envs, mw = (size_t)H * e->words;
+  int sms = 0;
+  APG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
+  e->gen_kind = kind; e->gen_max_rooms = max_rooms; e->gen_door = door_width; e->gen_branch = branching_prob;
+  e->gen_cells = ((W - 1) / 2) * ((H - 1) / 2) + 1;
+  e->gen_threads = sms * 8 * 64;  // 16 warps per SM: the generators are long serial chains, latency-bound
+  e->gen_scratch_words = kind == APG_MAPGEN_ROOMS
+                             ? 2 * mw + (apg_rooms::kMaxStack * sizeof(apg_rooms::View) + 3) / 4
+                             : (size_t)e->gen_cells;
+  if (e->d_env_maps) { cudaFree(e->d_env_maps); e->d_env_maps = nullptr; }
+  if (e->d_gen_scratch) { cudaFree(e->d_gen_scratch); e->d_gen_scratch = nullptr; }
+  APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_env_maps), N * mw * sizeof(unsigned)));
+  APG_CUDA(cudaMemset(e->d_env_maps, 0, N * mw * sizeof(unsigned)));
+  APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_gen_scratch), (size_t)e->gen_threads * e->gen_scratch_words * sizeof(unsigned)));
+  if (!e->d_gen_list) APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_gen_list), N * sizeof(int)));
+  if (!e->d_gen_count) APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_gen_count), sizeof(int)));
+  APG_CUDA(cudaMemset(e->d_gen_count, 0, sizeof(int)));
+  // exp(n * log(1 - p)) of numpy's binomial inversion, from the host's libm (the same one numpy calls)
+  double qn[apg_rooms::kMaxRooms + 1];
+  for (int k = 0; k <= apg_rooms::kMaxRooms; ++k) qn[k] = std::exp((double)k * std::log(1.0 - apg_rooms::kP));
+  if (!e->d_qn) APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_qn), sizeof(qn)));
+  APG_CUDA(cudaMemcpy(e->d_qn, qn, sizeof(qn), cudaMemcpyHostToDevice));
+  // beam filter: rooms maps are open, maze corridors are one cell wide (see apg_lidar_set_map_bank)
+  e->filter = kind == APG_MAPGEN_ROOMS ? 1 : 0;
+  if (const char* ov = getenv("APG_LIDAR_FILTER")) e->filter = atoi(ov) != 0;
+  e->n_maps = 0;
+  e->has_reset = false;
+  return APG_OK;
+}
+
 int apg_lidar_reset(apg_lidar_env* e, uint64_t seed) {
   APG_CHECK(e, APG_ERR_INVALID, "null env");
-  APG_CHECK(e->d_bank && e->have_beams, APG_ERR_STATE, "apg_lidar_reset before set_map_bank / set_beams");
+  APG_CHECK((e->d_bank || e->gen_kind) && e->have_beams, APG_ERR_STATE,
+            "apg_lidar_reset before set_map_bank / set_map_generator / set_beams");
   APG_CUDA(cudaSetDevice(e->cfg.device));
   int rc = lidar_launch(e, 2, seed, nullptr, nullptr, nullptr, nullptr);
   if (rc != APG_OK) return rc;

@@ -18,82 +18,17 @@
 
 #include "apg_common.h"
 #include "apg_rng.h"
+#include "apg_maze.cuh"
 #include "apg_rooms.cuh"
 
 namespace {
 
-__device__ __forceinline__ unsigned interval(apg::Pcg64& g, unsigned max, unsigned mask) {
-  unsigned v;
-  do { v = apg::pcg64_next32(g) & mask; } while (v > max);
-  return v;
-}
-
-// direction order of one cell: numpy's Generator.permutation on a 4-row array = shuffle(arange(4)); 2 bits per entry
-__device__ __forceinline__ unsigned draw_order(apg::Pcg64& g) {
-  unsigned o[4] = {0u, 1u, 2u, 3u};
-  {
-    const unsigned j = interval(g, 3u, 3u);
-    const unsigned t = o[3]; o[3] = o[j]; o[j] = t;
-  }
-  {
-    const unsigned j = interval(g, 2u, 3u);
-    const unsigned t = o[2]; o[2] = o[j]; o[j] = t;
-  }
-  {
-    const unsigned j = interval(g, 1u, 1u);
-    const unsigned t = o[1]; o[1] = o[j]; o[j] = t;
-  }
-  return o[0] | (o[1] << 2) | (o[2] << 4) | (o[3] << 6);
-}
-
-// frame: x (bits 0-7) | y (8-15) | order (16-23) | next direction slot k (24-26) | first (27)
 __global__ void maze_kernel(const unsigned long long* __restrict__ idx, int n, int W, int H, double branching_prob,
                             unsigned* __restrict__ bits, unsigned* __restrict__ stack, int cells) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
   const int words = (W + 31) >> 5;
-  unsigned* b = bits + (size_t)m * H * words;
-  for (int y = 0; y < H; ++y)
-    for (int w = 0; w < words; ++w) {
-      const int nb = min(32, W - w * 32);
-      b[y * words + w] = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);  // all walls
-    }
-  apg::Pcg64 g;
-  apg::pcg64_seed(g, idx[m]);
-  unsigned* st = stack + (size_t)m * cells;
-  b[1 * words] &= ~(1u << 1);  // starting cell (1, 1)
-  int sp = 0;
-  st[0] = 1u | (1u << 8) | (draw_order(g) << 16) | (1u << 27);
-  const int dxs[4] = {2, -2, 0, 0}, dys[4] = {0, 0, 2, -2};
-  while (sp >= 0) {
-    unsigned fr = st[sp];
-    const unsigned k = (fr >> 24) & 7u;
-    if (k == 4u) {
-      --sp;
-      continue;
-    }
-    const int x = fr & 0xff, y = (fr >> 8) & 0xff;
-    const unsigned d = (fr >> (16 + 2 * k)) & 3u;
-    fr += 1u << 24;
-    const int nx = x + dxs[d], ny = y + dys[d];
-    bool push = false;
-    if (nx > 0 && nx < W - 1 && ny > 0 && ny < H - 1 && ((b[ny * words + (nx >> 5)] >> (nx & 31)) & 1u)) {
-      const bool first = (fr >> 27) & 1u;
-      // `first or rng.random() < branching_prob`: the draw only happens when `first` is False
-      if (first || ((double)(apg::pcg64_next64(g) >> 11) * (1.0 / 9007199254740992.0)) < branching_prob) {
-        const int ix = x + dxs[d] / 2, iy = y + dys[d] / 2;
-        b[iy * words + (ix >> 5)] &= ~(1u << (ix & 31));
-        b[ny * words + (nx >> 5)] &= ~(1u << (nx & 31));
-        fr &= ~(1u << 27);
-        push = true;
-      }
-    }
-    st[sp] = fr;
-    if (push) {
-      ++sp;
-      st[sp] = (unsigned)nx | ((unsigned)ny << 8) | (draw_order(g) << 16) | (1u << 27);
-    }
-  }
+  apg_maze::generate(idx[m], W, H, branching_prob, bits + (size_t)m * H * words, stack + (size_t)m * cells);
 }
 
 // one thread per rooms map (csrc/apg_rooms.cuh); scratch: two bit planes and the view stack per map

@@ -21,7 +21,7 @@
 namespace apg_rooms {
 
 constexpr int kMaxRooms = 16;   // max_rooms (sub-rooms of one split) supported
-constexpr int kMaxStack = 96;   // pending room views (depth-first; a 255 x 255 map needs far fewer)
+constexpr int kMaxStack = 64;   // pending room views (depth-first: <= (sub-rooms - 1) per level, a few levels deep)
 constexpr double kP = 0.3;
 
 // view(a, b) -> map(y0 + (tr ? b : a), x0 + (tr ? a : b)); shape (A, B); cap = max_rooms of the pending split

@@ -64,17 +64,21 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=34)
     ap.add_argument("--prime-ms", type=float, default=60.0, help="minimum device time of the untimed priming phase")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lidar-maps", default="bank", choices=["bank", "procedural"],
+                    help="LIDAR workloads: bank = a finite bank of reference-generated maps (tests/golden), procedural = "
+                         "the reference's datasets of len 2**32, every reset generates its map on the device")
     ap.add_argument("--blend", default="float64", choices=["float64", "float32"],
                     help="image workloads: float64 = the reference's blend arithmetic (bit-exact pixels, default); "
                          "float32 = opt-in blend within the 1e-5 relative bar")
     return ap.parse_args()
 
 
-def workload_config(name: str, n: int, world: int, blend: str | None):
+def workload_config(name: str, n: int, world: int, blend: str | None, lidar_maps: str = "bank"):
     """The `config` object of a line -- the SAME keys in the GPU arm and in the reference arm."""
     w = WORKLOADS[name]
     return {"workload": w["desc"], "name": name, "num_envs_per_gpu": n, "global_num_envs": world * n,
-            "sharding": f"env-index x{world}", "blend": None if name in LIDAR else blend}
+            "sharding": f"env-index x{world}", "blend": None if name in LIDAR else blend,
+            "maps": lidar_maps if name in LIDAR else None}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -267,7 +271,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": 1e3 * wall / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(name, args.envs or w["n_envs"], int(os.environ.get("WORLD_SIZE", "1")), args.blend),
+        "config": workload_config(name, args.envs or w["n_envs"], int(os.environ.get("WORLD_SIZE", "1")), args.blend,
+                                  args.lidar_maps),
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
@@ -289,7 +294,11 @@ def build_env(name, args, rank, world, device):
         pw = 10
     elif name in LIDAR:
         fname, beams = LIDAR[name]
-        bank = apg.FloorMapBank.load_npz(os.path.join(GOLDEN, fname), args.bank or None)
+        if args.lidar_maps == "procedural":  # the reference's datasets of len 2**32: maps generated on the device per reset
+            bank = apg.FloorMapDatasetRooms(device=device) if name == "lidar_rooms" else \
+                apg.FloorMapDatasetMaze(63, 63, device=device)
+        else:
+            bank = apg.FloorMapBank.load_npz(os.path.join(GOLDEN, fname), args.bank or None)
         env = apg.LIDARLocalization2DVectorEnv(n, bank, lidar_beam_count=beams, device=device, env_offset=rank * n,
                                                check_errors="never")
         pw = 2
@@ -514,7 +523,7 @@ def run_workload(name, args, rank, world, local_rank, dist, sampler, peaks):
     res = {
         "value": value, "unit": "env-steps/s", "steps": K, "warmup": W, "ms_per_step": ms_max / K,
         "per_rank_ms": per_rank_ms, "primed_steps": prime_steps,
-        "config": workload_config(name, n, world, args.blend),
+        "config": workload_config(name, n, world, args.blend, args.lidar_maps),
         "timing": {"explicit_reset_s": round(reset_s, 3),
                    "l2": "per-step inputs come from a pool of %d distinct steps streamed from HBM (%.0f MB > 126 MB L2, "
                          "walked cyclically); engine-owned observation buffers are rewritten every step" %

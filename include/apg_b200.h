@@ -39,6 +39,11 @@ typedef enum {
 #define APG_FLAG_NAN_ACTION 1u
 #define APG_FLAG_NAN_PRED 2u
 #define APG_FLAG_OUT_OF_GRID 4u
+#define APG_FLAG_MAPGEN 8u /* a procedural map exceeded the generator's limits (the reference raises for such parameters) */
+
+/* procedural map datasets of apg_lidar_set_map_generator */
+#define APG_MAPGEN_ROOMS 1 /* FloorMapDatasetRooms(width, height, max_rooms, door_width) */
+#define APG_MAPGEN_MAZE 2  /* FloorMapDatasetMaze(width, height, branching_prob) */
 
 int apg_version(void);
 const char* apg_last_error(void);
@@ -274,6 +279,16 @@ int apg_lidar_set_stream(apg_lidar_env* env, void* cuda_stream);
 /* Upload the bit-packed occupancy bank: h_bits (n_maps, H, ceil(W/32)) uint32, bit x&31 of word x>>5 = wall.
  * Replaces the per-episode dataset fetch + shapely union (lidar_localization2d.py:279-291,298). */
 int apg_lidar_set_map_bank(apg_lidar_env* env, const uint32_t* h_bits, int64_t n_maps);
+/* Procedural-dataset mode, the alternative to a finite bank: the reference's datasets FloorMapDatasetRooms /
+ * FloorMapDatasetMaze have len == 2**32 and every (auto)reset fetches dataset[integers(0, 2**32)] drawn from the
+ * environment's own DatasetIterator stream (lidar_localization2d.py:297-298,547-557; dataset_iterator.py:27-32).  With a
+ * generator set, each step compacts the environments that reset, draws their dataset indices from the per-environment
+ * device streams and generates those maps on the device (csrc/apg_rooms.cuh, csrc/apg_maze.cuh: bit-identical to the
+ * reference's generators) into per-environment map slots before the step kernel runs; info["map_idx"] is the dataset
+ * index.  kind: APG_MAPGEN_ROOMS (max_rooms, door_width) or APG_MAPGEN_MAZE (branching_prob); width / height come from
+ * the env's cfg.  Not with static_map (generate the one map with apg_maps_generate_* and upload it as a bank). */
+int apg_lidar_set_map_generator(apg_lidar_env* env, int32_t kind, int32_t max_rooms, int32_t door_width,
+                                double branching_prob);
 /* Upload lidar_directions (B,2) float32 = (cos, sin)(linspace(-pi, pi, B, endpoint=False)) * range, computed by
  * the caller exactly like lidar_localization2d.py:180-187 (numpy float32 cos/sin). */
 int apg_lidar_set_beams(apg_lidar_env* env, const float* h_dirs);

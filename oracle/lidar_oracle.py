@@ -68,13 +68,24 @@ def scan(bits: np.ndarray, W: int, H: int, pos: np.ndarray, targets: np.ndarray)
 
 
 class LidarVecOracle:
-    def __init__(self, maps: np.ndarray, num_envs: int, beam_count: int = 8, lidar_range: float = 5,
-                 step_limit: int = 100, static_map: bool = False, static_map_index: int = 0):
-        self.maps = np.asarray(maps, dtype=bool)
-        self.M, self.H, self.W = self.maps.shape
-        self.bank = pack_maps(self.maps)
-        self.words = self.bank.shape[-1]
+    def __init__(self, maps: np.ndarray | None, num_envs: int, beam_count: int = 8, lidar_range: float = 5,
+                 step_limit: int = 100, static_map: bool = False, static_map_index: int = 0, dataset_fn=None,
+                 map_shape: tuple[int, int] | None = None):
+        """`maps`: a finite bank (M,H,W), or None with `dataset_fn(idx) -> (H,W) bool` and `map_shape=(H,W)`: the
+        reference's procedural datasets of len 2**32 (every reset fetches dataset[integers(0, 2**32)],
+        dataset_iterator.py:27-32); each environment then owns its current map."""
         self.N = int(num_envs)
+        self.dataset_fn = dataset_fn
+        if dataset_fn is not None:
+            self.H, self.W = map_shape
+            self.M = 2 ** 32
+            self.maps = np.zeros((self.N, self.H, self.W), dtype=bool)   # per-environment current maps
+            self.bank = pack_maps(self.maps)
+        else:
+            self.maps = np.asarray(maps, dtype=bool)
+            self.M, self.H, self.W = self.maps.shape
+            self.bank = pack_maps(self.maps)
+        self.words = self.bank.shape[-1]
         self.B = int(beam_count)
         self.range = float(lidar_range)
         self.T = int(step_limit)
@@ -101,7 +112,12 @@ class LidarVecOracle:
             self.map_idx[i] = self.g2[i].integers(0, self.M)
         else:
             self.map_idx[i] = self.static_idx
-        m = self.maps[self.map_idx[i]]
+        if self.dataset_fn is not None:
+            self.maps[i] = self.dataset_fn(int(self.map_idx[i]))
+            self.bank[i] = pack_maps(self.maps[i][None])[0]
+            m = self.maps[i]
+        else:
+            m = self.maps[self.map_idx[i]]
         rows, cols = np.where(m == 0)
         k = self.g0[i].integers(0, len(rows))
         self.pos[i] = np.array([cols[k], rows[k]], dtype=np.float32) + 0.5
@@ -109,15 +125,19 @@ class LidarVecOracle:
         self.aliased[i] = 1
         self.elapsed[i] = 0
 
+    def _c_idx(self):
+        """bank rows of the environments for the C batch calls"""
+        return np.arange(self.N, dtype=np.int64) if self.dataset_fn is not None else self.map_idx
+
     def _obs_dict(self):
         obs = {"lidar": self.lidar.copy(), "odometry": self.odo.copy()}
         if not self.static:
-            obs["map"] = (self.maps[self.map_idx][..., None].astype(np.float32) / 255)
+            obs["map"] = (self.maps[self._c_idx()][..., None].astype(np.float32) / 255)
         obs["time_step"] = (2.0 * self.elapsed / self.T - 1.0).astype(np.float32)
         return obs
 
     def _scan_obs(self, mask):
-        _l().apg_oracle_obs_batch(_p(self.bank), self.W, self.H, self.words, _p(self.map_idx), self.N,
+        _l().apg_oracle_obs_batch(_p(self.bank), self.W, self.H, self.words, _p(self._c_idx()), self.N,
                                   _p(mask.astype(np.uint8)), _p(self.pos), _p(self.init), _p(self.dirs), self.B,
                                   C.c_float(self.range), _p(self.lidar), _p(self.odo), _p(self.cells), _p(self.dists))
 
@@ -146,7 +166,7 @@ class LidarVecOracle:
         oob = np.zeros(N, np.uint8)
         for i in np.nonzero(self.autoreset)[0]:
             self._reset_env(i)
-        _l().apg_oracle_step_batch(_p(self.bank), self.W, self.H, self.words, _p(self.map_idx), N,
+        _l().apg_oracle_step_batch(_p(self.bank), self.W, self.H, self.words, _p(self._c_idx()), N,
                                    _p(stepped.astype(np.uint8)), _p(self.pos), _p(self.init), _p(self.aliased),
                                    _p(action), _p(prediction), _p(self.dirs), self.B, C.c_float(self.range),
                                    _p(self.lidar), _p(self.odo), _p(self.cells), _p(self.dists), _p(target), _p(base),

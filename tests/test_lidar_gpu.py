@@ -256,3 +256,50 @@ def test_host_step_chunks_and_mapped_outputs():
     for s in range(6):
         for x, y in zip(results[0][s], results[1][s]):
             assert np.array_equal(x, y), f"step {s}"
+
+
+@pytest.mark.parametrize("kind,B,N,steps", [("rooms", 64, 384, 208), ("maze", 12, 256, 104)])
+def test_procedural_dataset_mode_matches_oracle(kind, B, N, steps):
+    """Procedural-dataset mode (apg_lidar_set_map_generator): every (auto)reset draws dataset[integers(0, 2**32)] from the
+    env's DatasetIterator stream and generates the map on the device.  Against the oracle in dataset mode (pinned to the
+    live reference's LIDARLocRooms-v0 / LIDARLocMaze-v0 in tests/test_oracle_lidar.py): dataset indices, map observations,
+    positions, scans, rewards across one or two autoresets; a shard with env_offset reproduces its slice."""
+    import ap_gym_b200 as apg
+    from oracle.floor_map_oracle import maze, rooms
+    from oracle.lidar_oracle import LidarVecOracle
+
+    if kind == "rooms":
+        ds, fn, H, W = apg.FloorMapDatasetRooms(), (lambda i: rooms(i, 32, 32)), 32, 32
+    else:
+        ds, fn, H, W = apg.FloorMapDatasetMaze(), (lambda i: maze(i, 21, 21)), 21, 21
+    oracle = LidarVecOracle(None, N, beam_count=B, dataset_fn=fn, map_shape=(H, W))
+    env = apg.LIDARLocalization2DVectorEnv(N, ds, lidar_beam_count=B, emit_cells=True, output="numpy", check_errors="step")
+    half = N // 2
+    shard = apg.LIDARLocalization2DVectorEnv(N - half, ds, lidar_beam_count=B, output="numpy", env_offset=half)
+    oo, oinfo = oracle.reset(seed=77)
+    eo, einfo = env.reset(seed=77)
+    so, sinfo = shard.reset(seed=77)
+    assert np.array_equal(einfo["map_idx"], oinfo["map_idx"]) and einfo["map_idx"].max() > 2**31
+    assert np.array_equal(sinfo["map_idx"], oinfo["map_idx"][half:])
+    assert np.array_equal(eo["map"], oo["map"]) and np.array_equal(eo["lidar"], oo["lidar"])
+    rng = np.random.default_rng(3)
+    heading = rng.uniform(-np.pi, np.pi, N)
+    for s in range(steps):
+        heading += rng.normal(0, 0.5, N)
+        speed = rng.uniform(0, 1.3, N)
+        a = (np.stack([np.cos(heading), np.sin(heading)], -1) * speed[:, None]).astype(np.float32)
+        p = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        oo, orw, ote, otr, oinf = oracle.step(a, p)
+        eo, erw, ete, etr, einf = env.step({"action": a, "prediction": p})
+        so, srw, ste, strc, sinf = shard.step({"action": a[half:], "prediction": p[half:]})
+        assert np.array_equal(einf["map_idx"], oinf["map_idx"]), f"step {s} dataset indices"
+        assert np.array_equal(_np(env.state()["pos"]), oracle.pos), f"step {s} pos"
+        keep = _beam_mask(B, ~einf["_base_reward"])
+        assert np.array_equal(eo["lidar"][keep], oo["lidar"][keep]), f"step {s} lidar"
+        assert np.array_equal(eo["map"], oo["map"]), f"step {s} map observation"
+        assert np.array_equal(eo["odometry"], oo["odometry"]) and np.array_equal(eo["time_step"], oo["time_step"])
+        assert np.array_equal(ete, ote) and np.array_equal(erw.astype(np.float64), orw)
+        assert np.array_equal(so["lidar"], eo["lidar"][half:]) and np.array_equal(srw, erw[half:])
+        assert np.array_equal(sinf["map_idx"], einf["map_idx"][half:])
+    env.close()
+    shard.close()

@@ -57,3 +57,48 @@ def test_scan_matches_reference_on_adversarial_rays():
             assert d[0] == g[f"dist{m}"][i] and np.array_equal(c[0], g[f"cells{m}"][i]), (
                 f"map {m} ray {i}: pos {pos[i]} -> {tgt[i]}: got {d[0]} {c[0]}, "
                 f"reference {g[f'dist{m}'][i]} {g[f'cells{m}'][i]}")
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("env_id,kind", [("LIDARLocRooms-v0", "rooms"), ("LIDARLocMaze-v0", "maze")])
+def test_procedural_dataset_mode_matches_live_reference(env_id, kind):
+    """The reference's own registration (FloorMapDatasetRooms() / FloorMapDatasetMaze(), len 2**32, per-episode
+    dataset[integers(0, 2**32)]) run unmodified under the test-only shims, against the oracle in dataset mode with the
+    iterative generators of oracle/floor_map_oracle.py: dataset indices, maps, positions, observations, rewards across an
+    autoreset."""
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle", "shim"))
+    sys.path.insert(0, "/root/reference")
+    import ap_gym
+
+    from oracle.floor_map_oracle import maze, rooms
+    from oracle.lidar_oracle import LidarVecOracle
+
+    sys.setrecursionlimit(20000)
+    N, steps, seed = 3, 104, 5
+    env = ap_gym.make_vec(env_id, num_envs=N)
+    B = env.single_observation_space["lidar"].shape[0]
+    H, W = env.single_observation_space["map"].shape[:2]
+    fn = (lambda i: rooms(i, W, H)) if kind == "rooms" else (lambda i: maze(i, W, H))
+    oracle = LidarVecOracle(None, N, beam_count=B, dataset_fn=fn, map_shape=(H, W))
+    ro, rinfo = env.reset(seed=seed)
+    oo, oinfo = oracle.reset(seed=seed)
+    assert np.array_equal(np.asarray(rinfo["map_idx"], dtype=np.int64), oinfo["map_idx"])
+    assert np.array_equal(ro["map"], oo["map"]) and np.array_equal(ro["lidar"], oo["lidar"])
+    rng = np.random.default_rng(1)
+    for s in range(steps):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        p = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        ro, rr, rte, rtr, rinfo = env.step({"action": a, "prediction": p})
+        oo, orw, ote, otr, oinf = oracle.step(a, p)
+        if "map_idx" in rinfo:  # only the environments that were reset by this step report it (gymnasium `_key` masks)
+            m = np.asarray(rinfo.get("_map_idx", np.ones(N, bool)), dtype=bool)
+            assert np.array_equal(np.asarray(rinfo["map_idx"], dtype=np.int64)[m], oinf["map_idx"][m]), f"step {s} indices"
+        for k in ("lidar", "odometry", "map", "time_step"):
+            assert np.array_equal(ro[k], oo[k]), f"step {s} {k}"
+        assert np.array_equal(rte, ote) and np.array_equal(rtr, otr)
+        assert np.allclose(rr, orw, rtol=0, atol=1e-7)
+    env.close()
