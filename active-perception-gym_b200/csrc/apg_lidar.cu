@@ -270,7 +270,10 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
 //   phase 4  the block writes the map observation of the environments that reset;
 //   phase 5  beams: a group of G = min(32, pow2 >= B) lanes owns one environment, lane l casts beams l, l+G, ...
 //            and stores coalesced runs of the lidar row.
-__global__ void __launch_bounds__(kThreads, 8) lidar_step_kernel(const LidarParams p) {
+#ifndef APG_LIDAR_MINB
+#define APG_LIDAR_MINB 8  // resident blocks per SM the register allocation aims at (64 registers per thread)
+#endif
+__global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(const LidarParams p) {
   extern __shared__ unsigned smem_maps[];  // kEnvsPerBlock x (prows * pw): padded bitmaps, see MapView
   __shared__ float s_posx[kEnvsPerBlock], s_posy[kEnvsPerBlock];
   __shared__ int s_midx[kEnvsPerBlock];

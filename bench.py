@@ -496,7 +496,7 @@ def run_workload(name, args, rank, world, local_rank, dist, sampler, peaks):
     else:
         kernel = {0: "image_head_kernel + image_step_kernel (staged tiles, warp blend)",
                   1: "image_step_kernel (staged tiles, thread blend)",
-                  3: "tma_head_kernel + tma_blend_kernel (TMA tiles, persistent warps)",
+                  3: "tma_step_kernel (TMA tiles, persistent warps, three environments per pass)",
                   4: "image_rollout_kernel (persistent thread-per-env rollout)"}.get(variant, str(variant))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": facts.get("dram_bytes_per_step"),
