@@ -149,7 +149,7 @@ APG_HD int generate(uint64_t index, int W, int H, int max_rooms, int door_width,
         for (int db = 0; db < door_width; ++db) {
           int a = w + da;
           if (a < 0) a += A;  // numpy's negative indices wrap
-          if (a >= A || doors[i] + db >= B) return 1;
+          if (a < 0 || a >= A || doors[i] + db >= B) return 1;  // numpy raises IndexError
           set_cell(door, words, v, a, doors[i] + db);
         }
     }

@@ -30,7 +30,7 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert sorted(d["config"]) == sorted(["workload", "name", "num_envs_per_gpu", "global_num_envs", "sharding", "blend"])
+    assert sorted(d["config"]) == sorted(["workload", "name", "num_envs_per_gpu", "global_num_envs", "sharding", "blend", "maps"])
     assert d["steps"] == 17 and d["warmup"] == 3
 
 
@@ -48,7 +48,7 @@ def test_gpu_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert len(d["per_rank_ms"]) == 1 and d["primed_steps"] >= 34
     assert "with_obs" in d["e2e"] and d["e2e"]["with_obs"]["value"] > 0
-    assert sorted(d["config"]) == sorted(["workload", "name", "num_envs_per_gpu", "global_num_envs", "sharding", "blend"])
+    assert sorted(d["config"]) == sorted(["workload", "name", "num_envs_per_gpu", "global_num_envs", "sharding", "blend", "maps"])
 
 
 @pytest.mark.gpu

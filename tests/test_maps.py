@@ -77,18 +77,29 @@ def test_iterative_rooms_oracle_matches_live_reference_other_parameters():
             assert np.array_equal(rooms(i, W, W, mr, dw), ds.get_data_point(i)), (W, mr, dw, i)
 
 
-def _rooms_host(idx, W, mr, dw, tmp_path):
+_ROOMS_LIB = {}
+
+
+def _rooms_lib(tmp_path):
     """csrc/apg_rooms.cuh (the code the kernel runs per thread) compiled with g++."""
     import ctypes as C
     import subprocess
 
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lib_path = str(tmp_path / "librooms_harness.so")
-    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
-                        os.path.join(root, "active-perception-gym_b200", "csrc"), "-o", lib_path,
-                        os.path.join(root, "tests", "native", "rooms_harness.cpp")], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    lib = C.CDLL(lib_path)
+    if "lib" not in _ROOMS_LIB:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        lib_path = str(tmp_path / "librooms_harness.so")
+        r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
+                            os.path.join(root, "active-perception-gym_b200", "csrc"), "-o", lib_path,
+                            os.path.join(root, "tests", "native", "rooms_harness.cpp")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        _ROOMS_LIB["lib"] = C.CDLL(lib_path)
+    return _ROOMS_LIB["lib"]
+
+
+def _rooms_host(idx, W, mr, dw, tmp_path):
+    import ctypes as C
+
+    lib = _rooms_lib(tmp_path)
     idx = np.ascontiguousarray(idx, dtype=np.uint64)
     out = np.zeros((len(idx), W, (W + 31) // 32), dtype=np.uint32)
     bad = lib.apg_rooms_host(idx.ctypes.data_as(C.c_void_p), C.c_longlong(len(idx)), W, W, mr, dw,
@@ -126,3 +137,32 @@ def test_device_rooms_generator_matches_oracle_other_parameters():
                            (96, 14, 2, [3])]:
         bank = apg.FloorMapBank.generate_rooms(idx, W, W, max_rooms=mr, door_width=dw)
         assert np.array_equal(bank.bits, _pack([rooms(i, W, W, mr, dw) for i in idx])), (W, mr, dw)
+
+
+def test_host_device_rooms_generator_property(tmp_path):
+    """hypothesis: random sizes / max_rooms / door widths / 64-bit indices -- the host/device generator equals the oracle,
+    and reports a failure exactly where the reference's arithmetic raises (numpy: low >= high for the door draw)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from oracle.floor_map_oracle import rooms
+
+    @settings(max_examples=60, deadline=None)
+    @given(W=st.integers(12, 72), mr=st.integers(1, 14), dw=st.integers(1, 5), idx=st.integers(0, 2**64 - 1))
+    def check(W, mr, dw, idx):
+        try:
+            want = rooms(idx, W, W, mr, dw)
+        except (ValueError, IndexError):
+            want = None
+        import ctypes as C
+
+        lib = _rooms_lib(tmp_path)
+        i = np.array([idx], dtype=np.uint64)
+        out = np.zeros((1, W, (W + 31) // 32), dtype=np.uint32)
+        bad = lib.apg_rooms_host(i.ctypes.data_as(C.c_void_p), C.c_longlong(1), W, W, mr, dw, out.ctypes.data_as(C.c_void_p))
+        if want is None:
+            assert bad == 1, (W, mr, dw, idx)
+        else:
+            assert bad == 0 and np.array_equal(out, _pack([want])), (W, mr, dw, idx)
+
+    check()
