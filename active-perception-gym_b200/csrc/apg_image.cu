@@ -1287,6 +1287,13 @@ int apg_image_create(const apg_image_cfg* cfg, apg_image_env** out) {
   if (const char* ov = getenv("APG_IMG_HOST_RNG")) e->host_rng = atoi(ov) != 0;
   if (const char* ov = getenv("APG_IMG_PDL")) e->pdl = atoi(ov) ? 1 : 0;
   if (const char* ov = getenv("APG_IMG_TOP_UP")) e->top_up = atoi(ov) != 0;
+  if (const char* ov = getenv("APG_L2_FETCH")) {  // experiment: L2 fetch granularity hint of the context (32 / 64 / 128 bytes)
+    size_t before = 0, after = 0;
+    cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(ov));
+    cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "apg: cudaLimitMaxL2FetchGranularity %zu -> %zu\n", before, after);
+  }
   if (err == cudaSuccess && !generic_only && e->thread_blend && apg_img::small_plan(e->small, *cfg, e->words))
     A(apg_img::small_preload(e->small));
   if (err == cudaSuccess && !generic_only && !e->thread_blend) {

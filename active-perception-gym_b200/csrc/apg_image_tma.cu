@@ -66,6 +66,11 @@ namespace {
 #ifndef APG_TMA_PREFETCH_IN
 #define APG_TMA_PREFETCH_IN 0  // 1: prefetch.global.L2 of the next step's action / prediction at the end of phase H
 #endif
+#ifndef APG_TMA_BLOCKED
+#define APG_TMA_BLOCKED 1  // 1: footprints come from the BLOCKED copy of the bank (8 rows x 16 bytes per 128-byte line) as 16-byte
+                           //    cp.async pieces: 6.75 DRAM lines per glimpse instead of 13.75 (-8 % time, DRAM reads halved)
+                           // 0: one tensor-map box per glimpse from the row-major bank (cp.async.bulk.tensor.2d)
+#endif
 #ifndef APG_TMA_STAGE_ROWS
 #define APG_TMA_STAGE_ROWS 10  // sensor rows staged in shared memory between two 128-bit copy-outs
 #endif
@@ -163,6 +168,13 @@ __device__ __forceinline__ void tma_load_2d_hint(unsigned dst, const CUtensorMap
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(x), "r"(y), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void ldgsts16_hint(unsigned dst, const void* src, unsigned long long policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
+}
+// the barrier receives one arrival from this thread once all its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ unsigned long long policy_evict_first() {
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -252,7 +264,7 @@ template <int S0, int S1, int C, int IH, int IW>
 __global__ void __launch_bounds__(kWarps * 32, APG_TMA_MINB)
 tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1,
                 const __grid_constant__ CUtensorMap tmap2, const TableT* __restrict__ g_table, const int group_size,
-                const int n_groups, const RolloutPlan ro) {
+                const int n_groups, const int bank_rows, const unsigned char* __restrict__ bank_blk, const RolloutPlan ro) {
   using Gm = Geom<S0, S1, C>;
   extern __shared__ __align__(128) unsigned char smem[];
   TableT* table = reinterpret_cast<TableT*>(smem);
@@ -269,8 +281,8 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   // barriers, then the conversion table arrives with one bulk copy
   if (tid == 0) mbar_init(tbar, 1);
   if (lane == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[0], APG_TMA_BLOCKED ? 32 : 1);
+    mbar_init(&mbar[1], APG_TMA_BLOCKED ? 32 : 1);
   }
   if (tid < 6) s_stats[tid] = 0.0;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -289,6 +301,13 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   float* stage = reinterpret_cast<float*>(wbase + Gm::OFF_STAGE);
   // lane q < E issues the tensor-map copy of slot q of a pass (its own map: box height + q rows under row shift)
   const unsigned my_tile_u = smem_u32(wbase) + min(lane, Gm::E - 1) * Gm::TILE_STRIDE;
+#if APG_TMA_BLOCKED
+  constexpr int kPPR = Gm::BOX_W / 16;                            // 16-byte pieces per footprint row
+  constexpr int kTailItems = (Gm::E * Gm::BOX_H - 32) * kPPR;     // pieces of the (slot, row) pairs past the 32nd
+  static_assert(Gm::E * Gm::BOX_H >= 32 && kTailItems <= 32, "lane = (slot, row) pair, the tail piece by piece");
+  const int iq = lane / Gm::BOX_H, ir = lane - iq * Gm::BOX_H;
+  const int last_row = bank_rows - 1, ppr_bank = p.bank_pitch >> 4, last_pc = ppr_bank - 1;
+#endif
   const TableT* tab = table + (lane & (kReplicas - 1));
   // sensor_scale == 1 on this path (tma_plan): tap coordinate t of an axis = centre + (t - (S-1)/2), the offsets are
   // compile-time constants for the rows and one register per lane for its column
@@ -340,6 +359,36 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
       // (lane q issues the copy of slot q: the whole warp calls this; the transaction count is posted first, a copy that
       //  completes before it only drives the count negative while the arrival is still pending)
       auto issue_pass = [&](int st, int first, int nn) {
+#if APG_TMA_BLOCKED
+        // blocked bank (tma_encode): the 16-byte piece pc of bank row `row` lives at ((row / 8) * pieces_per_row + pc) * 128
+        // + (row % 8) * 16, i.e. a 128-byte line holds 8 rows x 16 bytes.  DRAM fills whole 128-byte lines (measured:
+        // tools/micro/gather_granularity.py); a footprint of 11 rows x 48 bytes touches 6.75 lines of this layout on
+        // average instead of 13.75 lines of a row-major bank.  Lane l < 32 copies the PPR pieces of (slot, row) pair l
+        // (iq, ir: per-lane constants), the pairs past 32 are spread over the first lanes piece by piece.  Slot q's
+        // rows land q rows down in its tile (the bank spread of the row shift without fetching extra rows).  Rows /
+        // pieces past the bank are clamped: they are only ever read with weight 0.
+        const unsigned tile_st = tiles_u + st * (Gm::E * Gm::TILE_STRIDE);
+        const unsigned long long pol = policy_evict_first();
+        if (iq < nn) {
+          const int2 xy = reinterpret_cast<const int2*>(hdrs + first + iq)[2];
+          const int row = min(xy.x + ir, last_row), pc0 = xy.y >> 4;
+          const unsigned char* src = bank_blk + ((size_t)(row >> 3) * ppr_bank + pc0) * 128 + (row & 7) * 16;
+          const unsigned dst = tile_st + iq * Gm::TILE_STRIDE + (kRowShift * iq + ir) * Gm::BOX_W;
+#pragma unroll
+          for (int piece = 0; piece < kPPR; ++piece) ldgsts16_hint(dst + piece * 16, src + min(piece, last_pc - pc0) * 128, pol);
+        }
+        if (lane < kTailItems) {
+          const int pair = 32 + lane / kPPR, piece = lane - (lane / kPPR) * kPPR;
+          const int q = pair / Gm::BOX_H, r = pair - q * Gm::BOX_H;
+          if (q < nn) {
+            const int2 xy = reinterpret_cast<const int2*>(hdrs + first + q)[2];
+            const int row = min(xy.x + r, last_row), pc = min((xy.y >> 4) + piece, last_pc);
+            ldgsts16_hint(tile_st + q * Gm::TILE_STRIDE + (kRowShift * q + r) * Gm::BOX_W + piece * 16,
+                          bank_blk + ((size_t)(row >> 3) * ppr_bank + pc) * 128 + (row & 7) * 16, pol);
+          }
+        }
+        cp_async_arrive_noinc(mbar_u + 8 * st);  // one arrival per lane once its pieces have landed (barrier count 32)
+#else
         if (lane == 0) mbar_expect_tx_u(mbar_u + 8 * st, nn * Gm::TILE_BYTES + kRowShift * Gm::BOX_W * ((nn * (nn - 1)) >> 1));
         if (lane < nn) {
           const int2 xy = reinterpret_cast<const int2*>(hdrs + first + lane)[2];
@@ -347,6 +396,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
           tma_load_2d_hint(my_tile_u + st * (Gm::E * Gm::TILE_STRIDE), my_map, xy.y, xy.x - kRowShift * lane, mbar_u + 8 * st,
                            policy_evict_first());
         }
+#endif
       };
       // ---------------------------------------------------------------- phase H: lane = environment
       // move -> header -> (the tiles of the first pass are requested: lane q reads the header it has just written) -> loss,
@@ -537,6 +587,17 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
   }
 }
 
+// row-major bank (pitch a multiple of 16, rows a multiple of 8) -> blocked copy: one thread per 16-byte piece
+__global__ void bank_to_blocked_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long rows, int ppr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // destination piece index
+  if (i >= rows * ppr) return;
+  const long long blk = i >> 3;          // (row / 8) * ppr + pc
+  const int rr = (int)(i & 7);
+  const long long br = blk / ppr;
+  const int pc = (int)(blk - br * ppr);
+  dst[i] = src[(br * 8 + rr) * ppr + pc];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -591,6 +652,8 @@ bool tma_plan(TmaPlan& plan, const apg_image_cfg& cfg, int bank_pitch, int words
 void tma_release(TmaPlan& plan) {
   if (plan.d_table) cudaFree(plan.d_table);
   plan.d_table = nullptr;
+  if (plan.d_bank_blk) cudaFree(plan.d_bank_blk);
+  plan.d_bank_blk = nullptr;
 }
 
 bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_items, int height) {
@@ -604,6 +667,20 @@ bool tma_encode(TmaPlan& plan, const void* d_bank, int bank_pitch, long long n_i
   // no L2 promotion: the copies are random 2-sector reads, anything wider would be wasted DRAM traffic
   // (tmap[q]: the box of slot q of a pass, q rows taller -- row shift, see Geom)
   plan.have_map = true;
+  plan.bank_rows = (int)rows;
+#if APG_TMA_BLOCKED
+  if (plan.d_bank_blk) cudaFree(plan.d_bank_blk);
+  plan.d_bank_blk = nullptr;
+  if (rows % 8 != 0 || bank_pitch % 16 != 0) return plan.have_map = false;
+  if (cudaMalloc(&plan.d_bank_blk, (size_t)rows * bank_pitch) != cudaSuccess) return plan.have_map = false;
+  {
+    const int ppr = bank_pitch / 16;
+    const long long pieces = rows * ppr;
+    bank_to_blocked_kernel<<<(unsigned)((pieces + 255) / 256), 256>>>(static_cast<const uint4*>(d_bank),
+                                                                      static_cast<uint4*>(plan.d_bank_blk), rows, ppr);
+    if (cudaDeviceSynchronize() != cudaSuccess) return plan.have_map = false;
+  }
+#endif
   for (int q = 0; q < 3; ++q) {
     const cuuint32_t box[2] = {(cuuint32_t)plan.box_w, (cuuint32_t)(plan.box_h + kRowShift * q)};
     const CUresult r = encode_fn()(&plan.tmap[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(d_bank), dims, strides,
@@ -647,7 +724,7 @@ int tma_launch(const TmaPlan& plan, const ImgParams& p, const RolloutPlan& ro, c
   cfg.dynamicSmemBytes = plan.smem;
   const TableT* table = reinterpret_cast<const TableT*>(plan.d_table);
   cudaError_t e = cudaLaunchKernelEx(&cfg, tma_step_kernel<10, 10, 3, 64, 64>, p, plan.tmap[0], plan.tmap[1], plan.tmap[2], table,
-                                     gs, n_groups, ro);
+                                     gs, n_groups, plan.bank_rows, static_cast<const unsigned char*>(plan.d_bank_blk), ro);
   if (e != cudaSuccess) return -(int)e;
   return 1;
 }

@@ -18,6 +18,8 @@ struct TmaPlan {
   int box_w = 0, box_h = 0;
   CUtensorMap tmap[3]; // the bank as a (rows, row bytes) uint8 tensor, box = one glimpse footprint (+ q rows, slot q)
   bool have_map = false;
+  void* d_bank_blk = nullptr;   // blocked copy of the bank (8 rows x 16 bytes per 128-byte line), engine-owned
+  int bank_rows = 0;            // rows of the bank tensor (items x height): row-copy variant clamps to it
 };
 
 // geometry / device check + kernel attributes + persistent grid size; returns false when the shape is not covered

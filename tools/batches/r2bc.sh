@@ -1,0 +1,31 @@
+#!/usr/bin/env bash
+# round-2 batch bc: blocked bank layout (8 rows x 16 bytes per 128-byte line) + cp.async pieces vs the tensor-map box
+set -u
+O=gpurun_out
+mkdir -p $O
+B="python bench.py --only --warmup 5 --no-cpu-baseline --e2e-steps 4"
+for v in default t_blocked; do
+  if [ "$v" = "default" ]; then unset APG_B200_LIB; else export APG_B200_LIB=$PWD/build/variants/libapg_$v.so; fi
+  for rep in 1 2; do
+    $B --workload tinyloc --steps 200 > $O/r2bc_tiny_${v}_k200_$rep.json 2> $O/r2bc_tiny_${v}_k200_$rep.err
+    $B --workload tinyloc --steps 20 > $O/r2bc_tiny_${v}_k20_$rep.json 2> $O/r2bc_tiny_${v}_k20_$rep.err
+  done
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum,gpu__time_duration.sum \
+      --clock-control none -k regex:tma_step -s 4 -c 1 --csv --log-file $O/r2bc_ncu_${v}.csv \
+      $B --workload tinyloc --steps 20 --prime-ms 0 > /dev/null 2>&1
+  python -m pytest tests/test_image_gpu.py -m gpu -q -x -k "tiny or tma or loc" > $O/r2bc_pytest_$v.log 2>&1
+  tail -n 2 $O/r2bc_pytest_$v.log
+done
+unset APG_B200_LIB
+python - <<PY
+import json,glob,csv
+for f in sorted(glob.glob("$O/r2bc_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], round(d["ms_per_step"]*1e3,2), "us/step value %.3e"%d["value"], "flags", d.get("error_flags"))
+    except Exception as e:
+        print(f, "FAILED", e)
+for f in sorted(glob.glob("$O/r2bc_ncu_*.csv")):
+    rows=[r for r in csv.reader(open(f)) if len(r)>10]
+    print(f.split('/')[-1], [(r[-3],r[-1]) for r in rows[1:]])
+PY
