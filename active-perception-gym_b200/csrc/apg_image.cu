@@ -805,6 +805,7 @@ int launch(apg_image_env* e, int mode, const float* d_action, const float* d_pre
   if (persistent(e)) {  // explicit reset through the persistent kernels (steps go through rollout_window)
     apg_img::RolloutPlan ro{};
     ro.n_steps = 1; ro.t0 = 0; ro.need_reset0 = 0; ro.first_mode = 2;
+    ro.time_obs[0] = (float)((0.0 / (double)c.step_limit) * 2.0 - 1.0);
     ro.slot_idx[0] = reinterpret_cast<const long long*>(slot->d_idx); ro.slot_pos[0] = slot->d_pos;
     ro.slot_target[0] = slot->d_target; ro.slot_inv[0] = slot->d_inv;
     const int n = e->small.spec ? apg_img::small_launch(e->small, p, ro, e->stream) : apg_img::tma_launch(e->tma, p, ro, e->stream);
@@ -1028,6 +1029,7 @@ int rollout_window(apg_image_env* e, const float* d_actions, const float* d_pred
       } else {
         t++; need = t >= e->cfg.step_limit;
       }
+      ro.time_obs[m] = (float)(((double)t / (double)e->cfg.step_limit) * 2.0 - 1.0);  // t = the clock after step m
       m++;
     }
     while (e->ring_count < resets) {

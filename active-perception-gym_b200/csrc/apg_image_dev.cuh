@@ -115,6 +115,7 @@ struct RolloutPlan {
   int need_reset0;  // the first step is an autoreset step
   int first_mode;   // 2: the first (only) step is an explicit reset from slot 0
   unsigned char reset_slot[kRolloutMaxSteps];  // for autoreset steps: which payload slot below
+  float time_obs[kRolloutMaxSteps];            // obs["time_step"] after each step (host: the reference's float64 expression)
   const long long* slot_idx[kRolloutMaxSlots];
   const double* slot_pos[kRolloutMaxSlots];
   const float* slot_target[kRolloutMaxSlots];

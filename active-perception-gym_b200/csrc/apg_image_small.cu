@@ -110,6 +110,13 @@ __device__ __forceinline__ void warp_copy_async(unsigned char* dst, const unsign
   for (int q = done + lane * 4; q < bytes; q += 128) __pipeline_memcpy_async(dst + q, src + q, 4);
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// 16-byte cp.async (SASS LDGSTS.128) on a shared-window address; joins the thread's current cp.async group like
+// __pipeline_memcpy_async
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 struct SmallSmem {  // per-block layout of the dynamic shared memory
   int fp_stride;    // bytes per environment footprint slot: (S0+1) rows of the bank pitch + 16 (bank-conflict padding)
   int fp_bytes;     // per warp: 32 slots; the output staging (32 x P floats) aliases this area
@@ -131,7 +138,10 @@ __host__ __device__ inline SmallSmem small_smem(int S0, int P, int K, int H, int
 
 // PITCH = bytes per bank row (a multiple of 16); KC = number of classes when known at compile time (the loops over the
 // logits unroll and their exp chains overlap), 0 = p.K
-template <int S0, int S1, int PITCH, int KC>
+// FULL: every warp of the launch owns 32 live environments ((n1 - n0) % 64 == 0) -- no per-thread `live` predicates, and
+// the three warp-cooperative copies of a step (footprints in, next logits in, glimpses out) are unrolled with per-lane
+// constant offsets instead of index arithmetic per piece.
+template <int S0, int S1, int PITCH, int KC, bool FULL>
 __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const ImgParams p, const SmallRollout ro) {
   constexpr int P = S0 * S1;
   const int K = KC ? KC : p.K;
@@ -140,9 +150,9 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
   const SmallSmem sm = small_smem(S0, P, K, p.H, PITCH);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n0 + blockIdx.x * kSmallThreads + tid;  // [n0, n1): the environments this launch steps (n0 % 32 == 0)
-  const bool live = n < p.n1;
+  const bool live = FULL ? true : (n < p.n1);
   const int warp_env0 = p.n0 + blockIdx.x * kSmallThreads + warp * 32;
-  const int n_env = max(0, min(32, p.n1 - warp_env0));  // environments of this warp
+  const int n_env = FULL ? 32 : max(0, min(32, p.n1 - warp_env0));  // environments of this warp
   unsigned char* wbase = smem_raw + warp * sm.warp_bytes;
   unsigned char* s_fp = wbase;                                   // footprint slots of the warp's environments
   float* s_out = reinterpret_cast<float*>(wbase);                // ... reused as the output staging (32 x P floats)
@@ -154,6 +164,13 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
   const unsigned wmask = (p.W >= 32) ? 0xffffffffu : ((1u << p.W) - 1u);
   const int lg_words = sm.lg_bytes >> 2;
   constexpr int ch_per_env = (S0 + 1) * (PITCH >> 4);            // 16-byte pieces of one footprint (divisions by it fold)
+  constexpr int kFpStride = (S0 + 1) * PITCH + 16;               // == sm.fp_stride
+  // FULL copies: lane = (environment of a batch of 8, piece of a group of 4); an environment's ch_per_env pieces are
+  // contiguous in the bank ((S0+1) whole rows) and in its slot, so one source / destination address per batch serves
+  // its ch_per_env / 4 groups with immediate offsets
+  static_assert(!FULL || ch_per_env % 4 == 0, "groups of 4 pieces");
+  const unsigned fp_dst_u = smem_u32(s_fp) + (lane >> 2) * kFpStride + (lane & 3) * 16;
+  const bool lg_fast = FULL && KC > 0 && ((reinterpret_cast<uintptr_t>(p.pred) | ((size_t)p.N * KC * 4)) & 15) == 0;
 
   grid_dependency_wait(p.pdl);
 
@@ -183,18 +200,31 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
   // logits of the first step on their way (stage 0)
   const unsigned char* pred_w = reinterpret_cast<const unsigned char*>(p.pred + (size_t)warp_env0 * K);
   const size_t pred_step = (size_t)p.N * K * 4;
-  if (ro.first_mode != 2 && n_env > 0) warp_copy_async(reinterpret_cast<unsigned char*>(s_lg), pred_w, n_env * K * 4, lane);
+  // the warp's logits of one step: 32 * K floats, contiguous
+  auto copy_logits = [&](float* dst, const unsigned char* src) {
+    if (lg_fast) {
+      constexpr int n16 = (32 * KC * 4) / 16;
+      const unsigned d = smem_u32(dst) + lane * 16;
+#pragma unroll
+      for (int q = 0; q < n16; q += 32)
+        if (q + 32 <= n16 || q + lane < n16) cp_async16(d + q * 16, src + (q + lane) * 16);
+    } else if (n_env > 0) {
+      warp_copy_async(reinterpret_cast<unsigned char*>(dst), src, n_env * K * 4, lane);
+    }
+  };
+  if (ro.first_mode != 2) copy_logits(s_lg, pred_w);
   __pipeline_commit();
   __syncwarp();
   double st1 = 0.0, st2 = 0.0, st3 = 0.0, st4 = 0.0, st5 = 0.0, st0 = 0.0;  // this thread's share of the shard statistics
 
   int t = ro.t0;
   bool need_reset = ro.need_reset0 != 0;
-  const float2* act = reinterpret_cast<const float2*>(p.action) + n;
+  const float2* act = reinterpret_cast<const float2*>(p.action) + n;  // running pointers: + N per step
   // the action of step k + 1 is requested during step k (registers): its latency is off the step's critical path
   float2 act_next = make_float2(0.0f, 0.0f);
   const bool have_act = live && p.action != nullptr;  // (an explicit reset launches without actions)
   if (have_act && ro.n_steps > 0) act_next = __ldcs(act);
+  const unsigned char* pred_next = pred_w;
   float* rew2 = p.reward2 ? p.reward2 + n : nullptr;
   unsigned char* don2 = p.done2 ? p.done2 + n : nullptr;
   float* gout = p.glimpse + (size_t)warp_env0 * P;
@@ -204,13 +234,14 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     const int t_stamp = (mode == 0) ? t : 0;
     const int t_after = (mode == 0) ? t + 1 : 0;
     const bool terminated = (mode == 0) && (t_after >= p.T);
-    const float time_obs = (float)(((double)t_after / (double)p.T) * 2.0 - 1.0);
+    const float time_obs = ro.time_obs[k];
     const float* x = s_lg + (k & 1) * lg_words + lane * K;
 
     // ---- inputs of the step
     float a0 = 0.0f, a1 = 0.0f;
     const float2 aa = act_next;
-    if (have_act && k + 1 < ro.n_steps) act_next = __ldcs(act + (size_t)(k + 1) * p.N);
+    act += p.N;
+    if (have_act && k + 1 < ro.n_steps) act_next = __ldcs(act);
     if (live) {
       if (mode == 0) {
         a0 = aa.x; a1 = aa.y;
@@ -229,8 +260,9 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     if (live && mode == 0) {
       if (isnan(a0) || isnan(a1)) err |= APG_FLAG_NAN_ACTION;
       if (p.track) {
-        p.stamp_xy[(size_t)(t_stamp * 2 + 0) * p.N + n] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
-        p.stamp_xy[(size_t)(t_stamp * 2 + 1) * p.N + n] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
+        int* sxy = p.stamp_xy + ((size_t)(t_stamp * 2) * p.N + n);
+        sxy[0] = (int)rint((px * p.lim_x) * p.rs + p.half_wr);
+        sxy[p.N] = (int)rint((py * p.lim_y) * p.rs + p.half_hr);
       }
       const float m = norm2f(a0, a1);
       float q0 = a0, q1 = a1;
@@ -259,7 +291,16 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
 #if APG_SMALL_COOP
     {
       const int my_row = idx * p.H + rmin;  // first bank row of this thread's footprint
-      const int total = n_env * ch_per_env;
+      if (FULL) {
+#pragma unroll
+        for (int eb = 0; eb < 4; ++eb) {
+          const int row_e = __shfl_sync(0xffffffffu, my_row, eb * 8 + (lane >> 2));
+          const unsigned char* src = bank + (size_t)row_e * PITCH + (lane & 3) * 16;
+#pragma unroll
+          for (int g = 0; g < ch_per_env / 4; ++g) cp_async16(fp_dst_u + eb * 8 * kFpStride + g * 64, src + g * 64);
+        }
+      }
+      const int total = FULL ? 0 : n_env * ch_per_env;
       for (int q = lane; q < ((total + 31) & ~31); q += 32) {
         const int e = q / ch_per_env, c = q - e * ch_per_env;
         const int row_e = __shfl_sync(0xffffffffu, my_row, e & 31);
@@ -283,9 +324,8 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
 #endif
     // ---- next step's logits -> the other stage (they have the rest of the step to arrive); committed AFTER the
     // footprints so that waiting for the footprints does not wait for them
-    if (k + 1 < ro.n_steps && n_env > 0)
-      warp_copy_async(reinterpret_cast<unsigned char*>(s_lg + ((k + 1) & 1) * lg_words), pred_w + (size_t)(k + 1) * pred_step,
-                      n_env * K * 4, lane);
+    pred_next += pred_step;
+    if (k + 1 < ro.n_steps) copy_logits(s_lg + ((k + 1) & 1) * lg_words, pred_next);
     __pipeline_commit();
 
     // ---- label, cross-entropy, reward, flags (image_classification.py:113-127, loss_fn.py:100-110,212-220); the
@@ -325,8 +365,8 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
         p.reward[n] = reward_out;
         p.base_reward[n] = base;
         p.loss[n] = (float)loss_d;
-        if (rew2) rew2[(size_t)k * p.N] = reward_out;
-        if (don2) don2[(size_t)k * p.N] = terminated ? 1 : 0;
+        if (rew2) *rew2 = reward_out;
+        if (don2) *don2 = terminated ? 1 : 0;
         if (mode == 0) {  // overlay colour + episode statistics: real steps only
           if (p.track) p.stamp_q[(size_t)t_stamp * p.N + n] = fminf(fmaxf(pq, 0.0f), 1.0f);
           if (t_stamp == 0) { acc1 = 0.0f; acc2 = 0.0f; accr = 0.0f; fc = -1; lic = -1; }
@@ -409,7 +449,15 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     }
     // ---- the warp's 32 glimpses leave as one contiguous run of 128-bit stores
     __syncwarp();
-    if (n_env > 0) {
+    if (FULL) {
+      constexpr int n4 = (32 * P) / 4;
+      static_assert((32 * P) % 4 == 0, "whole float4s");
+      const float4* s4 = reinterpret_cast<const float4*>(s_out) + lane;
+      float4* g4 = reinterpret_cast<float4*>(gout) + lane;
+#pragma unroll
+      for (int q = 0; q < n4; q += 32)
+        if (q + 32 <= n4 || q + lane < n4) g4[q] = s4[q];
+    } else if (n_env > 0) {
       const int total = n_env * P;  // floats; the run starts 16-byte aligned (warp_env0 is a multiple of 32)
       const float4* s4 = reinterpret_cast<const float4*>(s_out);
       float4* g4 = reinterpret_cast<float4*>(gout);
@@ -420,6 +468,8 @@ __global__ void __launch_bounds__(kSmallThreads, 7) image_rollout_kernel(const I
     __syncwarp();
     t = t_after;
     need_reset = terminated;
+    if (rew2) rew2 += p.N;
+    if (don2) don2 += p.N;
   }
   __pipeline_wait_prior(0);
 
@@ -470,9 +520,11 @@ bool small_plan(SmallPlan& plan, const apg_image_cfg& cfg, int words) {
 cudaError_t small_preload(const SmallPlan& plan) {
   if (!plan.spec) return cudaSuccess;
   cudaFuncAttributes a;
-  cudaError_t e = cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 10>);
+  cudaError_t e = cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 10, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 10, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 0, true>);
   if (e != cudaSuccess) return e;
-  return cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 0>);
+  return cudaFuncGetAttributes(&a, image_rollout_kernel<5, 5, 32, 0, false>);
 }
 
 int small_launch(const SmallPlan& plan, const ImgParams& p, const SmallRollout& ro, cudaStream_t stream) {
@@ -486,8 +538,14 @@ int small_launch(const SmallPlan& plan, const ImgParams& p, const SmallRollout& 
   cfg.gridDim = dim3((unsigned)((p.n1 - p.n0 + kSmallThreads - 1) / kSmallThreads));
   cfg.blockDim = dim3(kSmallThreads);
   cfg.dynamicSmemBytes = plan.smem;
-  cudaError_t e = (p.K == 10) ? cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 10>, p, ro)
-                              : cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 0>, p, ro);
+  const bool full = (p.n1 - p.n0) % kSmallThreads == 0;
+  cudaError_t e;
+  if (p.K == 10)
+    e = full ? cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 10, true>, p, ro)
+             : cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 10, false>, p, ro);
+  else
+    e = full ? cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 0, true>, p, ro)
+             : cudaLaunchKernelEx(&cfg, image_rollout_kernel<5, 5, 32, 0, false>, p, ro);
   if (e != cudaSuccess) return -(int)e;
   return 1;
 }

@@ -337,7 +337,7 @@ tma_step_kernel(const ImgParams p, const __grid_constant__ CUtensorMap tmap, con
     c.t_stamp = (c.mode == 0) ? t : 0;
     const int t_after = (c.mode == 0) ? t + 1 : 0;
     c.terminated = ((c.mode == 0) && (t_after >= p.T)) ? 1 : 0;
-    c.time_obs = (float)(((double)t_after / (double)p.T) * 2.0 - 1.0);
+    c.time_obs = ro.time_obs[k];
     c.action = p.action + (size_t)k * p.N * 2;
     c.pred = p.pred + (size_t)k * p.N * ((p.task == APG_TASK_CLASSIFICATION) ? p.K : 2);
     {
