@@ -1555,13 +1555,14 @@ int apg_image_step_host(apg_image_env* e, const float* h_action, const float* h_
   for (int c = 0; c < chunks && rc == APG_OK; ++c) {
     const size_t lo = (size_t)c * per, hi = lo + per < N ? lo + per : N;
     if (lo >= hi) break;
+    // a single chunk has nothing to overlap with: its copies go on the step stream itself (no event, no cross-stream wait)
+    cudaStream_t cs = chunks == 1 ? e->stream : e->copy_stream;
     cudaError_t ce = cudaMemcpyAsync(e->d_in_action + lo * 2, h_action + lo * 2, (hi - lo) * 2 * sizeof(float),
-                                     cudaMemcpyHostToDevice, e->copy_stream);
+                                     cudaMemcpyHostToDevice, cs);
     if (ce == cudaSuccess)
-      ce = cudaMemcpyAsync(e->d_in_pred + lo * K, h_pred + lo * K, (hi - lo) * K * sizeof(float), cudaMemcpyHostToDevice,
-                           e->copy_stream);
-    if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_in[c], e->copy_stream);
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->stream, e->ev_in[c], 0);
+      ce = cudaMemcpyAsync(e->d_in_pred + lo * K, h_pred + lo * K, (hi - lo) * K * sizeof(float), cudaMemcpyHostToDevice, cs);
+    if (ce == cudaSuccess && chunks > 1) ce = cudaEventRecord(e->ev_in[c], e->copy_stream);
+    if (ce == cudaSuccess && chunks > 1) ce = cudaStreamWaitEvent(e->stream, e->ev_in[c], 0);
     if (ce != cudaSuccess) {
       rc = apg::fail(APG_ERR_CUDA, "apg_image_step_host: %s", cudaGetErrorString(ce));
       break;

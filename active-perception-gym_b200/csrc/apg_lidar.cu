@@ -38,6 +38,7 @@ struct LidarParams {
   int N, W, H, words, B, G, T, M;
   int n0, n1;          // environments [n0, n1) of the shard are stepped by this launch (n0 a multiple of 32)
   int pad, pw, prows;  // shared-memory maps carry a free border of `pad` cells: (H + 2 pad) rows of pw words
+  int pmw;             // words per padded map slot: prows * pw rounded up to a multiple of 4 (16-byte bulk copies)
   int static_map, static_idx, emit_cells, sparse;
   int filter;  // 1: beams are pre-filtered (apg_lidar_filter.cuh) and only the rays that may touch a wall are walked
   int fQ;                   // sub-cells per cell and axis of the swath-pattern table
@@ -47,6 +48,7 @@ struct LidarParams {
   unsigned long long seed;  // mode 2: env i is seeded with seed + env_offset + i
   long long env_offset;
   const unsigned* bank;     // (M, H, words)
+  const unsigned* bank_pad; // (M, pmw) the same maps in the padded shared-memory form (bank mode), or nullptr
   // procedural-dataset mode (apg_lidar_set_map_generator): every environment owns its current map, generated on the
   // device at its (auto)reset by lidar_mapgen_kernel BEFORE this kernel; map_idx then holds the dataset index (uint32)
   const unsigned* env_maps; // (N, H, words) or nullptr (bank mode)
@@ -95,6 +97,31 @@ struct MapView {
   const unsigned* bits;  // shared memory, (H + 2 pad) rows of pw words
   int pw, pad;
 };
+
+// mbarrier / bulk-copy helpers of the map staging (bank mode): one cp.async.bulk (SASS UBLKCP) per environment
+__device__ __forceinline__ unsigned lidar_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lidar_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lidar_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void lidar_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lidar_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lidar_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(lidar_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void lidar_bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lidar_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(lidar_smem_u32(bar))
+               : "memory");
+}
 
 __device__ __forceinline__ int is_wall(const MapView& m, int xp, int yp) {
   return (int)((m.bits[yp * m.pw + (xp >> 5)] >> (xp & 31)) & 1u);
@@ -274,7 +301,8 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
 #define APG_LIDAR_MINB 8  // resident blocks per SM the register allocation aims at (64 registers per thread)
 #endif
 __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(const LidarParams p) {
-  extern __shared__ unsigned smem_maps[];  // kEnvsPerBlock x (prows * pw): padded bitmaps, see MapView
+  extern __shared__ __align__(128) unsigned smem_maps[];  // kEnvsPerBlock x pmw: padded bitmaps, see MapView
+  __shared__ __align__(8) unsigned long long s_bar;     // bank mode: the bulk copies of the block's maps complete here
   __shared__ float s_posx[kEnvsPerBlock], s_posy[kEnvsPerBlock];
   __shared__ int s_midx[kEnvsPerBlock];
   __shared__ unsigned s_reset_mask;  // bit e: environment e of the block is reset by this step
@@ -284,7 +312,15 @@ __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(co
   const int env0 = p.n0 + blockIdx.x * kEnvsPerBlock;
   const int nE = min(kEnvsPerBlock, p.n1 - env0);
   const int mw = p.H * p.words;    // words of one bank map
-  const int pmw = p.prows * p.pw;  // words of one padded shared-memory map
+  const int pmw = p.pmw;           // words of one padded shared-memory map slot
+  // bank mode: the bank holds the maps in the padded form as well, an environment's map is ONE bulk copy issued by the
+  // lane that has just decided its map index (the first version re-padded 32 maps per block and step with funnel
+  // shifts: 178 of 1 550 warp-instructions per env-step)
+  const bool bulk = p.bank_pad != nullptr;
+  if (bulk && warp == 0) {
+    if (lane == 0) lidar_mbar_init(&s_bar, 1);
+    __syncwarp();
+  }
   const float Wf = (float)p.W, Hf = (float)p.H;
 
   // ---------------------------------------------------------------- phase 1
@@ -317,7 +353,9 @@ __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(co
       midx = p.map_idx[n];
     }
     s_midx[lane] = midx;
+    if (bulk) lidar_bulk_load(smem_maps + (size_t)lane * pmw, p.bank_pad + (size_t)midx * pmw, (unsigned)pmw * 4u, &s_bar);
   }
+  if (bulk && tid == 0) lidar_mbar_expect_tx(&s_bar, (unsigned)nE * (unsigned)pmw * 4u);
   if (p.gen_count && blockIdx.x == 0 && tid == 0) *p.gen_count = 0;
   if (warp == 0) {
     const unsigned rm = __ballot_sync(0xffffffffu, act && do_reset);
@@ -329,7 +367,8 @@ __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(co
   // padded word j of padded row yp holds the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad (pad <= 31)
   // (item = (environment, padded row): a warp stages 32 rows at a time, each lane walks the few words of its row --
   //  no integer divisions in the inner loop)
-  for (int e = warp; e < nE; e += kWarpsPerBlock) {
+  if (bulk) lidar_mbar_wait(&s_bar, 0);
+  for (int e = warp; e < (bulk ? 0 : nE); e += kWarpsPerBlock) {
     const unsigned* map = p.env_maps ? p.env_maps + (size_t)(env0 + e) * mw : p.bank + (size_t)s_midx[e] * mw;
     for (int yp = lane; yp < p.prows; yp += 32) {
       const int y = yp - p.pad;
@@ -661,6 +700,8 @@ struct apg_lidar_env {
   int words = 0, G = 0, pad = 0, pw = 0, prows = 0;
   size_t smem = 0;
   unsigned* d_bank = nullptr;
+  unsigned* d_bank_pad = nullptr;  // the bank in the padded shared-memory form, pmw words per map (set_map_bank)
+  int pmw = 0;
   int64_t n_maps = 0;
   float* d_dirs = nullptr;
   bool have_beams = false;
@@ -706,7 +747,8 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   const apg_lidar_cfg& c = e->cfg;
   LidarParams p{};
   p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
-  p.pad = e->pad; p.pw = e->pw; p.prows = e->prows;
+  p.pad = e->pad; p.pw = e->pw; p.prows = e->prows; p.pmw = e->pmw;
+  p.bank_pad = e->gen_kind ? nullptr : e->d_bank_pad;
   p.filter = (e->filter && e->filter_fits && e->d_ftable && c.beam_count <= kQueueCap) ? 1 : 0;
   p.fQ = kFilterQ; p.ftable = e->d_ftable;
   p.n0 = e->r0; p.n1 = e->r1 < 0 ? c.num_envs : e->r1;
@@ -793,7 +835,8 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out) {
   }
   e->pw = (cfg->width + 2 * e->pad + 31) / 32;
   e->prows = cfg->height + 2 * e->pad;
-  e->smem = (size_t)kEnvsPerBlock * e->prows * e->pw * sizeof(unsigned);
+  e->pmw = (e->prows * e->pw + 3) & ~3;
+  e->smem = (size_t)kEnvsPerBlock * e->pmw * sizeof(unsigned);
   if (e->smem > 200 * 1024) {
     delete e;
     return apg::fail(APG_ERR_INVALID, "map too large for the shared-memory bitmaps (%zu bytes per block)", e->smem);
@@ -850,6 +893,7 @@ void apg_lidar_destroy(apg_lidar_env* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   apg::dev_free(e->d_bank); apg::dev_free(e->d_dirs);
+  if (e->d_bank_pad) cudaFree(e->d_bank_pad);
   if (e->d_ftable) cudaFree(e->d_ftable);
   if (e->d_env_maps) cudaFree(e->d_env_maps);
   if (e->d_gen_scratch) cudaFree(e->d_gen_scratch);
@@ -904,6 +948,25 @@ int apg_lidar_set_map_bank(apg_lidar_env* e, const uint32_t* h_bits, int64_t n_m
   APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_bank), count * sizeof(uint32_t)));
   APG_CUDA(cudaMemcpy(e->d_bank, clean.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice));
   e->n_maps = n_maps;
+  {  // the padded form the step kernel stages with one bulk copy per environment: padded word j of padded row yp holds
+     // the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad, rows / bits outside the map are free
+    std::vector<uint32_t> padded((size_t)n_maps * e->pmw, 0u);
+    const int pad = e->pad;
+    for (int64_t m = 0; m < n_maps; ++m)
+      for (int y = 0; y < e->cfg.height; ++y) {
+        const uint32_t* row = clean.data() + ((size_t)m * e->cfg.height + y) * e->words;
+        uint32_t* dst = padded.data() + (size_t)m * e->pmw + (size_t)(y + pad) * e->pw;
+        uint32_t lo = 0u;
+        for (int j = 0; j < e->pw; ++j) {
+          const uint32_t hi = j < e->words ? row[j] : 0u;
+          dst[j] = (hi << pad) | (lo >> (32 - pad));
+          lo = hi;
+        }
+      }
+    if (e->d_bank_pad) { cudaFree(e->d_bank_pad); e->d_bank_pad = nullptr; }
+    APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_bank_pad), padded.size() * sizeof(uint32_t)));
+    APG_CUDA(cudaMemcpy(e->d_bank_pad, padded.data(), padded.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   // share of the free cells whose eight neighbours are free as well (first <= 256 maps): the beam filter's payoff
   {
     const int W = e->cfg.width, H = e->cfg.height;
