@@ -98,7 +98,7 @@ struct MapView {
   int pw, pad;
 };
 
-// mbarrier / bulk-copy helpers of the map staging (bank mode): one cp.async.bulk (SASS UBLKCP) per environment
+// mbarrier / bulk-copy helpers of the map staging: one cp.async.bulk (SASS UBLKCP) per environment
 __device__ __forceinline__ unsigned lidar_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void lidar_mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lidar_smem_u32(bar)), "r"(count) : "memory");
@@ -290,7 +290,8 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
 // A block owns kEnvsPerBlock = 32 consecutive environments.
 //   phase 1  warp 0, lane = environment: autoreset decision; resetting environments draw their map from the env's own
 //            numpy-compatible stream (SeedSequence/PCG64/Lemire, apg_rng.h);
-//   phase 2  all threads stage the 32 bit-packed maps in shared memory (coalesced);
+//   phase 2  the 32 padded bitmaps arrive in shared memory, one bulk copy (cp.async.bulk, mbarrier) per environment,
+//            issued in phase 1 by the lane that decided the map index;
 //   phase 3  warp 0, lane = environment: start-cell draw (reset) or pose integration + collision ray + wall-slide
 //            rays (step) -- 32 environments advance in parallel instead of one warp re-evaluating one environment's
 //            serial ray chain 32 times -- then loss, reward, TimeLimit, episode statistics, state write-back;
@@ -302,7 +303,7 @@ __device__ __forceinline__ unsigned count_free(const unsigned* bits, int W, int 
 #endif
 __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(const LidarParams p) {
   extern __shared__ __align__(128) unsigned smem_maps[];  // kEnvsPerBlock x pmw: padded bitmaps, see MapView
-  __shared__ __align__(8) unsigned long long s_bar;     // bank mode: the bulk copies of the block's maps complete here
+  __shared__ __align__(8) unsigned long long s_bar;     // the bulk copies of the block's maps complete here
   __shared__ float s_posx[kEnvsPerBlock], s_posy[kEnvsPerBlock];
   __shared__ int s_midx[kEnvsPerBlock];
   __shared__ unsigned s_reset_mask;  // bit e: environment e of the block is reset by this step
@@ -313,11 +314,10 @@ __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(co
   const int nE = min(kEnvsPerBlock, p.n1 - env0);
   const int mw = p.H * p.words;    // words of one bank map
   const int pmw = p.pmw;           // words of one padded shared-memory map slot
-  // bank mode: the bank holds the maps in the padded form as well, an environment's map is ONE bulk copy issued by the
+  // the maps are kept in the padded form as well (bank or per-environment slots): an environment's map is ONE bulk copy issued by the
   // lane that has just decided its map index (the first version re-padded 32 maps per block and step with funnel
   // shifts: 178 of 1 550 warp-instructions per env-step)
-  const bool bulk = p.bank_pad != nullptr;
-  if (bulk && warp == 0) {
+  if (warp == 0) {
     if (lane == 0) lidar_mbar_init(&s_bar, 1);
     __syncwarp();
   }
@@ -353,9 +353,10 @@ __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(co
       midx = p.map_idx[n];
     }
     s_midx[lane] = midx;
-    if (bulk) lidar_bulk_load(smem_maps + (size_t)lane * pmw, p.bank_pad + (size_t)midx * pmw, (unsigned)pmw * 4u, &s_bar);
+    lidar_bulk_load(smem_maps + (size_t)lane * pmw, p.bank_pad + (size_t)(p.env_maps ? n : midx) * pmw, (unsigned)pmw * 4u,
+                    &s_bar);
   }
-  if (bulk && tid == 0) lidar_mbar_expect_tx(&s_bar, (unsigned)nE * (unsigned)pmw * 4u);
+  if (tid == 0) lidar_mbar_expect_tx(&s_bar, (unsigned)nE * (unsigned)pmw * 4u);
   if (p.gen_count && blockIdx.x == 0 && tid == 0) *p.gen_count = 0;
   if (warp == 0) {
     const unsigned rm = __ballot_sync(0xffffffffu, act && do_reset);
@@ -363,31 +364,10 @@ __global__ void __launch_bounds__(kThreads, APG_LIDAR_MINB) lidar_step_kernel(co
   }
   __syncthreads();
 
-  // ---------------------------------------------------------------- phase 2: stage the maps
-  // padded word j of padded row yp holds the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad (pad <= 31)
-  // (item = (environment, padded row): a warp stages 32 rows at a time, each lane walks the few words of its row --
-  //  no integer divisions in the inner loop)
-  if (bulk) lidar_mbar_wait(&s_bar, 0);
-  for (int e = warp; e < (bulk ? 0 : nE); e += kWarpsPerBlock) {
-    const unsigned* map = p.env_maps ? p.env_maps + (size_t)(env0 + e) * mw : p.bank + (size_t)s_midx[e] * mw;
-    for (int yp = lane; yp < p.prows; yp += 32) {
-      const int y = yp - p.pad;
-      unsigned* dst = smem_maps + e * pmw + yp * p.pw;
-      if (y >= 0 && y < p.H) {
-        const unsigned* row = map + (size_t)y * p.words;
-        unsigned lo = 0u;
-        for (int j = 0; j < p.pw; ++j) {
-          const unsigned hi = (j < p.words) ? row[j] : 0u;
-          dst[j] = __funnelshift_l(lo, hi, p.pad);  // (hi << pad) | (lo >> (32 - pad))
-          lo = hi;
-        }
-      } else {
-        for (int j = 0; j < p.pw; ++j) dst[j] = 0u;
-      }
-    }
-  }
-  __syncthreads();
-
+  // ---------------------------------------------------------------- phase 2: the maps have landed
+  // (padded form: padded word j of padded row yp holds the map bits [32 j - pad, 32 j - pad + 32) of row yp - pad;
+  //  written once per map by apg_lidar_set_map_bank / lidar_mapgen_kernel, copied here by the bulk-copy engine)
+  lidar_mbar_wait(&s_bar, 0);
   // ---------------------------------------------------------------- phase 3: lane = environment
   if (act) {
     MapView mv{smem_maps + (size_t)lane * pmw, p.pw, p.pad};
@@ -634,6 +614,8 @@ struct MapGenParams {
   apg::Pcg64* g2;
   int* map_idx;
   unsigned* env_maps;
+  unsigned* env_maps_pad;  // (N, pmw): the same map in the padded form the step kernel stages (rows outside the map stay 0)
+  int pad, pw, pmw;
   const double* qn_table;
   int* list;
   int* count;
@@ -686,6 +668,16 @@ __global__ void lidar_mapgen_kernel(const MapGenParams p) {
     } else {
       apg_maze::generate(idx, p.W, p.H, p.branching_prob, out, scr);
     }
+    // ... and its padded form: padded word j of padded row y + pad holds the map bits [32 j - pad, 32 j - pad + 32)
+    unsigned* outp = p.env_maps_pad + (size_t)n * p.pmw + (size_t)p.pad * p.pw;
+    for (int y = 0; y < p.H; ++y) {
+      unsigned lo = 0u;
+      for (int j = 0; j < p.pw; ++j) {
+        const unsigned hi = (j < p.words) ? out[y * p.words + j] : 0u;
+        outp[y * p.pw + j] = __funnelshift_l(lo, hi, p.pad);
+        lo = hi;
+      }
+    }
   }
 }
 
@@ -701,6 +693,7 @@ struct apg_lidar_env {
   size_t smem = 0;
   unsigned* d_bank = nullptr;
   unsigned* d_bank_pad = nullptr;  // the bank in the padded shared-memory form, pmw words per map (set_map_bank)
+  unsigned* d_env_maps_pad = nullptr;  // procedural mode: (N, pmw) padded slots written by the map generator
   int pmw = 0;
   int64_t n_maps = 0;
   float* d_dirs = nullptr;
@@ -748,7 +741,7 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
   LidarParams p{};
   p.N = c.num_envs; p.W = c.width; p.H = c.height; p.words = e->words; p.B = c.beam_count; p.G = e->G;
   p.pad = e->pad; p.pw = e->pw; p.prows = e->prows; p.pmw = e->pmw;
-  p.bank_pad = e->gen_kind ? nullptr : e->d_bank_pad;
+  p.bank_pad = e->gen_kind ? e->d_env_maps_pad : e->d_bank_pad;  // procedural mode: one padded slot per environment
   p.filter = (e->filter && e->filter_fits && e->d_ftable && c.beam_count <= kQueueCap) ? 1 : 0;
   p.fQ = kFilterQ; p.ftable = e->d_ftable;
   p.n0 = e->r0; p.n1 = e->r1 < 0 ? c.num_envs : e->r1;
@@ -769,6 +762,7 @@ int lidar_launch(apg_lidar_env* e, int mode, uint64_t seed, const float* d_actio
     g.N = p.N; g.W = p.W; g.H = p.H; g.words = p.words; g.n0 = p.n0; g.n1 = p.n1; g.mode = mode; g.kind = e->gen_kind;
     g.max_rooms = e->gen_max_rooms; g.door_width = e->gen_door; g.maze_cells = e->gen_cells; g.branching_prob = e->gen_branch;
     g.seed = seed; g.env_offset = c.env_offset; g.prev_done = e->d_prev_done; g.g0 = e->d_g0; g.g2 = e->d_g2;
+    g.env_maps_pad = e->d_env_maps_pad; g.pad = e->pad; g.pw = e->pw; g.pmw = e->pmw;
     g.map_idx = e->d_map_idx; g.env_maps = e->d_env_maps; g.qn_table = e->d_qn; g.list = e->d_gen_list;
     g.count = e->d_gen_count; g.scratch = e->d_gen_scratch; g.scratch_words = e->gen_scratch_words; g.err = e->d_err;
     lidar_reset_list_kernel<<<apg::ceil_div(p.n1 - p.n0, 256), 256, 0, e->stream>>>(g);
@@ -894,6 +888,7 @@ void apg_lidar_destroy(apg_lidar_env* e) {
   cudaStreamSynchronize(e->stream);
   apg::dev_free(e->d_bank); apg::dev_free(e->d_dirs);
   if (e->d_bank_pad) cudaFree(e->d_bank_pad);
+  if (e->d_env_maps_pad) cudaFree(e->d_env_maps_pad);
   if (e->d_ftable) cudaFree(e->d_ftable);
   if (e->d_env_maps) cudaFree(e->d_env_maps);
   if (e->d_gen_scratch) cudaFree(e->d_gen_scratch);
@@ -1044,6 +1039,9 @@ int apg_lidar_set_map_generator(apg_lidar_env* e, int32_t kind, int32_t max_room
                              ? 2 * mw + (apg_rooms::kMaxStack * sizeof(apg_rooms::View) + 3) / 4
                              : (size_t)e->gen_cells;
   if (e->d_env_maps) { cudaFree(e->d_env_maps); e->d_env_maps = nullptr; }
+  if (e->d_env_maps_pad) { cudaFree(e->d_env_maps_pad); e->d_env_maps_pad = nullptr; }
+  APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_env_maps_pad), N * (size_t)e->pmw * sizeof(unsigned)));
+  APG_CUDA(cudaMemset(e->d_env_maps_pad, 0, N * (size_t)e->pmw * sizeof(unsigned)));
   if (e->d_gen_scratch) { cudaFree(e->d_gen_scratch); e->d_gen_scratch = nullptr; }
   APG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_env_maps), N * mw * sizeof(unsigned)));
   APG_CUDA(cudaMemset(e->d_env_maps, 0, N * mw * sizeof(unsigned)));
