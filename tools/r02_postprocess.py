@@ -91,7 +91,7 @@ def main():
             short = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.strip()[:110]
             lines.append(f"{short}\n    " + ", ".join(f"{k} x{v}" for k, v in sorted(c.items())))
     lines.append("")
-    lines.append("# excerpt: the tensor-map copy and the table bulk copy of tma_step_kernel")
+    lines.append("# excerpt: every bulk copy (UBLKCP global<->shared), tensor-map copy (UTMALDG, APG_TMA_BLOCKED=0 builds only) and mbarrier operation of the library")
     for ln in sass.splitlines():
         if "UTMALDG" in ln or "UBLKCP" in ln or "SYNCS.ARRIVE.TRANS64" in ln or "SYNCS.PHASECHK" in ln:
             lines.append(ln.rstrip()[:120])
