@@ -439,24 +439,35 @@ def run_workload(name, args, rank, world, local_rank, dist, sampler, peaks):
     # measured twice: reward / flags only, and with the observation (obs["glimpse"] / obs["lidar"]) copied back too
     Ke = args.e2e_steps
     obs_elems = n * (env._B if is_lidar else env._S0 * env._S1 * env._C)
-    h_a = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    h_p = torch.empty((n, pw), dtype=torch.float32).pin_memory()
+    # every step copies ITS OWN inputs: a pool of distinct page-locked host steps (taken from the device pool), walked
+    # cyclically -- one fixed action repeated every step would drive the LIDAR robots into the walls (a different,
+    # slower state distribution than the device-timed rollout's)
+    hp = min(16, pool)
+    h_as = [acts[i].cpu().pin_memory() for i in range(hp)]
+    h_ps = [preds[i].cpu().pin_memory() for i in range(hp)]
     h_r = torch.empty((n,), dtype=torch.float32).pin_memory()
     h_te = torch.empty((n,), dtype=torch.uint8).pin_memory()
     h_tr = torch.empty((n,), dtype=torch.uint8).pin_memory()
     h_obs = torch.empty((obs_elems,), dtype=torch.float32).pin_memory()
-    h_a.copy_(acts[0].cpu())
-    h_p.copy_(preds[0].cpu())
     step_host = lib.apg_lidar_step_host if is_lidar else lib.apg_image_step_host
+
+    e2e_cursor = [0]
 
     def e2e(with_obs):
         o = h_obs.data_ptr() if with_obs else None
+
+        def one():
+            i = e2e_cursor[0] % hp
+            e2e_cursor[0] += 1
+            _capi.check(step_host(env._h, h_as[i].data_ptr(), h_ps[i].data_ptr(), h_r.data_ptr(), h_te.data_ptr(),
+                                  h_tr.data_ptr(), o))
+
         for _ in range(5):
-            _capi.check(step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(), h_tr.data_ptr(), o))
+            one()
         barrier()
         t0 = time.perf_counter()
         for _ in range(Ke):
-            _capi.check(step_host(env._h, h_a.data_ptr(), h_p.data_ptr(), h_r.data_ptr(), h_te.data_ptr(), h_tr.data_ptr(), o))
+            one()
         barrier()
         t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
@@ -534,6 +545,7 @@ def run_workload(name, args, rank, world, local_rank, dist, sampler, peaks):
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": ("apg_lidar_step_host" if is_lidar else "apg_image_step_host") +
                        " (pinned host action/prediction in, reward/terminated/truncated out)",
+                "inputs": "%d distinct page-locked host steps walked cyclically (each step copies its own inputs)" % hp,
                 "with_obs": {"value": e2e_obs_value, "d2h_bytes_per_step": d2h + obs_elems * 4,
                              "what": "the same call with the observation (" + ("lidar" if is_lidar else "glimpse") +
                                      ") copied back to pinned host memory as well"}},
