@@ -160,9 +160,13 @@ cudaError_t payload_preload() {
 int launch_device_payload(const PayloadArgs& a, cudaStream_t stream) {
   const long long raws = (a.Ng + kPayloadSlack + 1) / 2 + 1;  // raw draws behind the g2 word stream
   const long long wthreads = (raws + kRawsPerThread - 1) / kRawsPerThread;
-  payload_words_kernel<<<(unsigned)((wthreads + 127) / 128), 128, 0, stream>>>(a);
+  // 64-thread blocks (<= 56 registers per thread: 3 584 registers per block): small enough to become resident NEXT TO a
+  // block of the persistent rollout kernels -- the TinyImageNetLoc kernel leaves 4 096 registers per SM, the 128- and
+  // 256-thread blocks of the first version could only start after the whole window had finished
+  constexpr int kPayloadThreads = 64;
+  payload_words_kernel<<<(unsigned)((wthreads + kPayloadThreads - 1) / kPayloadThreads), kPayloadThreads, 0, stream>>>(a);
   static_assert(kDrawsPerThread >= 2, "N threads must cover the 2N uniform draws");
-  payload_values_kernel<<<(unsigned)((a.N + 255) / 256) + 1, 256, 0, stream>>>(a);
+  payload_values_kernel<<<(unsigned)((a.N + kPayloadThreads - 1) / kPayloadThreads) + 1, kPayloadThreads, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -(int)e;
   return 2;
