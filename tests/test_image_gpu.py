@@ -124,6 +124,52 @@ def test_engine_matches_oracle_seeded_mnist_2048():
     env.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K", [(192, 4), (200, 4), (200, 10), (64, 7)])
+def test_rollout_kernel_instantiations_match_oracle(N, K):
+    """The four instantiations of the thread-per-environment kernel: class count 10 / runtime, whole warps only
+    (N % 64 == 0: unrolled cooperative copies) / ragged batch -- 36 steps (2 autoresets) of seeded inputs vs the oracle,
+    through step() and through one rollout window."""
+    import torch
+
+    from oracle.datasets import synthetic_u8_bank
+    from oracle.image_oracle import ImageEnvOracle
+    import ap_gym_b200 as apg
+
+    imgs, labels = synthetic_u8_bank(seed=3, M=512, H=28, W=28, C=1, K=K)
+    cfg = apg.ImagePerceptionConfig(dataset=apg.ArrayImageDataset(imgs, labels, K))
+    oracle = ImageEnvOracle(imgs, labels, N, task="cls", num_classes=K, track_overlay=False)
+    env = apg.ImageClassificationVectorEnv(N, cfg, output="numpy")
+    env2 = apg.ImageClassificationVectorEnv(N, cfg)
+    o0, _ = oracle.reset(seed=21)
+    e0, _ = env.reset(seed=21)
+    env2.reset(seed=21)
+    assert np.array_equal(e0["glimpse"], o0["glimpse"])
+    rng = np.random.default_rng(9)
+    S = 36
+    acts = (rng.uniform(-1, 1, (S, N, 2)) * 1.3).astype(np.float32)
+    preds = (rng.standard_normal((S, N, K)) * 4).astype(np.float32)
+    rew = np.zeros((S, N), np.float32)
+    for s in range(S):
+        oo, orw, ote, otr, oinf = oracle.step(acts[s], preds[s])
+        eo, erw, ete, etr, einf = env.step({"action": acts[s], "prediction": preds[s]})
+        for k in oo:
+            assert np.array_equal(eo[k], oo[k]), f"step {s} obs {k}"
+        assert np.array_equal(ete, ote) and np.array_equal(einf["prediction"]["target"], oinf["prediction"]["target"])
+        assert_close(erw, orw, RTOL, ATOL, f"step {s} reward")
+        rew[s] = erw
+    r2 = torch.empty((S, N), dtype=torch.float32, device="cuda")
+    d2 = torch.empty((S, N), dtype=torch.uint8, device="cuda")
+    env2.rollout(torch.from_numpy(acts).cuda(), torch.from_numpy(preds).cuda(), rewards=r2, dones=d2)
+    assert np.array_equal(r2.cpu().numpy(), rew)
+    o1 = env.step({"action": acts[0], "prediction": preds[0]})[0]
+    o2 = env2.step({"action": torch.from_numpy(acts[0]).cuda(), "prediction": torch.from_numpy(preds[0]).cuda()})[0]
+    for k in o1:
+        assert np.array_equal(o2[k].cpu().numpy(), o1[k]), k
+    env.close()
+    env2.close()
+
+
 @pytest.mark.parametrize("geom", [
     dict(H=64, W=64, C=1, sensor_size=(36, 36), sensor_scale=1.0),   # more sensor rows than lanes per env, 2 chunks
     dict(H=40, W=48, C=3, sensor_size=(14, 14), sensor_scale=1.0),   # wide sensor: 42 floats per row, two chunks
