@@ -136,7 +136,9 @@ int apg_image_set_stream(apg_image_env* env, void* cuda_stream);
 
 /* Upload (h_*) or adopt (d_*, on_device=1, caller keeps ownership and must keep it alive) the image bank:
  * n_items images of (H, W, C) in bank_dtype, and their int32 labels.
- * Replaces the per-reset `dataset.get_data_point_batch(idx)` gather (image_perception_module.py:123-129). */
+ * Replaces the per-reset `dataset.get_data_point_batch(idx)` gather (image_perception_module.py:123-129).
+ * For the 64x64x3 uint8 geometry the engine also builds a blocked copy of the bank here (8 rows x 16 bytes per 128-byte
+ * line, the layout its step kernel reads): an adopted bank is snapshotted, call this again after changing it. */
 int apg_image_set_bank(apg_image_env* env, const void* bank, const int32_t* labels, int64_t n_items, int on_device);
 
 /* Explicit reset: ImagePerceptionModule.reset() + (localization) the target assignment of
@@ -277,7 +279,9 @@ int apg_lidar_create(const apg_lidar_cfg* cfg, apg_lidar_env** out);
 void apg_lidar_destroy(apg_lidar_env* env);
 int apg_lidar_set_stream(apg_lidar_env* env, void* cuda_stream);
 /* Upload the bit-packed occupancy bank: h_bits (n_maps, H, ceil(W/32)) uint32, bit x&31 of word x>>5 = wall.
- * Replaces the per-episode dataset fetch + shapely union (lidar_localization2d.py:279-291,298). */
+ * Replaces the per-episode dataset fetch + shapely union (lidar_localization2d.py:279-291,298).
+ * The bank is kept a second time with a free border of max(ceil(lidar_range) + 2, 7) cells around every map -- the form
+ * the step kernel stages in shared memory with one bulk copy per environment. */
 int apg_lidar_set_map_bank(apg_lidar_env* env, const uint32_t* h_bits, int64_t n_maps);
 /* Procedural-dataset mode, the alternative to a finite bank: the reference's datasets FloorMapDatasetRooms /
  * FloorMapDatasetMaze have len == 2**32 and every (auto)reset fetches dataset[integers(0, 2**32)] drawn from the
