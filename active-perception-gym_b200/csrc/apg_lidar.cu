@@ -148,12 +148,21 @@ __device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px,
   int cx = ws.cx, cy = ws.cy, n_pos = ws.n_pos, n_zero = ws.n_zero;
   bool have_first = ws.have_first, in_iv = ws.in_iv;
   double iv_t0 = ws.iv_t0, fex = ws.fex, fey = ws.fey;
-  const double sxd = (double)sx, syd = (double)sy;
-  // next grid lines in MAP coordinates (exact integers)
-  double gx = (double)((sx > 0 ? cx + 1 : cx) - m.pad), gy = (double)((sy > 0 ? cy + 1 : cy) - m.pad);
-  double tX = sx != 0 ? (gx - px) * inv_dx : INFINITY;
-  double tY = sy != 0 ? (gy - py) * inv_dy : INFINITY;
+  // The next grid line of an axis follows from the current cell: g = c + (s > 0 ? 1 : 0) - pad in MAP coordinates, an
+  // exact integer, so both crossing parameters t = (g - p) * inv are simply recomputed from (cx, cy) in every iteration
+  // -- the same separately rounded operations on the same values as updating them only on the axis that stepped, but
+  // no loop-carried float64 state (ptxas turned the conditional updates into unconditional arithmetic + four FSEL +
+  // two moves per axis: 18 of ~60 instructions per crossing).  An axis the ray does not move along gets a grid line far
+  // to the right and inv = +inf: t = +inf without a select.
+  constexpr int kBias = 1 << 20;
+  const int offx = (sx != 0 ? (sx > 0 ? 1 : 0) - m.pad : (1 << 19)) + kBias;
+  const int offy = (sy != 0 ? (sy > 0 ? 1 : 0) - m.pad : (1 << 19)) + kBias;
+  const double invx = sx != 0 ? inv_dx : INFINITY, invy = sy != 0 ? inv_dy : INFINITY;
+  constexpr double kMagic = 4503599627370496.0 + (double)kBias;  // 2^52 + bias: (double)(k - bias) = hilo(0x43300000, k) - kMagic
   for (;;) {
+    const double gx = __hiloint2double(0x43300000, cx + offx) - kMagic;
+    const double gy = __hiloint2double(0x43300000, cy + offy) - kMagic;
+    const double tX = (gx - px) * invx, tY = (gy - py) * invy;
     const bool stepx = tX <= tY, stepy = tY <= tX;
     const double tN = stepx ? tX : tY;
     if (!(tN <= 1.0)) break;  // the segment ends inside the current cell
@@ -178,8 +187,6 @@ __device__ __forceinline__ void walk(const MapView& m, WalkState& ws, double px,
       }
     }
     cx = ncx; cy = ncy;
-    if (stepx) { gx += sxd; tX = (gx - px) * inv_dx; }
-    if (stepy) { gy += syd; tY = (gy - py) * inv_dy; }
   }
   if (in_iv) { if (iv_t0 < 1.0) n_pos++; else n_zero++; }
   ws.n_pos = n_pos; ws.n_zero = n_zero; ws.fex = fex; ws.fey = fey;
